@@ -1,0 +1,221 @@
+// qk_playout_core.cuh -- one ply of a uniform-random Quantik playout on an
+// INCREMENTAL state, plus the Philox4x32-10 counter stream that drives it.
+//
+// Restates, per ply, the loop body shared by BeamSearchEngine._rollout
+// (beam_search.py:624-645) and MCTSEngine._simulate (mcts.py:385-437):
+//     check_game_winner -> generate_legal_moves -> none: mover loses
+//     -> uniform pick -> apply_move
+// The rules are not re-derived from the 8 bitboards every ply.  Instead each
+// playout carries 11 registers that are updated with a handful of LOP3s when a
+// piece lands:
+//     occ2            occupied squares (replicated in both 16-bit lanes)
+//     ra_lo/ra_hi     squares+shapes closed to role A (= the root's mover): the
+//                     row/column/zone scope of B's pieces of that shape, plus
+//                     whole lanes of shapes A has already placed twice
+//     rb_lo/rb_hi     same for role B
+//     ta_*/tb_*       lanes (shapes) of which the role has placed >= 1 piece
+//     lp_lo/lp_hi     per shape (colour-blind) the 12-bit set of lines that
+//                     contain it: rows 0-3, columns 4-7, zones 8-11
+// lanes: lo = shape A | shape B << 16, hi = shape C | shape D << 16.
+// Legal moves of the mover = ~(occ2 | r?_lo), ~(occ2 | r?_hi)   (2 LOP3)
+// A line is complete iff lp_A & lp_B & lp_C & lp_D != 0            (3 LOP3 + 1 SHF)
+#pragma once
+#include "qk_bits.cuh"
+
+namespace qk {
+
+// ---------------------------------------------------------------- Philox4x32-10
+// Salmon et al. (Random123); identical to cuRAND's curand_philox4x32_10 block
+// function.  Known-answer vectors are asserted in tests/.
+struct Philox4 { uint32_t v[4]; };
+
+QK_HD Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1)
+{
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t h0 = mulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+        uint32_t h1 = mulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+        uint32_t n0 = h1 ^ c1 ^ k0, n2 = h0 ^ c3 ^ k1;
+        c0 = n0; c1 = l1; c2 = n2; c3 = l0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    Philox4 o = { { c0, c1, c2, c3 } };
+    return o;
+}
+
+// Random-stream contract (DESIGN.md "Random stream"; shared with oracle/):
+//   key = (seed lo, seed hi); counter = (rollout lo, rollout hi, ply/4, root index);
+//   ply p uses word p % 4; move index = mulhi32(word, n_legal), ascending action order.
+QK_HD Philox4 stream_block(uint64_t seed, uint64_t rollout, uint32_t root_index, uint32_t block)
+{
+    return philox4x32_10((uint32_t)rollout, (uint32_t)(rollout >> 32), block, root_index,
+                         (uint32_t)seed, (uint32_t)(seed >> 32));
+}
+
+// ---------------------------------------------------------------- per-square table
+// x = scope of square p (its row | column | zone), y = its three line bits; both
+// replicated in the two 16-bit lanes so one AND with the lane mask routes them.
+struct SquareLut { uint32_t scope2, lines2; };
+
+QK_HD SquareLut square_lut(int p)
+{
+    uint32_t scope = (0xFu << (p & 12)) | (0x1111u << (p & 3)) | (0x33u << (p & 10));
+    uint32_t lines = (1u << (p >> 2)) | (16u << (p & 3)) | (256u << (((p >> 3) << 1) | ((p >> 1) & 1)));
+    SquareLut e = { (scope & 0xFFFFu) * 0x10001u, lines * 0x10001u };
+    return e;
+}
+// position of the k-th set bit of a byte (k < popcount), else 0
+QK_HD uint32_t kth_in_byte(uint32_t byte, uint32_t k)
+{
+    for (uint32_t b = 0; b < 8; ++b)
+        if ((byte >> b) & 1u) { if (k == 0) return b; --k; }
+    return 0;
+}
+
+// ---------------------------------------------------------------- root record
+// What k_prepare_roots writes and k_playout reloads at every refill (48 B = 3 x uint4).
+struct __attribute__((aligned(16))) RootRec {
+    uint32_t occ2, ra_lo, ra_hi, rb_lo;
+    uint32_t rb_hi, ta_lo, ta_hi, tb_lo;
+    uint32_t tb_hi, lp_lo, lp_hi, flags;
+};
+// flags: bit 0 = player to move at the root (role A); bits 8..9 = result known at
+// the root without playing (0 = none, 1 = P0 wins, 2 = P1 wins); bits 16.. = pieces on board
+enum { QK_ROOT_IMMEDIATE_SHIFT = 8 };
+
+QK_HD uint32_t lanes_with_one(uint32_t u)
+{
+    return ((u & 0xFFFFu) ? 0x0000FFFFu : 0u) | ((u >> 16) ? 0xFFFF0000u : 0u);
+}
+QK_HD uint32_t line_presence2(uint32_t u)   // 12-bit line sets of the two lanes of u
+{
+    uint32_t r = 0;
+    for (int p = 0; p < 16; ++p) {
+        uint32_t e = square_lut(p).lines2;
+        if ((u >> p) & 1u) r |= e & 0xFFFFu;
+        if ((u >> (p + 16)) & 1u) r |= e & 0xFFFF0000u;
+    }
+    return r;
+}
+
+QK_HD RootRec make_root(const State4 &s)
+{
+    RootRec r;
+    int player = 0;
+    int code = validate(s, &player);
+    int win = win_status(s);                 // checked first by both rollout loops
+    uint32_t immediate = win ? (uint32_t)win : (code != 0 ? 2u : 0u);   // invalid: (0, {}) -> P0 cannot move
+    uint32_t a_ab = player ? s.z : s.x, a_cd = player ? s.w : s.y;
+    uint32_t b_ab = player ? s.x : s.z, b_cd = player ? s.y : s.w;
+    uint32_t o = s.x | s.y | s.z | s.w;
+    o = (o | (o >> 16)) & 0xFFFFu;
+    r.occ2 = o * 0x10001u;
+    r.ra_lo = scope_fill(b_ab) | lanes_with_two(a_ab);  r.ra_hi = scope_fill(b_cd) | lanes_with_two(a_cd);
+    r.rb_lo = scope_fill(a_ab) | lanes_with_two(b_ab);  r.rb_hi = scope_fill(a_cd) | lanes_with_two(b_cd);
+    r.ta_lo = lanes_with_one(a_ab); r.ta_hi = lanes_with_one(a_cd);
+    r.tb_lo = lanes_with_one(b_ab); r.tb_hi = lanes_with_one(b_cd);
+    r.lp_lo = line_presence2(s.x | s.z); r.lp_hi = line_presence2(s.y | s.w);
+    r.flags = (uint32_t)player | (immediate << QK_ROOT_IMMEDIATE_SHIFT) | ((uint32_t)popc(o) << 16);
+    return r;
+}
+
+// ---------------------------------------------------------------- one ply
+struct PlayState {
+    uint32_t occ2, ra_lo, ra_hi, rb_lo, rb_hi, ta_lo, ta_hi, tb_lo, tb_hi, lp_lo, lp_hi;
+};
+QK_HD PlayState load_play_state(const RootRec &r)
+{
+    PlayState p = { r.occ2, r.ra_lo, r.ra_hi, r.rb_lo, r.rb_hi, r.ta_lo, r.ta_hi, r.tb_lo, r.tb_hi, r.lp_lo, r.lp_hi };
+    return p;
+}
+
+// Plays one move for role ROLE (0 = A moves, 1 = B moves) using random word `rnd`.
+// blocked: the mover had no legal move (mover loses; state untouched in a way that matters)
+// win:     the move completed a line (mover wins)
+// lut / sel8: the 16-entry square table and the 256x8 k-th-bit table (shared memory
+// in the kernel, plain arrays in hostsim).  action (optional) = shape*16 + square.
+template <int ROLE>
+QK_HD void ply_step(PlayState &st, uint32_t rnd, const SquareLut *lut, const uint8_t *sel8,
+                    bool &blocked, bool &win, int *action = nullptr)
+{
+    uint32_t &rm_lo = ROLE ? st.rb_lo : st.ra_lo, &rm_hi = ROLE ? st.rb_hi : st.ra_hi;   // mover
+    uint32_t &ro_lo = ROLE ? st.ra_lo : st.rb_lo, &ro_hi = ROLE ? st.ra_hi : st.rb_hi;   // other
+    uint32_t &tm_lo = ROLE ? st.tb_lo : st.ta_lo, &tm_hi = ROLE ? st.tb_hi : st.ta_hi;
+
+    // generate_legal_moves: 64-bit action mask, bit = shape*16 + square
+    uint32_t legal_lo = ~(st.occ2 | rm_lo), legal_hi = ~(st.occ2 | rm_hi);
+    int nlo = popc(legal_lo), n = nlo + popc(legal_hi);
+    blocked = (n == 0);
+
+    // uniform pick: k-th legal action in ascending order
+    int k = (int)mulhi(rnd, (uint32_t)n);
+    bool up = k >= nlo;                                   // shapes C,D
+    uint32_t w = up ? legal_hi : legal_lo;
+    k -= up ? nlo : 0;
+    int c = popc(w & 0xFFFFu);
+    bool odd = k >= c;                                    // shapes B / D (upper lane)
+    k -= odd ? c : 0;
+    w = odd ? (w >> 16) : w;
+    c = popc(w & 0xFFu);
+    bool hib = k >= c;                                    // squares 8..15
+    k -= hib ? c : 0;
+    uint32_t byte = (hib ? (w >> 8) : w) & 0xFFu;
+    uint32_t p = (uint32_t)sel8[(byte << 3) | (uint32_t)(k & 7)] + (hib ? 8u : 0u);
+
+    // apply_move + incremental rule state
+    uint32_t lane = odd ? 0xFFFF0000u : 0x0000FFFFu;
+    uint32_t l_lo = up ? 0u : lane, l_hi = up ? lane : 0u;
+    SquareLut e = lut[p & 15u];
+    st.occ2 |= 0x00010001u << (p & 15u);
+    ro_lo |= e.scope2 & l_lo;  ro_hi |= e.scope2 & l_hi;  // opponent may no longer use this shape in my scope
+    rm_lo |= tm_lo & l_lo;     rm_hi |= tm_hi & l_hi;     // second piece of the shape: lane exhausted for me
+    tm_lo |= l_lo;             tm_hi |= l_hi;
+    st.lp_lo |= e.lines2 & l_lo; st.lp_hi |= e.lines2 & l_hi;
+
+    // has_winning_line: a line holding all four shapes
+    uint32_t all4 = st.lp_lo & st.lp_hi;
+    win = (all4 & (all4 >> 16)) != 0;
+    if (action) *action = (int)(p & 15u) + (odd ? 16 : 0) + (up ? 32 : 0);
+}
+
+// ---------------------------------------------------------------- scalar playout
+// Whole playout on one thread, same ply_step as the kernel.  Used by
+// k_playout's tail handling and by tests/hostsim.  Returns +1 / -1 / 0 from
+// player 0's point of view (beam_search.py:635, mcts.py:417-419,437).
+QK_HD int playout_one(const RootRec &root, uint64_t seed, uint64_t rollout, uint32_t root_index,
+                      int max_plies, int *plies_out, const SquareLut *lut = nullptr, const uint8_t *sel8 = nullptr)
+{
+#ifndef __CUDA_ARCH__
+    static SquareLut h_lut[16];
+    static uint8_t h_sel8[2048];
+    static bool ready = false;
+    if (!ready) {
+        for (int p = 0; p < 16; ++p) h_lut[p] = square_lut(p);
+        for (uint32_t i = 0; i < 2048; ++i) h_sel8[i] = (uint8_t)kth_in_byte(i >> 3, i & 7);
+        ready = true;
+    }
+    if (!lut) { lut = h_lut; sel8 = h_sel8; }
+#endif
+    int result = 0, ply = 0;
+    uint32_t immediate = (root.flags >> QK_ROOT_IMMEDIATE_SHIFT) & 3u;
+    int a_wins = (root.flags & 1u) ? -1 : 1;             // role A is the root's mover
+    PlayState st = load_play_state(root);
+    Philox4 rnd = { { 0, 0, 0, 0 } };
+    for (;;) {
+        if (max_plies >= 0 && ply >= max_plies) { result = 0; break; }      // mcts.py:412,436-437
+        if (ply == 0 && immediate) { result = immediate == 1 ? 1 : -1; break; }
+        if ((ply & 3) == 0) rnd = stream_block(seed, rollout, root_index, (uint32_t)(ply >> 2));
+        bool blocked, win;
+        if (ply & 1) ply_step<1>(st, rnd.v[ply & 3], lut, sel8, blocked, win);
+        else         ply_step<0>(st, rnd.v[ply & 3], lut, sel8, blocked, win);
+        int mover_wins = (ply & 1) ? -a_wins : a_wins;
+        if (blocked) { result = -mover_wins; break; }                       // beam :641-642, mcts :427-429
+        ++ply;
+        if (max_plies >= 0 && ply >= max_plies) { result = 0; break; }      // cut-off precedes the win test
+        if (win) { result = mover_wins; break; }
+    }
+    if (plies_out) *plies_out = ply;
+    return result;
+}
+
+}  // namespace qk

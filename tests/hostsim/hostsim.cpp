@@ -1,0 +1,48 @@
+// hostsim.cpp -- compiles the kernels' __host__ __device__ rule code (qk_bits.cuh,
+// qk_playout_core.cuh) for the CPU so the exact bit tricks can be checked against the
+// oracle in the CPU-only test tier.  TEST INFRASTRUCTURE; never part of the product.
+#include <stdint.h>
+#include <stddef.h>
+#include "qk_bits.cuh"
+#ifdef QK_HOSTSIM_PLAYOUT
+#include "qk_playout_core.cuh"
+#endif
+
+using namespace qk;
+static State4 ld(const uint16_t *p) { State4 s = { (uint32_t)p[0] | ((uint32_t)p[1] << 16), (uint32_t)p[2] | ((uint32_t)p[3] << 16),
+                                                   (uint32_t)p[4] | ((uint32_t)p[5] << 16), (uint32_t)p[6] | ((uint32_t)p[7] << 16) }; return s; }
+static void st(uint16_t *p, const State4 &s) { p[0] = s.x; p[1] = s.x >> 16; p[2] = s.y; p[3] = s.y >> 16; p[4] = s.z; p[5] = s.z >> 16; p[6] = s.w; p[7] = s.w >> 16; }
+
+extern "C" {
+void hs_movegen(const uint16_t *s, size_t n, uint64_t *mask, uint8_t *to_move, uint8_t *status)
+{ for (size_t i = 0; i < n; ++i) { int p, c; mask[i] = movegen(ld(s + 8 * i), &p, &c); to_move[i] = p; status[i] = c; } }
+void hs_win(const uint16_t *s, size_t n, uint8_t *w) { for (size_t i = 0; i < n; ++i) w[i] = win_status(ld(s + 8 * i)); }
+void hs_canonical(const uint16_t *s, size_t n, int cs, uint16_t *out, uint32_t *tr)
+{
+    for (size_t i = 0; i < n; ++i) {
+        State4 a = ld(s + 8 * i), c = cs ? canonical<true>(a) : canonical<false>(a);
+        st(out + 8 * i, c);
+        if (tr) { State4 c2 = canonical_with_transform(a, cs != 0, tr + i); if (c2.x != c.x || c2.y != c.y || c2.z != c.z || c2.w != c.w) tr[i] = 0xFFFFFFFFu; }
+    }
+}
+void hs_orbit(const uint16_t *s, size_t n, uint8_t *o) { for (size_t i = 0; i < n; ++i) o[i] = orbit_size(ld(s + 8 * i)); }
+void hs_apply_symmetry(const uint16_t *s, const uint32_t *tr, size_t n, uint16_t *out) { for (size_t i = 0; i < n; ++i) st(out + 8 * i, apply_symmetry(ld(s + 8 * i), tr[i])); }
+uint16_t hs_d4(uint16_t v, int d4) { return (uint16_t)d4_apply((uint32_t)v, d4); }
+void hs_apply(const uint16_t *s, const uint8_t *a, size_t n, uint16_t *out)
+{ for (size_t i = 0; i < n; ++i) { State4 x = ld(s + 8 * i); int p = 0; if (validate(x, &p) != 0) p = 0; st(out + 8 * i, apply_action(x, p, a[i])); } }
+int hs_select(uint32_t lo, uint32_t hi, int k) { return select_bit64(lo, hi, popc(lo), k); }
+#ifdef QK_HOSTSIM_PLAYOUT
+void hs_playouts(const uint16_t *roots, size_t n_roots, uint32_t rollouts, uint64_t seed, uint64_t first, uint32_t root_base,
+                 int max_plies, int8_t *outcome, uint8_t *plies)
+{
+    for (size_t r = 0; r < n_roots; ++r) {
+        RootRec rec = make_root(ld(roots + 8 * r));
+        for (uint32_t j = 0; j < rollouts; ++j) {
+            int pl;
+            outcome[r * rollouts + j] = (int8_t)playout_one(rec, seed, first + j, root_base + (uint32_t)r, max_plies, &pl);
+            plies[r * rollouts + j] = (uint8_t)pl;
+        }
+    }
+}
+#endif
+}

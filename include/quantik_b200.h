@@ -1,0 +1,173 @@
+/*
+ * quantik_b200.h -- C ABI of libquantik_b200.so: the B200 (sm_100a) implementation
+ * of quantik-core's batched-simulation hot path.
+ *
+ * The reference (mberlanda/quantik-core-py 1.1.0) is pure Python and has no FFI
+ * layer; its seam is the set of module-level functions the engines import by name
+ * (mcts.py:15-19, beam_search.py:20-22, minimax.py:49-51, game_stats.py:7-22) plus
+ * the batch wire format of storage/compact_state.py:125-172.  Every entry point
+ * below cites the reference function it replaces.  INTEGRATION.md shows the
+ * ctypes binding a maintainer would add on the reference side.
+ *
+ * Conventions
+ *  - A state is 8 little-endian uint16 words [P0.A P0.B P0.C P0.D P1.A P1.B P1.C
+ *    P1.D], bit i = square i, row-major 4x4 (commons.py:10-13;
+ *    memory/bitboard_compact.py:36-37 `<8H`).  Batches are N x 8 words, 16-byte
+ *    aligned (storage/compact_state.py:125-147).
+ *  - An action is shape*16 + square (action-index.v1, docs/API_PORTABILITY.md:21;
+ *    api_portability_report.py:75-76); a legal-move set is the 64-bit mask of
+ *    actions in that numbering, which is also the reference's move order
+ *    (move.py:247,262-266).
+ *  - A transform is d4 | colour_swap << 3 | perm[0] << 4 | perm[1] << 6 |
+ *    perm[2] << 8 | perm[3] << 10, fields as in SymmetryTransform
+ *    (symmetry.py:45-62).
+ *  - Every pointer may be HOST memory (numpy) or DEVICE memory (torch data_ptr);
+ *    the library asks cudaPointerGetAttributes.  Host buffers are staged through
+ *    the device's stream-ordered pool and the call returns when results are in
+ *    place; with device buffers only, the call is asynchronous on `stream`.
+ *  - `dev` is the CUDA device ordinal, `stream` a cudaStream_t (NULL = default
+ *    stream).  Return value 0 = success, negative = QK_E_*; qk_last_error() has
+ *    the text (thread local).  There is no CPU fallback: without a usable sm_100
+ *    device every compute entry point fails with QK_E_CUDA / QK_E_NO_DEVICE.
+ *  - No global RNG state: a playout's moves are a pure function of
+ *    (seed, root index, rollout index, ply) -- see qk_playouts.
+ */
+#ifndef QUANTIK_B200_H
+#define QUANTIK_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QK_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define QK_API __attribute__((visibility("default")))
+#else
+#define QK_API
+#endif
+
+enum {
+    QK_OK = 0,
+    QK_E_BAD_ARG = -1,     /* null pointer, n out of range, depth out of range ...      */
+    QK_E_CUDA = -2,        /* a CUDA runtime call failed; text in qk_last_error()        */
+    QK_E_NO_DEVICE = -3,   /* no CUDA device / not an sm_100 part / qk_init not called   */
+    QK_E_NOMEM = -4
+};
+
+/* WinStatus, game_utils.py:32-37 */
+enum { QK_NO_WIN = 0, QK_PLAYER_0_WINS = 1, QK_PLAYER_1_WINS = 2 };
+/* ValidationResult, state_validator.py:16-27 */
+enum { QK_V_OK = 0, QK_V_TURN_BALANCE_INVALID = 1, QK_V_SHAPE_COUNT_EXCEEDED = 2, QK_V_NOT_PLAYER_TURN = 3,
+       QK_V_ILLEGAL_PLACEMENT = 4, QK_V_PIECE_OVERLAP = 5 };
+
+#define QK_MAX_DEPTH 16
+
+/* ---- lifetime ------------------------------------------------------------------ */
+QK_API int qk_abi_version(void);
+/* Creates the per-device context (stream-ordered memory pool kept warm, SM count). */
+QK_API int qk_init(int dev);
+QK_API int qk_shutdown(int dev);
+QK_API const char *qk_last_error(void);
+/* SM count and clock (kHz) of an initialised device; either pointer may be NULL. */
+QK_API int qk_device_info(int dev, int *sm_count, int *sm_clock_khz);
+
+/* ---- rules primitives, one state per thread --------------------------------------
+ * qk_movegen_masks  <- move.generate_legal_moves / generate_legal_moves_list
+ *                      (move.py:199-291) + state_validator._validate_game_state_single_pass
+ *                      (state_validator.py:126-168).  to_move = side to move, status =
+ *                      ValidationResult; an invalid state yields mask 0, to_move 0
+ *                      (move.py:223-225).  Any output pointer may be NULL.              */
+QK_API int qk_movegen_masks(const uint16_t *states, size_t n, uint64_t *action_mask, uint8_t *to_move,
+                     uint8_t *status, int dev, void *stream);
+/* qk_apply_moves    <- move.apply_move (move.py:135-166); no legality check, like the
+ *                      reference.  action = shape*16 + square places a piece of the side to
+ *                      move; action | 0x80 | player << 6 places it for an explicit player
+ *                      (Move.player, move.py:24-39).                                     */
+QK_API int qk_apply_moves(const uint16_t *states, const uint8_t *action, size_t n, uint16_t *out,
+                   int dev, void *stream);
+/* qk_win_status     <- game_utils.check_game_winner / has_winning_line
+ *                      (game_utils.py:123-189): WinStatus per state.                     */
+QK_API int qk_win_status(const uint16_t *states, size_t n, uint8_t *win_status, int dev, void *stream);
+
+/* ---- symmetry ---------------------------------------------------------------------
+ * qk_canonical      <- SymmetryHandler.find_canonical_form / get_canonical_payload
+ *                      (symmetry.py:289-354,398-410), State.canonical_payload/key
+ *                      (core.py:162-180).  payload = the 16-byte canonical `<8H`; the
+ *                      18-byte key is 01 02 + payload.  color_swap = 0 is the reference
+ *                      default (192 images), 1 the optional 384-image mode.  transform
+ *                      (may be NULL) receives the SymmetryTransform the reference returns. */
+QK_API int qk_canonical(const uint16_t *states, size_t n, int color_swap, uint16_t *payload,
+                 uint16_t *transform, int dev, void *stream);
+/* qk_orbit_size     <- SymmetryHandler.count_orbit_size (symmetry.py:356-396),
+ *                      State.symmetry_count (core.py:182-192).                          */
+QK_API int qk_orbit_size(const uint16_t *states, size_t n, uint8_t *orbit, int dev, void *stream);
+/* qk_apply_symmetry <- SymmetryHandler.apply_symmetry (symmetry.py:252-287).             */
+QK_API int qk_apply_symmetry(const uint16_t *states, const uint16_t *transform, size_t n, uint16_t *out,
+                      int dev, void *stream);
+/* qk_canon_dedup    <- the canonical merge of game_stats.py:487-505 /
+ *                      beam_search.py:526-546 / generate_opening_book.py:458-496:
+ *                      canonicalise n states, merge equal payloads, sum multiplicities
+ *                      (mult == NULL: 1 each).  uniq (capacity `cap` states) receives the
+ *                      distinct payloads sorted in byte order, uniq_mult their summed
+ *                      multiplicities, *n_uniq the count (host pointer).  Synchronous.   */
+QK_API int qk_canon_dedup(const uint16_t *states, const uint64_t *mult, size_t n, int color_swap,
+                   uint16_t *uniq, uint64_t *uniq_mult, size_t cap, size_t *n_uniq,
+                   int dev, void *stream);
+
+/* ---- random playouts ---------------------------------------------------------------
+ * qk_playouts       <- BeamSearchEngine._rollout/_default_evaluate (beam_search.py:614-645)
+ *                      when max_plies < 0 (play to a true terminal; result +-1), and
+ *                      MCTSEngine._simulate (mcts.py:385-437, uniform branch of
+ *                      _select_rollout_move :345-364) when max_plies >= 0 (stop after
+ *                      max_plies moves, result 0 = the reference's 0.0).
+ * For every root r < n_roots, `rollouts_per_root` playouts are run; rollout j uses the
+ * Philox4x32-10 counter stream  key = seed, counter = (j + first_rollout (64 bit),
+ * ply / 4, root_index_base + r), word ply % 4, move = mulhi32(word, n_legal)-th legal
+ * action.  Outputs (any may be NULL): wins_p0 / wins_p1 / draws [n_roots] tallies;
+ * per_playout [n_roots * rollouts] int8 outcome from player 0's view (+1, -1, 0);
+ * per_plies [n_roots * rollouts] moves played.                                          */
+QK_API int qk_playouts(const uint16_t *roots, size_t n_roots, uint32_t rollouts_per_root, uint64_t seed,
+                int max_plies, uint32_t *wins_p0, uint32_t *wins_p1, uint32_t *draws,
+                int8_t *per_playout, int dev, void *stream);
+QK_API int qk_playouts_ex(const uint16_t *roots, size_t n_roots, uint32_t rollouts_per_root, uint64_t seed,
+                   uint64_t first_rollout, uint32_t root_index_base, int max_plies,
+                   uint32_t *wins_p0, uint32_t *wins_p1, uint32_t *draws,
+                   int8_t *per_playout, uint8_t *per_plies, int dev, void *stream);
+/* qk_random_roots   <- benchmarks/dataset.py:38-51 (random non-terminal mid-game
+ *                      positions by rejection): root i = empty board + (min_plies +
+ *                      i % span) uniform-random plies, stream key seed ^ "ROOTS",
+ *                      counter (i, attempt, ply/4, 0).  Writes n states for
+ *                      i = first .. first+n-1.                                            */
+QK_API int qk_random_roots(uint64_t seed, uint64_t first, size_t n, int min_plies, int span,
+                    uint16_t *out_states, int dev, void *stream);
+
+/* ---- exhaustive enumeration ---------------------------------------------------------
+ * qk_perft          <- the counting rules of game_stats.SymmetryTable
+ *                      (_process_parent_state / _process_move / _handle_no_legal_moves,
+ *                      game_stats.py:384-485) as a raw tree walk below each root, weighted
+ *                      by mult (NULL = 1).  Arrays have depth+1 entries, index = plies
+ *                      below the root:
+ *   nodes[d]             move sequences of length d ("Total Legal Moves" of depth d)
+ *   wins_p0/p1[d]        sequences whose d-th move completed a line, by mover
+ *   blocked_pX_loses[d]  non-won positions at depth d < depth where X must move and
+ *                        cannot (the reference books them at depth d+1 as a win of the
+ *                        other player); entry [depth] is 0.
+ * Output pointers must be HOST memory; the call is synchronous.                          */
+QK_API int qk_perft(const uint16_t *roots, const uint64_t *mult, size_t n_roots, int depth,
+             uint64_t *nodes, uint64_t *wins_p0, uint64_t *wins_p1,
+             uint64_t *blocked_p0_loses, uint64_t *blocked_p1_loses, int dev, void *stream);
+
+/* ---- measurement aid ------------------------------------------------------------------
+ * Runs a dependency-free integer micro-kernel and reports warp-instructions x 32 per
+ * second for (a) a pure LOP3/IADD3 stream and (b) a LOP3 + IMAD mix: the measured
+ * integer-issue roofline denominators used by bench.py.                                   */
+QK_API int qk_int_issue_peak(int dev, double *alu_lane_ops_per_s, double *mixed_lane_ops_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QUANTIK_B200_H */

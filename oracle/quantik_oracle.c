@@ -269,10 +269,11 @@ QO_API void qo_win_batch(const uint16_t *states, size_t n, uint8_t *win)
     for (long i = 0; i < (long)n; ++i) win[i] = (uint8_t)qo_check_game_winner(states + 8 * i);
 }
 QO_API void qo_apply_batch(const uint16_t *states, const uint8_t *action, size_t n, uint16_t *out)
-{   /* mover = side to move (state_validator); action = shape*16+pos */
+{   /* action = shape*16+pos for the side to move (state_validator), or | 0x80 | player << 6 */
     for (size_t i = 0; i < n; ++i) {
         int p; qo_validate(states + 8 * i, &p); if (p < 0) p = 0;
-        qo_apply(states + 8 * i, p, action[i] >> 4, action[i] & 15, out + 8 * i);
+        if (action[i] & 0x80) p = (action[i] >> 6) & 1;
+        qo_apply(states + 8 * i, p, (action[i] >> 4) & 3, action[i] & 15, out + 8 * i);
     }
 }
 QO_API void qo_canonical_batch(const uint16_t *states, size_t n, int color_swap, uint16_t *payload, int32_t *transform)

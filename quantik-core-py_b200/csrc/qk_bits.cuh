@@ -236,7 +236,7 @@ QK_HD Key128 sorted_image(uint32_t c0ab, uint32_t c0cd, uint32_t c1ab, uint32_t 
     uint32_t k0 = prmt(c0ab, c1ab, 0x0145), k1 = prmt(c0ab, c1ab, 0x2367);
     uint32_t k2 = prmt(c0cd, c1cd, 0x0145), k3 = prmt(c0cd, c1cd, 0x2367);
     cswap(k0, k1); cswap(k2, k3); cswap(k0, k2); cswap(k1, k3); cswap(k1, k2);
-    Key128 r = { prmt(k0, k1, 0x3276), prmt(k2, k3, 0x3276), prmt(k0, k1, 0x1045), prmt(k2, k3, 0x1045) };
+    Key128 r = { prmt(k0, k1, 0x3276), prmt(k2, k3, 0x3276), prmt(k0, k1, 0x1054), prmt(k2, k3, 0x1054) };
     return r;
 }
 QK_HD State4 key_to_state(const Key128 &k)

@@ -1,0 +1,86 @@
+// qk_common.cuh -- host-side plumbing shared by the translation units of
+// libquantik_b200.so: per-device context, error text, host<->device staging.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include <string>
+#include <vector>
+
+#include "../../include/quantik_b200.h"
+
+namespace qk {
+
+struct Ctx {
+    bool ok = false;
+    int dev = -1;
+    int sms = 0;
+    int clock_khz = 0;
+    cudaMemPool_t pool = nullptr;
+};
+
+void set_error(const std::string &msg);
+int cuda_fail(cudaError_t e, const char *what);          // records text, returns QK_E_CUDA
+Ctx *get_ctx(int dev);                                   // nullptr (+error text) when not initialised
+
+#define QK_CUDA(call)                                                     \
+    do {                                                                  \
+        cudaError_t e__ = (call);                                         \
+        if (e__ != cudaSuccess) return ::qk::cuda_fail(e__, #call);       \
+    } while (0)
+
+// One API call: resolves every caller pointer to a device pointer, staging host
+// buffers through the device's stream-ordered pool, and copies results back.
+class Call {
+public:
+    Call(int dev, void *stream);
+    ~Call();
+    bool valid() const { return ctx_ != nullptr; }
+    int status() const { return status_; }
+    Ctx *ctx() const { return ctx_; }
+    cudaStream_t stream() const { return stream_; }
+
+    const void *in(const void *p, size_t bytes);          // nullptr stays nullptr
+    void *out(void *p, size_t bytes, bool zero = false);  // nullptr stays nullptr
+    void *temp(size_t bytes, bool zero = false);
+    int finish();                                         // copy-backs, frees, sync if host buffers were used
+    int sync();
+
+private:
+    struct Back { void *host; void *dev; size_t bytes; };
+    Ctx *ctx_ = nullptr;
+    cudaStream_t stream_ = nullptr;
+    int status_ = QK_OK;
+    bool any_host_ = false;
+    int prev_dev_ = -1;
+    std::vector<void *> temps_;
+    std::vector<Back> backs_;
+    void *alloc(size_t bytes);
+};
+
+inline unsigned grid_for(size_t n, unsigned block, int sms, unsigned per_sm)
+{
+    size_t want = (n + block - 1) / block;
+    size_t cap = (size_t)sms * per_sm;
+    if (want < 1) want = 1;
+    return (unsigned)(want < cap ? want : cap);
+}
+
+// launchers implemented in the kernel translation units (all asynchronous on `s`)
+int launch_movegen(const uint4 *states, size_t n, uint64_t *mask, uint8_t *to_move, uint8_t *status, Ctx *c, cudaStream_t s);
+int launch_apply(const uint4 *states, const uint8_t *action, size_t n, uint4 *out, Ctx *c, cudaStream_t s);
+int launch_win(const uint4 *states, size_t n, uint8_t *win, Ctx *c, cudaStream_t s);
+int launch_canonical(const uint4 *states, size_t n, int color_swap, uint4 *payload, uint16_t *transform, Ctx *c, cudaStream_t s);
+int launch_orbit(const uint4 *states, size_t n, uint8_t *orbit, Ctx *c, cudaStream_t s);
+int launch_apply_symmetry(const uint4 *states, const uint16_t *transform, size_t n, uint4 *out, Ctx *c, cudaStream_t s);
+int launch_playouts(const uint4 *roots, size_t n_roots, uint32_t rollouts, uint64_t seed, uint64_t first_rollout,
+                    uint32_t root_index_base, int max_plies, uint32_t *wins_p0, uint32_t *wins_p1, uint32_t *draws,
+                    int8_t *per_playout, uint8_t *per_plies, void *rootrec_scratch, Ctx *c, cudaStream_t s);
+size_t playout_scratch_bytes(size_t n_roots);
+int launch_random_roots(uint64_t seed, uint64_t first, size_t n, int min_plies, int span, uint4 *out, Ctx *c, cudaStream_t s);
+int run_perft(Call &call, const uint4 *roots, const uint64_t *mult, size_t n_roots, int depth, uint64_t *host_out /*5 x (depth+1)*/);
+int run_dedup(Call &call, const uint4 *states, const uint64_t *mult, size_t n, int color_swap,
+              uint16_t *uniq_host_or_dev, uint64_t *uniq_mult, size_t cap, size_t *n_uniq);
+int run_issue_peak(Ctx *c, double *alu, double *mixed);
+
+}  // namespace qk

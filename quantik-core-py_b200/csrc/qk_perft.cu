@@ -1,0 +1,308 @@
+// qk_perft.cu -- exhaustive enumeration below a batch of roots (BASELINE configs 2
+// and 5) with the counting rules of game_stats.SymmetryTable (game_stats.py:384-485).
+//
+// Plan of one qk_perft call (host driver run_perft at the bottom):
+//   k_perft_filter_roots  roots -> frontier of valid, not-yet-won positions
+//   k_perft_expand        level-synchronous widening, one position per thread, until the
+//                         frontier has enough items to fill the machine
+//   k_perft_dfs           one frontier item per WARP: depth-first walk with a
+//                         warp-shared frame stack in shared memory.  Interior nodes are
+//                         expanded cooperatively (lane l materialises children l and
+//                         l+32 of the 64-bit action mask); positions one ply above the
+//                         target depth ("leaf parents") are queued in shared memory and
+//                         consumed 32 at a time, one per lane, so the dominant work runs
+//                         with full warps.
+//   k_perft_leaf          frontier already one ply above the target: one per thread.
+// The last ply is never materialised: move counts and winning-move counts of a leaf
+// parent come from popcounts (qk_perft_core.cuh).
+#include "qk_common.cuh"
+#include "qk_perft_core.cuh"
+
+namespace qk {
+
+static constexpr unsigned kBlock = 256;
+static constexpr unsigned kWarps = kBlock / 32;
+static constexpr unsigned kFull = 0xFFFFFFFFu;
+static constexpr int kRows = QK_MAX_DEPTH + 1;        // counters[5][17]: nodes, wins_p0, wins_p1, blocked_p0, blocked_p1
+typedef unsigned long long u64;
+
+__device__ __forceinline__ u64 warp_sum(u64 v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    return v;
+}
+__device__ __forceinline__ State4 to_state(const uint4 &v) { State4 s = { v.x, v.y, v.z, v.w }; return s; }
+__device__ __forceinline__ uint4 to_u4(const State4 &s) { return make_uint4(s.x, s.y, s.z, s.w); }
+
+// ------------------------------------------------------------------ roots -> frontier
+__global__ void __launch_bounds__(kBlock) k_perft_filter_roots(const uint4 *__restrict__ roots, const u64 *__restrict__ mult,
+                                                                size_t n, int depth, uint4 *__restrict__ out_states,
+                                                                u64 *__restrict__ out_mult, u64 *__restrict__ out_count,
+                                                                u64 *__restrict__ counters)
+{
+    size_t i = blockIdx.x * (size_t)kBlock + threadIdx.x;
+    const unsigned lane = threadIdx.x & 31u;
+    u64 m = 0, blocked = 0;
+    bool keep = false;
+    State4 s = { 0, 0, 0, 0 };
+    if (i < n) {
+        s = to_state(__ldg(roots + i));
+        m = mult ? mult[i] : 1ull;
+        int player;
+        if (win_status(s) == 0) {                       // a finished root has nothing below it
+            if (validate(s, &player) != 0) blocked = m; // generate_legal_moves -> (0, {})  (move.py:223-225)
+            else keep = true;
+        }
+    }
+    u64 tot = warp_sum(m), blk = warp_sum(blocked);
+    unsigned kmask = __ballot_sync(kFull, keep);
+    u64 base = 0;
+    if (lane == 0) {
+        if (tot) atomicAdd(counters + 0 * kRows + 0, tot);
+        if (blk && depth > 0) atomicAdd(counters + 3 * kRows + 0, blk);
+        if (kmask) base = atomicAdd(out_count, (u64)__popc(kmask));
+    }
+    base = __shfl_sync(kFull, base, 0);
+    if (keep) {
+        u64 o = base + __popc(kmask & ((1u << lane) - 1u));
+        out_states[o] = to_u4(s);
+        out_mult[o] = m;
+    }
+}
+
+// ------------------------------------------------------------------ one level, thread per position
+// _process_parent_state (game_stats.py:384-424): total_moves, wins by the mover, children
+__global__ void __launch_bounds__(kBlock) k_perft_expand(const uint4 *__restrict__ in_states, const u64 *__restrict__ in_mult,
+                                                          size_t n, int d, uint4 *__restrict__ out_states,
+                                                          u64 *__restrict__ out_mult, u64 *__restrict__ out_count,
+                                                          u64 *__restrict__ counters)
+{
+    size_t i = blockIdx.x * (size_t)kBlock + threadIdx.x;
+    const unsigned lane = threadIdx.x & 31u;
+    State4 s = { 0, 0, 0, 0 };
+    u64 m = 0;
+    uint32_t nl = 0, nh = 0;
+    int mover = 0, n_moves = 0, n_wins = 0;
+    u64 c_nodes = 0, c_w0 = 0, c_w1 = 0, c_b0 = 0, c_b1 = 0;
+    if (i < n) {
+        s = to_state(__ldg(in_states + i));
+        m = in_mult[i];
+        mover = piece_balance(s);
+        uint32_t lo, hi, wab, wcd;
+        legal_masks(s, mover, lo, hi);
+        winning_squares(s, wab, wcd);
+        n_moves = popc(lo) + popc(hi);
+        n_wins = popc(lo & wab) + popc(hi & wcd);
+        nl = lo & ~wab; nh = hi & ~wcd;
+        c_nodes = (u64)n_moves * m;
+        if (mover == 0) { c_w0 = (u64)n_wins * m; c_b0 = n_moves ? 0 : m; }
+        else            { c_w1 = (u64)n_wins * m; c_b1 = n_moves ? 0 : m; }
+    }
+    c_nodes = warp_sum(c_nodes); c_w0 = warp_sum(c_w0); c_w1 = warp_sum(c_w1); c_b0 = warp_sum(c_b0); c_b1 = warp_sum(c_b1);
+    // exclusive scan of the children counts inside the warp, one reservation per warp
+    uint32_t cnt = (uint32_t)(popc(nl) + popc(nh)), incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(kFull, incl, o); if (lane >= (unsigned)o) incl += t; }
+    uint32_t total = __shfl_sync(kFull, incl, 31);
+    u64 base = 0;
+    if (lane == 0) {
+        if (c_nodes) atomicAdd(counters + 0 * kRows + d + 1, c_nodes);
+        if (c_w0) atomicAdd(counters + 1 * kRows + d + 1, c_w0);
+        if (c_w1) atomicAdd(counters + 2 * kRows + d + 1, c_w1);
+        if (c_b0) atomicAdd(counters + 3 * kRows + d, c_b0);
+        if (c_b1) atomicAdd(counters + 4 * kRows + d, c_b1);
+        if (total) base = atomicAdd(out_count, (u64)total);
+    }
+    base = __shfl_sync(kFull, base, 0) + (incl - cnt);
+    for (uint32_t w = nl; w; w &= w - 1) {
+        out_states[base] = to_u4(apply_action(s, mover, __ffs((int)w) - 1));
+        out_mult[base++] = m;
+    }
+    for (uint32_t w = nh; w; w &= w - 1) {
+        out_states[base] = to_u4(apply_action(s, mover, 32 + __ffs((int)w) - 1));
+        out_mult[base++] = m;
+    }
+}
+
+// ------------------------------------------------------------------ frontier one ply above the target
+__global__ void __launch_bounds__(kBlock) k_perft_leaf(const uint4 *__restrict__ states, const u64 *__restrict__ mult,
+                                                        size_t n, int d, u64 *__restrict__ counters)
+{
+    const unsigned lane = threadIdx.x & 31u;
+    u64 c_nodes = 0, c_w0 = 0, c_w1 = 0, c_b0 = 0, c_b1 = 0;
+    for (size_t i = blockIdx.x * (size_t)kBlock + threadIdx.x; i < n; i += (size_t)gridDim.x * kBlock) {
+        State4 s = to_state(__ldg(states + i));
+        u64 m = mult[i];
+        int nm, nw;
+        int mover = leaf_parent_counts(s, nm, nw);
+        c_nodes += (u64)nm * m;
+        if (mover == 0) { c_w0 += (u64)nw * m; c_b0 += nm ? 0 : m; }
+        else            { c_w1 += (u64)nw * m; c_b1 += nm ? 0 : m; }
+    }
+    c_nodes = warp_sum(c_nodes); c_w0 = warp_sum(c_w0); c_w1 = warp_sum(c_w1); c_b0 = warp_sum(c_b0); c_b1 = warp_sum(c_b1);
+    if (lane == 0) {
+        if (c_nodes) atomicAdd(counters + 0 * kRows + d + 1, c_nodes);
+        if (c_w0) atomicAdd(counters + 1 * kRows + d + 1, c_w0);
+        if (c_w1) atomicAdd(counters + 2 * kRows + d + 1, c_w1);
+        if (c_b0) atomicAdd(counters + 3 * kRows + d, c_b0);
+        if (c_b1) atomicAdd(counters + 4 * kRows + d, c_b1);
+    }
+}
+
+// ------------------------------------------------------------------ warp-cooperative DFS
+struct WarpScratch {
+    uint4 queue[96];              // leaf parents waiting for a full warp (<= 31 + 64)
+    uint4 frame_state[QK_MAX_DEPTH];
+    u64 frame_mask[QK_MAX_DEPTH]; // non-winning children of frame_state still to visit
+    u64 cnt[5 * kRows];           // this warp's share of the counters, weighted by multiplicity
+};
+
+__global__ void __launch_bounds__(kBlock) k_perft_dfs(const uint4 *__restrict__ items, const u64 *__restrict__ mult, u64 n_items,
+                                                       int d0, int depth, u64 *__restrict__ next_item, u64 *__restrict__ counters)
+{
+    __shared__ WarpScratch s_scratch[kWarps];
+    WarpScratch &ws = s_scratch[threadIdx.x >> 5];
+    const unsigned lane = threadIdx.x & 31u;
+    const uint32_t lt = (1u << lane) - 1u;
+    for (int k = lane; k < 5 * kRows; k += 32) ws.cnt[k] = 0;
+    __syncwarp();
+
+    const int rem0 = depth - d0;   // >= 2: plies left below an item
+    for (;;) {
+        u64 idx = 0;
+        if (lane == 0) idx = atomicAdd(next_item, 1ull);
+        idx = __shfl_sync(kFull, idx, 0);
+        if (idx >= n_items) break;
+        const State4 item = to_state(__ldg(items + idx));
+        const u64 m = mult[idx];
+        const int leaf_mover = (piece_balance(item) + rem0 - 1) & 1;   // who moves one ply above the target
+        u64 leaf_nodes = 0, leaf_wins = 0, leaf_blocked = 0;           // per lane, unweighted
+
+        int sp = 0, qn = 0;
+        State4 node = item;
+        int node_rem = rem0;
+        bool expand = true;
+        for (;;) {
+            if (expand) {
+                // ---- interior node (warp-uniform): its moves, its winning moves
+                const int d = depth - node_rem;
+                const int mover = piece_balance(node);
+                uint32_t lo, hi, wab, wcd;
+                legal_masks(node, mover, lo, hi);
+                const int n_moves = popc(lo) + popc(hi);
+                if (n_moves == 0) {
+                    if (lane == 0) ws.cnt[(3 + mover) * kRows + d] += m;           // game_stats.py:426-443
+                } else {
+                    winning_squares(node, wab, wcd);
+                    const uint32_t nl = lo & ~wab, nh = hi & ~wcd;
+                    if (lane == 0) {
+                        ws.cnt[0 * kRows + d + 1] += (u64)n_moves * m;             // :401
+                        ws.cnt[(1 + mover) * kRows + d + 1] += (u64)(popc(lo & wab) + popc(hi & wcd)) * m;   // :411-415
+                    }
+                    if (node_rem == 2) {
+                        // children are leaf parents: lane l writes children l and l+32 into the queue
+                        const int c_lo = popc(nl);
+                        if ((nl >> lane) & 1u) ws.queue[qn + popc(nl & lt)] = to_u4(apply_action(node, mover, (int)lane));
+                        if ((nh >> lane) & 1u) ws.queue[qn + c_lo + popc(nh & lt)] = to_u4(apply_action(node, mover, 32 + (int)lane));
+                        qn += c_lo + popc(nh);
+                        __syncwarp();
+                        while (qn >= 32) {
+                            qn -= 32;
+                            int nm, nw;
+                            leaf_parent_counts(to_state(ws.queue[qn + lane]), nm, nw);
+                            leaf_nodes += nm; leaf_wins += nw; leaf_blocked += nm == 0;
+                            __syncwarp();
+                        }
+                    } else if (nl | nh) {
+                        if (lane == 0) { ws.frame_state[sp] = to_u4(node); ws.frame_mask[sp] = ((u64)nh << 32) | nl; }
+                        ++sp;
+                        __syncwarp();
+                    }
+                }
+            }
+            if (sp == 0) break;
+            // ---- next unvisited child of the top frame
+            const u64 fm = ws.frame_mask[sp - 1];
+            __syncwarp();
+            if (fm == 0) { --sp; expand = false; continue; }
+            if (lane == 0) ws.frame_mask[sp - 1] = fm & (fm - 1);
+            const State4 parent = to_state(ws.frame_state[sp - 1]);
+            node = apply_action(parent, piece_balance(parent), __ffsll((long long)fm) - 1);
+            node_rem = rem0 - sp;       // frame k sits k plies below the item
+            expand = true;
+            __syncwarp();
+        }
+        // ---- drain the queue, fold this item's leaf tallies into the warp counters
+        if ((int)lane < qn) {
+            int nm, nw;
+            leaf_parent_counts(to_state(ws.queue[lane]), nm, nw);
+            leaf_nodes += nm; leaf_wins += nw; leaf_blocked += nm == 0;
+        }
+        __syncwarp();
+        leaf_nodes = warp_sum(leaf_nodes); leaf_wins = warp_sum(leaf_wins); leaf_blocked = warp_sum(leaf_blocked);
+        if (lane == 0) {
+            ws.cnt[0 * kRows + depth] += leaf_nodes * m;
+            ws.cnt[(1 + leaf_mover) * kRows + depth] += leaf_wins * m;
+            ws.cnt[(3 + leaf_mover) * kRows + depth - 1] += leaf_blocked * m;
+        }
+        __syncwarp();
+    }
+    __syncwarp();
+    for (int k = lane; k < 5 * kRows; k += 32)
+        if (ws.cnt[k]) atomicAdd(counters + k, ws.cnt[k]);
+}
+
+// ------------------------------------------------------------------ host driver
+int run_perft(Call &call, const uint4 *roots, const uint64_t *mult, size_t n_roots, int depth, uint64_t *host_out)
+{
+    cudaStream_t s = call.stream();
+    Ctx *c = call.ctx();
+    // device block: counters[5][17], frontier size, dfs work counter
+    u64 *d_ctr = (u64 *)call.temp((5 * kRows + 2) * sizeof(u64), true);
+    if (!d_ctr) return call.status();
+    u64 *d_count = d_ctr + 5 * kRows, *d_next = d_count + 1;
+
+    uint4 *cur_s = (uint4 *)call.temp(n_roots * 16);
+    u64 *cur_m = (u64 *)call.temp(n_roots * 8);
+    if (!cur_s || !cur_m) return call.status();
+    k_perft_filter_roots<<<(unsigned)((n_roots + kBlock - 1) / kBlock), kBlock, 0, s>>>(
+        roots, (const u64 *)mult, n_roots, depth, cur_s, cur_m, d_count, d_ctr);
+    QK_CUDA(cudaGetLastError());
+    u64 n_cur = 0;
+    QK_CUDA(cudaMemcpyAsync(&n_cur, d_count, sizeof(u64), cudaMemcpyDeviceToHost, s));
+    QK_CUDA(cudaStreamSynchronize(s));
+
+    // widen until every warp of a full machine has several items (or the target is near)
+    const u64 want_items = (u64)c->sms * 4 * kWarps * 8;
+    int d = 0;
+    while (n_cur > 0 && d < depth) {
+        const int rem = depth - d;
+        if (rem == 1) {
+            k_perft_leaf<<<grid_for(n_cur, kBlock, c->sms, 8), kBlock, 0, s>>>(cur_s, cur_m, n_cur, d, d_ctr);
+            QK_CUDA(cudaGetLastError());
+            break;
+        }
+        if (n_cur >= want_items || n_cur * 64 > (1ull << 26)) {
+            QK_CUDA(cudaMemsetAsync(d_next, 0, sizeof(u64), s));
+            k_perft_dfs<<<c->sms * 4, kBlock, 0, s>>>(cur_s, cur_m, n_cur, d, depth, d_next, d_ctr);
+            QK_CUDA(cudaGetLastError());
+            break;
+        }
+        uint4 *nxt_s = (uint4 *)call.temp(n_cur * 64 * 16);
+        u64 *nxt_m = (u64 *)call.temp(n_cur * 64 * 8);
+        if (!nxt_s || !nxt_m) return call.status();
+        QK_CUDA(cudaMemsetAsync(d_count, 0, sizeof(u64), s));
+        k_perft_expand<<<(unsigned)((n_cur + kBlock - 1) / kBlock), kBlock, 0, s>>>(cur_s, cur_m, n_cur, d, nxt_s, nxt_m, d_count, d_ctr);
+        QK_CUDA(cudaGetLastError());
+        QK_CUDA(cudaMemcpyAsync(&n_cur, d_count, sizeof(u64), cudaMemcpyDeviceToHost, s));
+        QK_CUDA(cudaStreamSynchronize(s));
+        cur_s = nxt_s; cur_m = nxt_m;
+        ++d;
+    }
+    QK_CUDA(cudaMemcpyAsync(host_out, d_ctr, 5 * kRows * sizeof(u64), cudaMemcpyDeviceToHost, s));
+    QK_CUDA(cudaStreamSynchronize(s));
+    return QK_OK;
+}
+
+}  // namespace qk

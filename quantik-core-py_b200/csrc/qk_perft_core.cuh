@@ -1,0 +1,49 @@
+// qk_perft_core.cuh -- bulk counting of the last perft ply.
+//
+// For a non-won, valid position ("leaf parent") the enumerator of
+// game_stats.py:384-424 needs, per parent: how many legal moves it has
+// (total_moves, :401) and how many of them complete a line (:411-415, credited to
+// the mover).  Neither needs the children to be materialised:
+//   moves = popc(legal mask)
+//   a placement of shape s on square p wins  <=>  p is legal for s and some line
+//   through p already holds the three OTHER shapes
+// so winning placements = popc(legal_s & (rows|cols|zones holding all shapes but s)).
+#pragma once
+#include "qk_bits.cuh"
+
+namespace qk {
+
+QK_HD uint32_t swap_lanes(uint32_t v) { return prmt(v, 0, 0x1032); }
+QK_HD uint32_t dup_low(uint32_t v) { return prmt(v, 0, 0x1010); }
+
+// squares where dropping shape s would complete a line; lanes (A|B<<16, C|D<<16)
+QK_HD void winning_squares(const State4 &s, uint32_t &win_ab, uint32_t &win_cd)
+{
+    uint32_t u01 = s.x | s.z, u23 = s.y | s.w;
+    uint32_t t01 = pair_or1(u01), t23 = pair_or1(u23);
+    // "some piece of shape t shares this row / zone / column" as square masks
+    uint32_t r01 = row_presence(t01) * 0xFu, r23 = row_presence(t23) * 0xFu;
+    uint32_t z01 = zone_presence(t01) * 0x33u, z23 = zone_presence(t23) * 0x33u;
+    uint32_t c01 = col_presence(u01) * 0x1111u, c23 = col_presence(u23) * 0x1111u;
+    // for shape A: has(B) & has(C) & has(D) = swap(x01) & dup(x23 & x23>>16); etc.
+    uint32_t rb01 = dup_low(r01 & (r01 >> 16)), rb23 = dup_low(r23 & (r23 >> 16));
+    uint32_t zb01 = dup_low(z01 & (z01 >> 16)), zb23 = dup_low(z23 & (z23 >> 16));
+    uint32_t cb01 = dup_low(c01 & (c01 >> 16)), cb23 = dup_low(c23 & (c23 >> 16));
+    win_ab = (swap_lanes(r01) & rb23) | (swap_lanes(z01) & zb23) | (swap_lanes(c01) & cb23);
+    win_cd = (swap_lanes(r23) & rb01) | (swap_lanes(z23) & zb01) | (swap_lanes(c23) & cb01);
+}
+
+// state must be valid and not already won.  Returns the mover; n_moves / n_wins
+// as described above.
+QK_HD int leaf_parent_counts(const State4 &s, int &n_moves, int &n_wins)
+{
+    int mover = piece_balance(s);           // 0 -> P0 to move, 1 -> P1 (state_validator.py:82-98)
+    uint32_t lo, hi, wab, wcd;
+    legal_masks(s, mover, lo, hi);
+    winning_squares(s, wab, wcd);
+    n_moves = popc(lo) + popc(hi);
+    n_wins = popc(lo & wab) + popc(hi & wcd);
+    return mover;
+}
+
+}  // namespace qk

@@ -1,0 +1,246 @@
+// qk_playout.cu -- batched uniform-random playouts (BASELINE configs 1 and 4).
+//
+// k_prepare_roots : root (16 B) -> RootRec (48 B): incremental rule state + result
+//                   already known at the root (won / invalid).
+// k_playout       : one playout per thread at a time, state in registers
+//                   (qk_playout_core.cuh).  The flat playout space
+//                   [0, n_roots * rollouts) is cut into one contiguous chunk per
+//                   thread.  A thread whose game ends picks up its next playout at the
+//                   next 4-ply boundary, where the whole warp computes one Philox4x32-10
+//                   block (4 words = 4 plies) anyway -- so the refill never diverges the
+//                   RNG code, and a playout's moves stay a pure function of
+//                   (seed, root, rollout, ply).
+//                   Tallies are kept per thread while the root stays the same and are
+//                   flushed with warp-aggregated atomics.
+// k_random_roots  : the config-4 mid-game root generator.
+#include "qk_common.cuh"
+#include "qk_playout_core.cuh"
+
+namespace qk {
+
+static constexpr unsigned kBlock = 256;
+static constexpr unsigned kFull = 0xFFFFFFFFu;
+
+struct PlayoutArgs {
+    const RootRec *roots;
+    uint64_t total;          // n_roots * rollouts
+    uint64_t chunk;          // playouts per thread
+    uint64_t seed;
+    uint64_t first_rollout;
+    uint32_t rollouts;
+    uint32_t root_index_base;
+    int max_plies;
+    uint32_t *wins_p0, *wins_p1, *draws;
+    int8_t *per_playout;
+    uint8_t *per_plies;
+};
+
+__global__ void __launch_bounds__(kBlock) k_prepare_roots(const uint4 *__restrict__ states, size_t n, RootRec *__restrict__ out)
+{
+    size_t i = blockIdx.x * (size_t)kBlock + threadIdx.x;
+    if (i >= n) return;
+    uint4 v = __ldg(states + i);
+    State4 s = { v.x, v.y, v.z, v.w };
+    out[i] = make_root(s);
+}
+
+__device__ __forceinline__ void fill_tables(SquareLut *lut, uint8_t *sel8)
+{
+    if (threadIdx.x < 16) lut[threadIdx.x] = square_lut((int)threadIdx.x);
+    for (uint32_t i = threadIdx.x; i < 2048; i += blockDim.x) sel8[i] = (uint8_t)kth_in_byte(i >> 3, i & 7);
+    __syncthreads();
+}
+
+// add a lane's tallies for `root`; lanes of the calling (converged or not) group that
+// share a root are summed first so that one lane per root issues the atomics
+__device__ __forceinline__ void flush_tallies(const PlayoutArgs &a, uint32_t root, uint32_t n, uint32_t p0, uint32_t dr)
+{
+    unsigned active = __activemask();
+    unsigned peers = __match_any_sync(active, root);
+    uint32_t sn = __reduce_add_sync(peers, n), sp0 = __reduce_add_sync(peers, p0), sdr = __reduce_add_sync(peers, dr);
+    if ((unsigned)(__ffs(peers) - 1) == (threadIdx.x & 31u) && sn) {
+        if (a.wins_p0 && sp0) atomicAdd(a.wins_p0 + root, sp0);
+        if (a.wins_p1 && sn - sp0 - sdr) atomicAdd(a.wins_p1 + root, sn - sp0 - sdr);
+        if (a.draws && sdr) atomicAdd(a.draws + root, sdr);
+    }
+}
+
+template <bool CUTOFF, bool PER_PLAYOUT>
+__global__ void __launch_bounds__(kBlock) k_playout(const PlayoutArgs a)
+{
+    __shared__ SquareLut s_lut[16];
+    __shared__ __align__(16) uint8_t s_sel8[2048];
+    fill_tables(s_lut, s_sel8);
+
+    const uint64_t tid = blockIdx.x * (uint64_t)kBlock + threadIdx.x;
+    const uint64_t begin = tid * a.chunk;
+    uint32_t remaining = 0;               // playouts this thread still has to START
+    uint32_t root = 0, j = 0;             // next playout to start = (root, j)
+    if (begin < a.total) {
+        uint64_t end = begin + a.chunk < a.total ? begin + a.chunk : a.total;
+        remaining = (uint32_t)(end - begin);
+        root = (uint32_t)(begin / a.rollouts);
+        j = (uint32_t)(begin % a.rollouts);
+    }
+
+    PlayState st = {};
+    bool active = false;
+    int a_wins = 1;                        // result (P0 view) if role A, the root's mover, wins
+    uint32_t ply = 0, block = 0;
+    uint32_t cur_root = root, cur_j = 0;   // the playout in flight
+    uint32_t acc_root = root, acc_n = 0, acc_p0 = 0, acc_dr = 0;
+
+    for (;;) {
+        // ---- 4-ply boundary: threads without a game in flight start their next one
+        if (!active && remaining) {
+            if (root != acc_root) {
+                flush_tallies(a, acc_root, acc_n, acc_p0, acc_dr);
+                acc_root = root; acc_n = acc_p0 = acc_dr = 0;
+            }
+            const uint4 *rp = reinterpret_cast<const uint4 *>(a.roots + root);
+            uint4 r0 = __ldg(rp), r1 = __ldg(rp + 1), r2 = __ldg(rp + 2);
+            st.occ2 = r0.x; st.ra_lo = r0.y; st.ra_hi = r0.z; st.rb_lo = r0.w;
+            st.rb_hi = r1.x; st.ta_lo = r1.y; st.ta_hi = r1.z; st.tb_lo = r1.w;
+            st.tb_hi = r2.x; st.lp_lo = r2.y; st.lp_hi = r2.z;
+            uint32_t flags = r2.w;
+            a_wins = (flags & 1u) ? -1 : 1;
+            cur_root = root; cur_j = j;
+            ply = 0; block = 0;
+            --remaining;
+            if (++j == a.rollouts) { j = 0; ++root; }
+            uint32_t immediate = (flags >> QK_ROOT_IMMEDIATE_SHIFT) & 3u;
+            if ((CUTOFF && a.max_plies == 0) || immediate) {
+                // nothing to play (mcts.py:412 cut-off first, then the root's own result)
+                int res = (CUTOFF && a.max_plies == 0) ? 0 : (immediate == 1 ? 1 : -1);
+                ++acc_n; acc_p0 += res > 0; acc_dr += res == 0;
+                if (PER_PLAYOUT) {
+                    size_t o = (size_t)cur_root * a.rollouts + cur_j;
+                    if (a.per_playout) a.per_playout[o] = (int8_t)res;
+                    if (a.per_plies) a.per_plies[o] = 0;
+                }
+            } else {
+                active = true;
+            }
+        }
+        if (!__any_sync(kFull, active)) {
+            if (!__any_sync(kFull, remaining != 0)) break;
+            continue;
+        }
+
+        // ---- one Philox block = four plies, roles alternate A B A B
+        const uint64_t rollout = a.first_rollout + cur_j;
+        const Philox4 rnd = stream_block(a.seed, rollout, a.root_index_base + cur_root, block);
+        ++block;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            bool blocked, win;
+            if (q & 1) ply_step<1>(st, rnd.v[q], s_lut, s_sel8, blocked, win);
+            else       ply_step<0>(st, rnd.v[q], s_lut, s_sel8, blocked, win);
+            if (active) {
+                const int mover_wins = (q & 1) ? -a_wins : a_wins;
+                int res = 0;
+                bool fin;
+                if (blocked) { res = -mover_wins; fin = true; }            // beam_search.py:641-642
+                else {
+                    ++ply;
+                    if (CUTOFF && ply >= (uint32_t)a.max_plies) { res = 0; fin = true; }   // mcts.py:412,436-437
+                    else { res = mover_wins; fin = win; }                   // beam_search.py:633-635
+                }
+                if (fin) {
+                    active = false;
+                    ++acc_n; acc_p0 += res > 0;
+                    if (CUTOFF) acc_dr += res == 0;
+                    if (PER_PLAYOUT) {
+                        size_t o = (size_t)cur_root * a.rollouts + cur_j;
+                        if (a.per_playout) a.per_playout[o] = (int8_t)res;
+                        if (a.per_plies) a.per_plies[o] = (uint8_t)ply;
+                    }
+                }
+            }
+        }
+    }
+    flush_tallies(a, acc_root, acc_n, acc_p0, acc_dr);
+}
+
+size_t playout_scratch_bytes(size_t n_roots) { return n_roots * sizeof(RootRec); }
+
+int launch_playouts(const uint4 *roots, size_t n_roots, uint32_t rollouts, uint64_t seed, uint64_t first_rollout,
+                    uint32_t root_index_base, int max_plies, uint32_t *wins_p0, uint32_t *wins_p1, uint32_t *draws,
+                    int8_t *per_playout, uint8_t *per_plies, void *rootrec_scratch, Ctx *c, cudaStream_t s)
+{
+    RootRec *recs = (RootRec *)rootrec_scratch;
+    k_prepare_roots<<<(unsigned)((n_roots + kBlock - 1) / kBlock), kBlock, 0, s>>>(roots, n_roots, recs);
+    QK_CUDA(cudaGetLastError());
+
+    PlayoutArgs a;
+    a.roots = recs;
+    a.total = (uint64_t)n_roots * rollouts;
+    a.seed = seed; a.first_rollout = first_rollout; a.rollouts = rollouts; a.root_index_base = root_index_base;
+    a.max_plies = max_plies;
+    a.wins_p0 = wins_p0; a.wins_p1 = wins_p1; a.draws = draws; a.per_playout = per_playout; a.per_plies = per_plies;
+
+    // persistent-style grid: every SM fully populated (8 CTAs x 256 threads = 64 warps),
+    // fewer CTAs only when there are not enough playouts to give each thread one
+    uint64_t max_threads = (uint64_t)c->sms * 8 * kBlock;
+    uint64_t threads = a.total < max_threads ? a.total : max_threads;
+    unsigned grid = (unsigned)((threads + kBlock - 1) / kBlock);
+    a.chunk = (a.total + (uint64_t)grid * kBlock - 1) / ((uint64_t)grid * kBlock);
+    if (a.chunk >= (1ull << 32)) { set_error("qk_playouts: more than 2^32 playouts per thread"); return QK_E_BAD_ARG; }
+
+    const bool cutoff = max_plies >= 0, pp = per_playout || per_plies;
+    if (cutoff && pp) k_playout<true, true><<<grid, kBlock, 0, s>>>(a);
+    else if (cutoff) k_playout<true, false><<<grid, kBlock, 0, s>>>(a);
+    else if (pp) k_playout<false, true><<<grid, kBlock, 0, s>>>(a);
+    else k_playout<false, false><<<grid, kBlock, 0, s>>>(a);
+    QK_CUDA(cudaGetLastError());
+    return QK_OK;
+}
+
+// ------------------------------------------------------------------ root generator
+// benchmarks/dataset.py:38-51 semantics (rejection of finished lines); see
+// include/quantik_b200.h qk_random_roots.  One thread per root; not a hot path.
+__global__ void __launch_bounds__(kBlock) k_random_roots(uint64_t seed, uint64_t first, size_t n, int min_plies, int span,
+                                                          uint4 *__restrict__ out)
+{
+    __shared__ SquareLut s_lut[16];
+    __shared__ __align__(16) uint8_t s_sel8[2048];
+    fill_tables(s_lut, s_sel8);
+    size_t ii = blockIdx.x * (size_t)kBlock + threadIdx.x;
+    if (ii >= n) return;
+    const uint64_t i = first + ii;
+    const int target = min_plies + (int)(i % (uint64_t)span);
+    const uint64_t rseed = seed ^ 0x524F4F5453ull;
+    State4 empty = { 0, 0, 0, 0 };
+    const RootRec root = make_root(empty);
+    for (uint32_t attempt = 0;; ++attempt) {
+        PlayState st = load_play_state(root);
+        State4 cur = empty;
+        bool ok = true;
+        Philox4 rnd = { { 0, 0, 0, 0 } };
+        for (int ply = 0; ply < target && ok; ++ply) {
+            if ((ply & 3) == 0)
+                rnd = philox4x32_10((uint32_t)i, attempt, (uint32_t)(ply >> 2), 0u, (uint32_t)rseed, (uint32_t)(rseed >> 32));
+            bool blocked, win;
+            int action;
+            if (ply & 1) ply_step<1>(st, rnd.v[ply & 3], s_lut, s_sel8, blocked, win, &action);
+            else         ply_step<0>(st, rnd.v[ply & 3], s_lut, s_sel8, blocked, win, &action);
+            if (blocked || win) { ok = false; break; }
+            cur = apply_action(cur, ply & 1, action);
+        }
+        if (ok) {   // the side to move at the root must still have a move
+            uint32_t r_lo = (target & 1) ? st.rb_lo : st.ra_lo, r_hi = (target & 1) ? st.rb_hi : st.ra_hi;
+            ok = (~(st.occ2 | r_lo) | ~(st.occ2 | r_hi)) != 0;
+        }
+        if (ok) { out[ii] = make_uint4(cur.x, cur.y, cur.z, cur.w); return; }
+    }
+}
+
+int launch_random_roots(uint64_t seed, uint64_t first, size_t n, int min_plies, int span, uint4 *out, Ctx *c, cudaStream_t s)
+{
+    (void)c;
+    k_random_roots<<<(unsigned)((n + kBlock - 1) / kBlock), kBlock, 0, s>>>(seed, first, n, min_plies, span, out);
+    QK_CUDA(cudaGetLastError());
+    return QK_OK;
+}
+
+}  // namespace qk

@@ -1,0 +1,266 @@
+"""Batched hot-path operations over N x 8 uint16 state buffers.
+
+Inputs may be numpy arrays (host: staged by the library, call returns when the
+result is in place) or CUDA torch tensors (device: zero-copy, asynchronous on
+torch's current stream).  Outputs come back in the same kind of container.
+
+The buffer layout is the reference's batch wire format
+(``storage/compact_state.py:125-147``: N concatenated ``<8H`` payloads).
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+
+from . import _native as N
+
+SEED_DEFAULT = 0x5155414E54494B31  # "QUANTIK1"
+
+try:  # torch is plumbing only (device buffers, streams); numpy-only use works without it
+    import torch
+except Exception:  # pragma: no cover
+    torch = None
+
+
+def _is_torch(x) -> bool:
+    return torch is not None and isinstance(x, torch.Tensor)
+
+
+class _Buf:
+    """pointer + owner of one argument"""
+
+    __slots__ = ("ptr", "obj", "n")
+
+    def __init__(self, ptr, obj, n):
+        self.ptr, self.obj, self.n = ptr, obj, n
+
+
+def _states_in(x) -> Tuple[_Buf, bool, int]:
+    """-> (buffer, on_device, device ordinal)"""
+    if _is_torch(x):
+        if not x.is_cuda:
+            return _states_in(x.numpy())
+        if not x.is_contiguous():
+            x = x.contiguous()
+        nbytes = x.numel() * x.element_size()
+        if nbytes % 16:
+            raise ValueError("state tensor must hold a whole number of 16-byte states")
+        return _Buf(x.data_ptr(), x, nbytes // 16), True, x.device.index or 0
+    a = np.ascontiguousarray(x, dtype=np.uint16)
+    if a.ndim == 1:
+        if a.size % 8:
+            raise ValueError("Invalid bitboard data")  # core.py:30-31
+        a = a.reshape(-1, 8)
+    if a.ndim != 2 or a.shape[1] != 8:
+        raise ValueError("states must have shape (N, 8)")
+    return _Buf(a.ctypes.data, a, a.shape[0]), False, 0
+
+
+def _out(shape, dtype, like_dev: bool, dev: int):
+    if like_dev:
+        tdt = {np.uint8: torch.uint8, np.int8: torch.int8, np.uint16: torch.int16, np.uint32: torch.int32,
+               np.uint64: torch.int64}[dtype]
+        t = torch.empty(shape, dtype=tdt, device=f"cuda:{dev}")
+        return _Buf(t.data_ptr(), t, t.shape[0] if t.ndim else 1)
+    a = np.empty(shape, dtype)
+    return _Buf(a.ctypes.data, a, a.shape[0] if a.ndim else 1)
+
+
+def _aux_in(x, dtype, on_dev: bool, dev: int) -> _Buf:
+    if x is None:
+        return _Buf(None, None, 0)
+    if _is_torch(x) and x.is_cuda:
+        x = x.contiguous()
+        return _Buf(x.data_ptr(), x, x.numel())
+    a = np.ascontiguousarray(x.cpu().numpy() if _is_torch(x) else x, dtype=dtype)
+    return _Buf(a.ctypes.data, a, a.size)
+
+
+def _stream(on_dev: bool, dev: int):
+    if on_dev:
+        return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    return None
+
+
+def _dev(device: Optional[int], on_dev: bool, dev: int) -> int:
+    return dev if on_dev else (0 if device is None else int(device))
+
+
+# ----------------------------------------------------------------------------- primitives
+def movegen_masks(states, device: Optional[int] = None):
+    """generate_legal_moves for every state -> (action_mask u64, to_move u8, status u8).
+
+    Replaces ``move.generate_legal_moves`` (move.py:199-268): bit ``shape*16+pos`` of the mask
+    is a legal move of ``to_move``; an invalid state gives mask 0 / to_move 0 (move.py:223-225)
+    with ``status`` = the ``ValidationResult`` code (state_validator.py:16-27)."""
+    s, on_dev, d = _states_in(states)
+    d = _dev(device, on_dev, d)
+    lib = N.init(d)
+    mask, tm, st = _out((s.n,), np.uint64, on_dev, d), _out((s.n,), np.uint8, on_dev, d), _out((s.n,), np.uint8, on_dev, d)
+    N.check(lib.qk_movegen_masks(s.ptr, s.n, mask.ptr, tm.ptr, st.ptr, d, _stream(on_dev, d)))
+    return mask.obj, tm.obj, st.obj
+
+
+def apply_moves(states, actions, device: Optional[int] = None):
+    """apply_move (move.py:135-166) of action ``shape*16+pos`` by the side to move."""
+    s, on_dev, d = _states_in(states)
+    d = _dev(device, on_dev, d)
+    lib = N.init(d)
+    a = _aux_in(actions, np.uint8, on_dev, d)
+    if a.n != s.n:
+        raise ValueError("one action per state required")
+    out = _out((s.n, 8), np.uint16, on_dev, d)
+    N.check(lib.qk_apply_moves(s.ptr, a.ptr, s.n, out.ptr, d, _stream(on_dev, d)))
+    return out.obj
+
+
+def win_status(states, device: Optional[int] = None):
+    """check_game_winner (game_utils.py:161-189) -> WinStatus codes."""
+    s, on_dev, d = _states_in(states)
+    d = _dev(device, on_dev, d)
+    lib = N.init(d)
+    out = _out((s.n,), np.uint8, on_dev, d)
+    N.check(lib.qk_win_status(s.ptr, s.n, out.ptr, d, _stream(on_dev, d)))
+    return out.obj
+
+
+def canonical_payloads(states, color_swap: bool = False, want_transform: bool = False, device: Optional[int] = None):
+    """find_canonical_form (symmetry.py:289-354) -> (N, 8) canonical bitboards
+    [, transform codes d4 | cs<<3 | perm[i] << (4+2i)]."""
+    s, on_dev, d = _states_in(states)
+    d = _dev(device, on_dev, d)
+    lib = N.init(d)
+    out = _out((s.n, 8), np.uint16, on_dev, d)
+    tr = _out((s.n,), np.uint16, on_dev, d) if want_transform else _Buf(None, None, 0)
+    N.check(lib.qk_canonical(s.ptr, s.n, int(bool(color_swap)), out.ptr, tr.ptr, d, _stream(on_dev, d)))
+    return (out.obj, tr.obj) if want_transform else out.obj
+
+
+def canonical_keys(states, device: Optional[int] = None):
+    """State.canonical_key (core.py:171-180) for a host batch -> list of 18-byte keys."""
+    pay = canonical_payloads(np.asarray(states, dtype=np.uint16), device=device)
+    raw = np.ascontiguousarray(pay).astype("<u2").tobytes()
+    return [b"\x01\x02" + raw[16 * i:16 * i + 16] for i in range(len(pay))]
+
+
+def orbit_sizes(states, device: Optional[int] = None):
+    """count_orbit_size (symmetry.py:356-396)."""
+    s, on_dev, d = _states_in(states)
+    d = _dev(device, on_dev, d)
+    lib = N.init(d)
+    out = _out((s.n,), np.uint8, on_dev, d)
+    N.check(lib.qk_orbit_size(s.ptr, s.n, out.ptr, d, _stream(on_dev, d)))
+    return out.obj
+
+
+def encode_transform(d4: int, color_swap: bool, perm) -> int:
+    return int(d4) | (int(bool(color_swap)) << 3) | sum(int(p) << (4 + 2 * i) for i, p in enumerate(perm))
+
+
+def decode_transform(code: int):
+    code = int(code)
+    return code & 7, bool(code & 8), tuple((code >> (4 + 2 * i)) & 3 for i in range(4))
+
+
+def apply_symmetry(states, transforms, device: Optional[int] = None):
+    """apply_symmetry (symmetry.py:252-287) with one transform code per state."""
+    s, on_dev, d = _states_in(states)
+    d = _dev(device, on_dev, d)
+    lib = N.init(d)
+    t = _aux_in(transforms, np.uint16, on_dev, d)
+    if t.n != s.n:
+        raise ValueError("one transform per state required")
+    out = _out((s.n, 8), np.uint16, on_dev, d)
+    N.check(lib.qk_apply_symmetry(s.ptr, t.ptr, s.n, out.ptr, d, _stream(on_dev, d)))
+    return out.obj
+
+
+def canon_dedup(states, mult=None, color_swap: bool = False, cap: Optional[int] = None, device: Optional[int] = None):
+    """Canonicalise, merge equal payloads, sum multiplicities (game_stats.py:487-505).
+    -> (unique payloads sorted in byte order (U, 8), multiplicities (U,))."""
+    s, on_dev, d = _states_in(states)
+    d = _dev(device, on_dev, d)
+    lib = N.init(d)
+    m = _aux_in(mult, np.uint64, on_dev, d)
+    cap = s.n if cap is None else int(cap)
+    uniq = _out((cap, 8), np.uint16, on_dev, d)
+    um = _out((cap,), np.uint64, on_dev, d)
+    nu = ctypes.c_size_t(0)
+    N.check(lib.qk_canon_dedup(s.ptr, m.ptr, s.n, int(bool(color_swap)), uniq.ptr, um.ptr, cap, ctypes.byref(nu),
+                               d, _stream(on_dev, d)))
+    return uniq.obj[:nu.value], um.obj[:nu.value]
+
+
+# ----------------------------------------------------------------------------- playouts
+def playouts(roots, rollouts: int, seed: int = SEED_DEFAULT, max_plies: int = -1, first_rollout: int = 0,
+             root_index_base: int = 0, per_playout: bool = False, device: Optional[int] = None) -> Dict[str, object]:
+    """``rollouts`` uniform-random playouts from every root.
+
+    max_plies < 0: BeamSearchEngine._rollout semantics (beam_search.py:624-645), results +-1.
+    max_plies >= 0: MCTSEngine._simulate semantics (mcts.py:385-437), 0 after max_plies moves.
+    Returns wins_p0 / wins_p1 / draws (u32 per root) and, if ``per_playout``, ``outcome``
+    (int8, P0 view) and ``plies`` (u8) of shape (n_roots, rollouts)."""
+    s, on_dev, d = _states_in(roots)
+    d = _dev(device, on_dev, d)
+    lib = N.init(d)
+    n = s.n
+    w0, w1, dr = (_out((n,), np.uint32, on_dev, d) for _ in range(3))
+    oc = _out((n, rollouts), np.int8, on_dev, d) if per_playout else _Buf(None, None, 0)
+    pl = _out((n, rollouts), np.uint8, on_dev, d) if per_playout else _Buf(None, None, 0)
+    N.check(lib.qk_playouts_ex(s.ptr, n, int(rollouts), int(seed) & 0xFFFFFFFFFFFFFFFF, int(first_rollout),
+                               int(root_index_base), int(max_plies), w0.ptr, w1.ptr, dr.ptr, oc.ptr, pl.ptr,
+                               d, _stream(on_dev, d)))
+    out = {"wins_p0": w0.obj, "wins_p1": w1.obj, "draws": dr.obj}
+    if per_playout:
+        out["outcome"], out["plies"] = oc.obj, pl.obj
+    return out
+
+
+def random_roots(n: int, seed: int = SEED_DEFAULT, first: int = 0, min_plies: int = 5, span: int = 7,
+                 device: Optional[int] = None, as_torch: bool = False):
+    """Mid-game root generator of BASELINE config 4 (benchmarks/dataset.py:38-51 rejection rule)."""
+    d = 0 if device is None else int(device)
+    lib = N.init(d)
+    out = _out((n, 8), np.uint16, as_torch, d)
+    N.check(lib.qk_random_roots(int(seed) & 0xFFFFFFFFFFFFFFFF, int(first), n, int(min_plies), int(span), out.ptr,
+                                d, _stream(as_torch, d)))
+    return out.obj
+
+
+# ----------------------------------------------------------------------------- perft
+def perft(roots, depth: int, mult=None, device: Optional[int] = None) -> Dict[str, np.ndarray]:
+    """Raw tree walk with SymmetryTable's counting rules (game_stats.py:384-485).
+    -> uint64[depth+1] arrays nodes, wins_p0, wins_p1, blocked_p0_loses, blocked_p1_loses."""
+    s, on_dev, d = _states_in(roots)
+    d = _dev(device, on_dev, d)
+    lib = N.init(d)
+    m = _aux_in(mult, np.uint64, on_dev, d)
+    if mult is not None and m.n != s.n:
+        raise ValueError("one multiplicity per root required")
+    arrs = [np.zeros(depth + 1, np.uint64) for _ in range(5)]
+    N.check(lib.qk_perft(s.ptr, m.ptr, s.n, int(depth), *[a.ctypes.data for a in arrs], d, _stream(on_dev, d)))
+    return dict(zip(["nodes", "wins_p0", "wins_p1", "blocked_p0_loses", "blocked_p1_loses"], arrs))
+
+
+def symmetry_table_rows(p: Dict[str, np.ndarray]):
+    """Re-express perft counters from the EMPTY board in the reference's table convention
+    (GAME_TREE_ANALYSIS.md:4-11): row d = [total_legal_moves, p0_wins, p1_wins, ongoing], where a
+    blocked mover at depth d-1 is booked as a win of the other player at depth d
+    (game_stats.py:397-398,426-443) and 'ongoing' = non-won positions at depth d."""
+    rows = []
+    for d in range(1, len(p["nodes"])):
+        w0 = int(p["wins_p0"][d]) + int(p["blocked_p1_loses"][d - 1])
+        w1 = int(p["wins_p1"][d]) + int(p["blocked_p0_loses"][d - 1])
+        ongoing = int(p["nodes"][d]) - int(p["wins_p0"][d]) - int(p["wins_p1"][d])
+        rows.append([int(p["nodes"][d]), w0, w1, ongoing])
+    return rows
+
+
+def int_issue_peak(device: int = 0):
+    """Measured integer issue rates (lane-ops/s): pure LOP3 stream, LOP3+IMAD mix."""
+    lib = N.init(device)
+    a, m = ctypes.c_double(), ctypes.c_double()
+    N.check(lib.qk_int_issue_peak(device, ctypes.byref(a), ctypes.byref(m)))
+    return {"alu": a.value, "mixed": m.value}

@@ -7,6 +7,7 @@
 #ifdef QK_HOSTSIM_PLAYOUT
 #include "qk_playout_core.cuh"
 #endif
+#include "qk_perft_core.cuh"
 
 using namespace qk;
 static State4 ld(const uint16_t *p) { State4 s = { (uint32_t)p[0] | ((uint32_t)p[1] << 16), (uint32_t)p[2] | ((uint32_t)p[3] << 16),
@@ -30,6 +31,8 @@ void hs_apply_symmetry(const uint16_t *s, const uint32_t *tr, size_t n, uint16_t
 uint16_t hs_d4(uint16_t v, int d4) { return (uint16_t)d4_apply((uint32_t)v, d4); }
 void hs_apply(const uint16_t *s, const uint8_t *a, size_t n, uint16_t *out)
 { for (size_t i = 0; i < n; ++i) { State4 x = ld(s + 8 * i); int p = 0; if (validate(x, &p) != 0) p = 0; st(out + 8 * i, apply_action(x, p, a[i])); } }
+void hs_leaf_parent(const uint16_t *s, size_t n, uint8_t *mover, uint8_t *moves, uint8_t *wins)
+{ for (size_t i = 0; i < n; ++i) { int m, w; mover[i] = leaf_parent_counts(ld(s + 8 * i), m, w); moves[i] = m; wins[i] = w; } }
 int hs_select(uint32_t lo, uint32_t hi, int k) { return select_bit64(lo, hi, popc(lo), k); }
 #ifdef QK_HOSTSIM_PLAYOUT
 void hs_playouts(const uint16_t *roots, size_t n_roots, uint32_t rollouts, uint64_t seed, uint64_t first, uint32_t root_base,

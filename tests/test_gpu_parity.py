@@ -1,0 +1,361 @@
+"""GPU tier: the CUDA path, called through the C-ABI (quantik_b200.batch -> libquantik_b200.so),
+against (1) golden vectors produced by the reference itself, (2) the pinned C oracle on seeded
+inputs, (3) the reference's published tables, (4) size-independent properties at full size.
+Everything here is integer work: the bar is bit-exact."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+import oracle as O
+import quantik_b200 as Q
+from quantik_b200 import batch as B
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+SEED = Q.SEED_DEFAULT
+
+
+def _npz(name):
+    return np.load(os.path.join(G, name))
+
+
+def _meta():
+    return json.load(open(os.path.join(G, "reference_meta.json")))
+
+
+def _enc(t):
+    t = t.astype(np.uint32)
+    return (t[:, 0] | (t[:, 1] << 3) | (t[:, 2] << 4) | (t[:, 3] << 6) | (t[:, 4] << 8) | (t[:, 5] << 10)).astype(np.uint16)
+
+
+def _random_positions(n, seed=1234):
+    """reachable positions of every depth + corrupted ones, generated with the oracle"""
+    a = O.make_roots(n // 2, seed=seed, min_plies=0, span=13)
+    b = a[: n // 4].copy()
+    rng = np.random.default_rng(seed)
+    b[np.arange(len(b)), rng.integers(0, 8, len(b))] ^= (1 << rng.integers(0, 16, len(b))).astype(np.uint16)
+    c = (rng.integers(0, 65536, (n // 4, 8)) & rng.integers(0, 65536, (n // 4, 8)) & rng.integers(0, 65536, (n // 4, 8))).astype(np.uint16)
+    return np.ascontiguousarray(np.concatenate([a, b, c]))
+
+
+# ----------------------------------------------------------------------------- primitives
+def test_primitives_vs_reference_goldens():
+    d = _npz("states_reference.npz")
+    s = d["states"]
+    mask, to_move, status = B.movegen_masks(s)
+    assert np.array_equal(mask, d["mask"]) and np.array_equal(to_move, d["to_move"]) and np.array_equal(status, d["v_code"])
+    assert np.array_equal(B.win_status(s), d["win"])
+    c, t = B.canonical_payloads(s, want_transform=True)
+    assert np.array_equal(c, d["canon192"]) and np.array_equal(t, _enc(d["tr192"]))
+    assert np.array_equal(B.canonical_payloads(s), d["canon192"])
+    c, t = B.canonical_payloads(s, color_swap=True, want_transform=True)
+    assert np.array_equal(c, d["canon384"]) and np.array_equal(t, _enc(d["tr384"]))
+    assert np.array_equal(B.canonical_payloads(s, color_swap=True), d["canon384"])
+    assert np.array_equal(B.orbit_sizes(s), d["orbit"])
+
+
+def test_primitives_vs_oracle_large_random():
+    s = _random_positions(200_000)
+    mask, to_move, status = B.movegen_masks(s)
+    om, ot, os_ = O.movegen_masks(s)
+    assert np.array_equal(mask, om) and np.array_equal(to_move, ot) and np.array_equal(status, os_)
+    assert len(np.unique(status)) >= 4          # several ValidationResult codes are exercised
+    assert np.array_equal(B.win_status(s), O.win_status(s))
+    sub = s[:60_000]
+    assert np.array_equal(B.canonical_payloads(sub), O.canonical(sub))
+    assert np.array_equal(B.canonical_payloads(sub[:20_000], color_swap=True), O.canonical(sub[:20_000], True))
+    assert np.array_equal(B.orbit_sizes(sub[:20_000]), O.orbit_size(sub[:20_000]))
+    # apply_moves: every legal move of 2000 positions, side to move and explicit player
+    valid = s[(status == 0) & (mask != 0)][:2000]
+    vm, _, _ = O.movegen_masks(valid)
+    rng = np.random.default_rng(5)
+    acts = np.array([rng.choice([b for b in range(64) if (int(m) >> b) & 1]) for m in vm], np.uint8)
+    assert np.array_equal(B.apply_moves(valid, acts), O.apply_moves(valid, acts))
+    explicit = (acts | 0x80 | (rng.integers(0, 2, len(acts)) << 6)).astype(np.uint8)
+    assert np.array_equal(B.apply_moves(valid, explicit), O.apply_moves(valid, explicit))
+
+
+def test_edge_sizes():
+    e = np.zeros((0, 8), np.uint16)
+    assert len(B.win_status(e)) == 0 and len(B.canonical_payloads(e)) == 0
+    one = np.zeros((1, 8), np.uint16)
+    assert int(B.movegen_masks(one)[0][0]) == 0xFFFFFFFFFFFFFFFF      # test_api_portability_report.py: empty board
+    for n in (1, 31, 32, 33, 255, 257, 1000):                          # ragged tails around warp / block sizes
+        s = _random_positions(4 * n)[:n]
+        assert np.array_equal(B.canonical_payloads(s), O.canonical(s))
+        assert np.array_equal(B.movegen_masks(s)[0], O.movegen_masks(s)[0])
+
+
+def test_fixture_cases_and_api_records():
+    cases = json.load(open(os.path.join(G, "fixture_cases.json")))["cases"]
+    s = np.array([c["bb"] for c in cases], np.uint16)
+    mask, to_move, status = B.movegen_masks(s)
+    win, canon, orbit = B.win_status(s), B.canonical_payloads(s), B.orbit_sizes(s)
+    c384 = B.canonical_payloads(s, color_swap=True)
+    for i, c in enumerate(cases):
+        assert f"0x{int(mask[i]):016x}" == c["mask"] and int(to_move[i]) == c["to_move"] and int(status[i]) == c["v_code"]
+        assert int(win[i]) == c["win"] and int(orbit[i]) == c["orbit"]
+        assert (b"\x01\x02" + canon[i].astype("<u2").tobytes()).hex() == c["canonical_key"]
+        assert c384[i].tolist() == c["canon384"]
+    # the reference's cross-stack conformance record (api_portability_report.py:152-191), field by field
+    moves = {"empty": (0, 0), "mixed": (2, 12), "single": (1, 5), "single_illegal": (1, 0), "blocked": (0, 1)}
+    for rec in _meta()["api_portability_cases"]:
+        ours = Q.portability_case_report(rec["case_id"], rec["qfen"], *moves[rec["case_id"]])
+        assert ours == rec, rec["case_id"]
+
+
+def test_dataset_sample1000_sha256_and_orbit_dedup():
+    d = _npz("dataset_depth4_sample1000.npz")
+    keys = B.canonical_keys(d["states"])
+    assert hashlib.sha256(b"".join(keys)).hexdigest() == "0a2e95cb49b528c54bbf5b11e55b72c7f71b7cdb388205787f0b1ca72684fa7e"
+    assert len(set(keys)) == 1000
+    assert int(np.asarray(B.orbit_sizes(d["states"])).astype(int).sum()) == 153592
+    # the full 192-orbit of every position dedups back to the same 1000 payloads, 192 each
+    codes = np.array([B.encode_transform(d4, False, O.perm(pi)) for d4 in range(8) for pi in range(24)], np.uint16)
+    images = B.apply_symmetry(np.repeat(d["states"], 192, axis=0), np.tile(codes, 1000))
+    assert len(np.unique(images.view(np.uint8).reshape(-1, 16), axis=0)) == 153592
+    uniq, mult = B.canon_dedup(images)
+    want = d["canon192"][np.lexsort(d["canon192"].astype("<u2").view(np.uint8).reshape(-1, 16).T[::-1])]
+    assert np.array_equal(uniq, want) and np.all(mult == 192)
+
+
+def test_symmetry_images_and_single_state_api():
+    g = _npz("symmetry_images.npz")
+    assert np.array_equal(B.apply_symmetry(g["states"], _enc(g["transform"])), g["image"])
+    # single-state mirror of the reference API
+    st = Q.State.from_qfen("A.bC/..../d..B/...a")
+    assert st.canonical_key().hex() == "010200000001010008000008020000000010" and st.symmetry_count() == 192
+    assert Q.State.empty().canonical_key() == b"\x01\x02" + b"\x00" * 16           # tests/test_core.py:38-47
+    bb = (1, 0, 0, 2048, 0, 2, 64, 0)
+    player, by_shape = Q.generate_legal_moves(bb)
+    assert player == 0 and sorted(by_shape) == [0, 1, 2, 3] and sum(len(v) for v in by_shape.values()) == 35
+    assert Q.generate_legal_moves(bb, player_id=1) == (0, {})                        # move.py:228-229
+    assert Q.generate_legal_moves((1, 1, 0, 0, 0, 0, 0, 0)) == (0, {})               # move.py:223-225
+    assert Q.apply_move(bb, Q.Move(0, 2, 12)) == (1, 0, 4096, 2048, 0, 2, 64, 0)
+    assert Q.check_game_winner(Q.bb_from_qfen("AbCd/..../..../....")) == Q.WinStatus.PLAYER_1_WINS
+    assert Q.has_winning_line(bb) is False
+    canon, tr = Q.SymmetryHandler.find_canonical_form((0, 8, 0, 0, 0, 0, 4, 0))
+    assert canon == (0, 0, 0, 4096, 0, 0, 256, 0) and (tr.d4_index, tr.color_swap, tr.shape_perm) == (6, False, (0, 3, 2, 1))
+    assert Q.SymmetryHandler.apply_symmetry((0, 8, 0, 0, 0, 0, 4, 0), tr) == canon
+    # forbidden squares for an opponent piece on square 0 (tests/test_move.py:225-276)
+    _, moves = Q.generate_legal_moves((1, 0, 0, 0, 0, 0, 0, 0))
+    assert sorted(set(range(16)) - {m.position for m in moves[0]}) == [0, 1, 2, 3, 4, 5, 8, 12]
+    # first moves: 64 -> 3 canonical classes of multiplicity 16/16/32 (tests/test_game_stats.py:40-73)
+    firsts = np.array([Q.apply_move((0,) * 8, Q.Move(0, s, p)) for s in range(4) for p in range(16)], np.uint16)
+    uniq, mult = B.canon_dedup(firsts)
+    assert len(uniq) == 3 and sorted(mult.tolist()) == [16, 16, 32]
+
+
+def test_canon_dedup_vs_oracle_with_multiplicities():
+    s = _random_positions(120_000, seed=77)[:60_000]      # reachable states: many symmetric duplicates
+    mult = np.random.default_rng(3).integers(1, 1000, len(s)).astype(np.uint64)
+    uniq, um = B.canon_dedup(s, mult)
+    oc = O.canonical(s).astype("<u2").view(np.uint8).reshape(-1, 16)
+    keys, inv = np.unique(oc, axis=0, return_inverse=True)
+    want_mult = np.zeros(len(keys), np.uint64)
+    np.add.at(want_mult, inv.ravel(), mult)
+    assert np.array_equal(uniq.astype("<u2").view(np.uint8).reshape(-1, 16), keys)
+    assert np.array_equal(um, want_mult)
+    ones = np.full((5, 8), 0xFFFF, np.uint16)              # the payload that equals the table's empty marker
+    uniq, um = B.canon_dedup(np.concatenate([s[:100], ones]))
+    assert np.array_equal(uniq[-1], ones[0]) and int(um[-1]) == 5
+
+
+# ----------------------------------------------------------------------------- playouts
+def test_playouts_vs_reference_rules_goldens():
+    p = _npz("playouts_philox.npz")
+    seed = int(p["seed"])
+    e = np.zeros((1, 8), np.uint16)
+    n = len(p["empty_outcome"])
+    r = B.playouts(e, n, seed, per_playout=True)
+    assert np.array_equal(r["outcome"][0], p["empty_outcome"]) and np.array_equal(r["plies"][0], p["empty_plies"])
+    assert int(r["wins_p0"][0]) == int((p["empty_outcome"] > 0).sum()) and int(r["wins_p1"][0]) == int((p["empty_outcome"] < 0).sum())
+    r = B.playouts(p["roots"], p["roots_outcome"].shape[1], seed, first_rollout=int(p["roots_first_rollout"]),
+                   root_index_base=int(p["roots_index_base"]), per_playout=True)
+    assert np.array_equal(r["outcome"], p["roots_outcome"]) and np.array_equal(r["plies"], p["roots_plies"])
+    assert np.array_equal(r["wins_p0"], (p["roots_outcome"] > 0).sum(1))
+    for mp in (16, 12, 5, 0):                                # MCTS cut-off semantics (mcts.py:412,436-437)
+        want = p[f"cut{mp}_outcome"]
+        r = B.playouts(e, len(want), seed, max_plies=mp, per_playout=True)
+        assert np.array_equal(r["outcome"][0], want) and np.array_equal(r["plies"][0], p[f"cut{mp}_plies"])
+        assert int(r["draws"][0]) == int((want == 0).sum())
+
+
+def test_playouts_vs_oracle_per_seed_1m():
+    n = 1 << 20
+    e = np.zeros((1, 8), np.uint16)
+    g = B.playouts(e, n, SEED, per_playout=True)
+    o = O.playouts(e, n, SEED, per_playout=True)
+    assert np.array_equal(g["outcome"], o["outcome"]) and np.array_equal(g["plies"], o["plies"])
+    assert int(g["wins_p0"][0]) == int(o["wins_p0"][0]) and int(g["wins_p1"][0]) == int(o["wins_p1"][0]) and int(g["draws"][0]) == 0
+    # tallies-only kernel variant gives the same counts
+    t = B.playouts(e, n, SEED)
+    assert int(t["wins_p0"][0]) == int(o["wins_p0"][0]) and int(t["wins_p1"][0]) == int(o["wins_p1"][0])
+    # north_star: win rate within binomial 3 sigma of the reference's own RNG (MT19937 random.choice)
+    for ref in (_meta()["survey_mt19937_100k"], _meta()["mt19937_empty_board"]):
+        sigma = (0.25 / n + 0.25 / ref["n"]) ** 0.5
+        assert abs(int(t["wins_p0"][0]) / n - ref["p0_wins"] / ref["n"]) < 3 * sigma
+    lens = np.bincount(g["plies"][0], minlength=17)
+    assert lens[:4].sum() == 0 and lens[16] > 0             # games last 4..16 plies
+
+
+def test_playouts_sharding_invariance_and_mid_roots():
+    roots = O.make_roots(300, seed=SEED)
+    assert np.array_equal(B.random_roots(300, seed=SEED), roots)
+    assert np.array_equal(B.random_roots(4096, seed=99, first=1000), O.make_roots(4096, seed=99, first=1000))
+    full = B.playouts(roots, 256, SEED, per_playout=True)
+    o = O.playouts(roots, 256, SEED, per_playout=True)
+    assert np.array_equal(full["outcome"], o["outcome"]) and np.array_equal(full["plies"], o["plies"])
+    assert np.array_equal(full["wins_p0"], o["wins_p0"]) and np.array_equal(full["wins_p1"], o["wins_p1"])
+    # a root shard / rollout shard computed separately is identical to the slice of the full job
+    part = B.playouts(roots[100:200], 256, SEED, root_index_base=100, per_playout=True)
+    assert np.array_equal(part["outcome"], full["outcome"][100:200])
+    half = B.playouts(roots, 128, SEED, first_rollout=128, per_playout=True)
+    assert np.array_equal(half["outcome"], full["outcome"][:, 128:])
+    # special roots: blocked mover, already won, invalid
+    sp = np.array([Q.bb_from_qfen("A..C/bbd./CD.A/.adB"), Q.bb_from_qfen("AbCd/..../..../...."), (1, 1, 0, 0, 0, 0, 0, 0)], np.uint16)
+    g, oo = B.playouts(sp, 64, SEED, per_playout=True), O.playouts(sp, 64, SEED, per_playout=True)
+    assert np.array_equal(g["outcome"], oo["outcome"]) and np.array_equal(g["plies"], oo["plies"])
+    assert g["wins_p0"].tolist() == [64, 0, 0] and g["wins_p1"].tolist() == [0, 64, 64]
+    # cut-off on mid-game roots
+    g, oo = B.playouts(roots[:64], 128, SEED, max_plies=3, per_playout=True), O.playouts(roots[:64], 128, SEED, max_plies=3, per_playout=True)
+    assert np.array_equal(g["outcome"], oo["outcome"]) and np.array_equal(g["draws"], oo["draws"])
+
+
+def test_playouts_config4_sample_and_full_size_properties():
+    roots = B.random_roots(65536, seed=SEED)
+    assert np.array_equal(roots[:2048], O.make_roots(2048, seed=SEED))
+    mask, _, status = B.movegen_masks(roots)
+    assert np.all(status == 0) and np.all(mask != 0) and np.all(B.win_status(roots) == 0)
+    pieces = np.unpackbits(np.ascontiguousarray(roots[:4096]).view(np.uint8), axis=1).sum(1)
+    assert pieces.min() == 5 and pieces.max() == 11
+    r = B.playouts(roots, 1024, SEED)                          # BASELINE config 4: 67 108 864 playouts
+    assert np.all(r["wins_p0"].astype(np.int64) + r["wins_p1"] == 1024) and np.all(r["draws"] == 0)
+    o = O.playouts(roots[:96], 1024, SEED)                    # oracle sample, bit-exact tallies
+    assert np.array_equal(r["wins_p0"][:96], o["wins_p0"]) and np.array_equal(r["wins_p1"][:96], o["wins_p1"])
+    # BASELINE config 1 scaled up: 2^26 playouts from the empty board
+    n = 1 << 26
+    t = B.playouts(np.zeros((1, 8), np.uint16), n, SEED)
+    assert int(t["wins_p0"][0]) + int(t["wins_p1"][0]) == n and int(t["draws"][0]) == 0
+    assert abs(int(t["wins_p0"][0]) / n - 0.4867) < 0.004      # reference MT19937 estimate 0.4853..0.4881
+
+
+# ----------------------------------------------------------------------------- perft
+PUBLISHED = [  # GAME_TREE_ANALYSIS.md:4-9: total legal moves, P0 wins, P1 wins, ongoing
+    [64, 0, 0, 64], [3392, 0, 0, 3392], [167552, 0, 0, 167552], [6776960, 0, 6912, 6770048],
+    [231883776, 1050624, 0, 230833152], [6241600512, 0, 81653760, 6159946752]]
+
+
+def test_perft_empty_board_depth6_published_table():
+    e = np.zeros((1, 8), np.uint16)
+    for depth in range(0, 7):
+        p = B.perft(e, depth)
+        assert int(p["nodes"][0]) == 1
+        assert B.symmetry_table_rows(p) == PUBLISHED[:depth], depth
+        assert int(p["blocked_p0_loses"].sum()) == 0 and int(p["blocked_p1_loses"].sum()) == 0
+
+
+def test_perft_weighted_canonical_roots_and_oracle():
+    d = _npz("depth4_canonical.npz")                         # the 10 946 depth-4 classes from the reference
+    p = B.perft(d["states"], 2, d["mult"])
+    assert int(p["nodes"][0]) == 6770048
+    assert [int(p["nodes"][1]), int(p["wins_p0"][1]), int(p["wins_p1"][1])] == [231883776, 1050624, 0]
+    assert [int(p["nodes"][2]), int(p["wins_p0"][2]), int(p["wins_p1"][2])] == [6241600512, 0, 81653760]
+    # depth 7 and 8 of the published table through symmetry-weighted roots (GAME_TREE_ANALYSIS.md:10-11)
+    p = B.perft(d["states"], 4, d["mult"])
+    assert int(p["nodes"][3]) == 132400548864 and int(p["wins_p0"][3]) + int(p["blocked_p1_loses"][2]) == 3886838784
+    assert int(p["nodes"][4]) == 2097048766464 and int(p["wins_p1"][4]) + int(p["blocked_p0_loses"][3]) == 118862401536
+    assert int(p["nodes"][4]) - int(p["wins_p0"][4]) - int(p["wins_p1"][4]) == 1978186364928
+    # late-game roots exercise the blocked-mover counters; compare all five arrays with the oracle
+    roots = O.make_roots(64, seed=4242, min_plies=8, span=4)
+    mult = np.arange(1, 65, dtype=np.uint64)
+    for depth in (1, 2, 3, 5):
+        g, o = B.perft(roots, depth, mult), O.perft(roots, depth, mult)
+        for k in o:
+            assert np.array_equal(g[k], o[k]), (depth, k)
+    assert int(O.perft(roots, 5, mult)["blocked_p0_loses"].sum() + O.perft(roots, 5, mult)["blocked_p1_loses"].sum()) > 0
+    # won and invalid roots
+    sp = np.array([Q.bb_from_qfen("AbCd/..../..../...."), (1, 1, 0, 0, 0, 0, 0, 0), Q.bb_from_qfen("A..C/bbd./CD.A/.adB")], np.uint16)
+    g, o = B.perft(sp, 3), O.perft(sp, 3)
+    for k in o:
+        assert np.array_equal(g[k], o[k]), k
+
+
+def test_perft_is_symmetry_invariant():
+    roots = O.make_roots(16, seed=31, min_plies=4, span=3)
+    base = B.perft(roots, 4)
+    codes = np.full(16, B.encode_transform(3, False, (2, 0, 3, 1)), np.uint16)
+    img = B.perft(B.apply_symmetry(roots, codes), 4)
+    for k in base:
+        assert np.array_equal(base[k], img[k])
+
+
+# ----------------------------------------------------------------------------- device buffers, engines
+def test_device_tensor_path_matches_host_path():
+    import torch
+    s = _random_positions(50_000, seed=9)
+    t = torch.from_numpy(s.view(np.int16)).cuda()
+    mask, tm, st = B.movegen_masks(t)
+    hm, htm, hst = B.movegen_masks(s)
+    assert np.array_equal(mask.cpu().numpy().view(np.uint64), hm) and np.array_equal(tm.cpu().numpy(), htm)
+    assert np.array_equal(B.canonical_payloads(t).cpu().numpy().view(np.uint16), B.canonical_payloads(s))
+    roots = torch.from_numpy(O.make_roots(512).view(np.int16)).cuda()
+    with torch.cuda.stream(torch.cuda.Stream()):
+        r = B.playouts(roots, 512, SEED)
+        torch.cuda.current_stream().synchronize()
+    h = B.playouts(roots.cpu().numpy().view(np.uint16), 512, SEED)
+    assert np.array_equal(r["wins_p0"].cpu().numpy().view(np.uint32), h["wins_p0"])
+    assert np.array_equal(r["wins_p1"].cpu().numpy().view(np.uint32), h["wins_p1"])
+
+
+def test_engine_plugins():
+    class FakeState:
+        def __init__(self, bb):
+            self.bb = tuple(int(x) for x in bb)
+
+    roots = O.make_roots(5, seed=11)
+    ev = Q.GpuRolloutEvaluator(rollouts=512, seed=SEED)
+    vals = [ev(FakeState(r)) for r in roots]                 # BeamSearchConfig.evaluator protocol
+    o = O.playouts(roots, 512, SEED)
+    want = (o["wins_p0"].astype(float) - o["wins_p1"]) / 512
+    assert np.allclose(vals, want) and all(-1.0 <= v <= 1.0 for v in vals)
+    ev2 = Q.GpuRolloutEvaluator(rollouts=512, seed=SEED)
+    assert np.allclose(ev2.evaluate_many(roots), want)
+    stats = {"rollouts": 0}
+    f = Q.gpu_default_evaluate(Q.GpuRolloutEvaluator(rollouts=8, seed=SEED))
+    v = f(None, FakeState(roots[0]), 64, stats)
+    assert stats["rollouts"] == 64 and -1.0 <= v <= 1.0      # tests/test_beam_search.py:1023-1035
+
+    class Node:
+        def __init__(self, flags, depth):
+            self.flags, self.depth = flags, depth
+
+    class Tree:
+        def __init__(self, node, bb):
+            self._n, self._s = node, FakeState(bb)
+
+        def get_node(self, _):
+            return self._n
+
+        def get_state(self, _):
+            return self._s
+
+    class Cfg:
+        max_depth = 16
+
+    class Engine:
+        config = Cfg()
+
+    sim = Q.gpu_simulate(rollouts_per_leaf=256, seed=SEED)
+    eng = Engine()
+    eng.tree = Tree(Node(1 | 2, 3), roots[0])
+    assert sim(eng, 0) == 1.0                                 # terminal flag short-cut (mcts.py:396-403)
+    eng.tree = Tree(Node(0, 16), roots[0])
+    assert sim(eng, 0) == 0.0                                 # depth >= max_depth -> 0.0 (mcts.py:412,437)
+    eng.tree = Tree(Node(0, 0), np.zeros(8, np.uint16))
+    o = O.playouts(np.zeros((1, 8), np.uint16), 256, SEED, root_index_base=1, max_plies=16)
+    assert abs(sim(eng, 0) - (float(o["wins_p0"][0]) - float(o["wins_p1"][0])) / 256) < 1e-12

@@ -1,0 +1,112 @@
+"""The kernels' __host__ __device__ rule code (csrc/qk_bits.cuh, qk_playout_core.cuh,
+qk_perft_core.cuh) compiled for the CPU and checked against the reference-generated golden
+vectors and the oracle.  Catches bit-trick errors without a GPU; the GPU tier re-checks the
+same functions through the C-ABI."""
+import ctypes
+import os
+import random
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle as O
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+G = os.path.join(HERE, "golden")
+
+
+def P(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+@pytest.fixture(scope="module")
+def hs():
+    subprocess.check_call(["sh", os.path.join(HERE, "hostsim", "build.sh")])
+    lib = ctypes.CDLL(os.path.join(HERE, "hostsim", "_build", "libqk_hostsim.so"))
+    lib.hs_d4.restype = ctypes.c_uint16
+    return lib
+
+
+def enc(t):
+    t = t.astype(np.uint32)
+    return np.ascontiguousarray(t[:, 0] | (t[:, 1] << 3) | (t[:, 2] << 4) | (t[:, 3] << 6) | (t[:, 4] << 8) | (t[:, 5] << 10))
+
+
+def test_rules_primitives(hs):
+    d = np.load(os.path.join(G, "states_reference.npz"))
+    s = np.ascontiguousarray(d["states"])
+    n = len(s)
+    mask, tm, st = np.zeros(n, np.uint64), np.zeros(n, np.uint8), np.zeros(n, np.uint8)
+    hs.hs_movegen(P(s), ctypes.c_size_t(n), P(mask), P(tm), P(st))
+    assert np.array_equal(mask, d["mask"]) and np.array_equal(tm, d["to_move"]) and np.array_equal(st, d["v_code"])
+    w = np.zeros(n, np.uint8)
+    hs.hs_win(P(s), ctypes.c_size_t(n), P(w))
+    assert np.array_equal(w, d["win"])
+    for cs, key, trk in ((0, "canon192", "tr192"), (1, "canon384", "tr384")):
+        out, tr = np.zeros_like(s), np.zeros(n, np.uint32)
+        hs.hs_canonical(P(s), ctypes.c_size_t(n), cs, P(out), P(tr))
+        assert np.array_equal(out, d[key])
+        assert np.array_equal(tr, enc(d[trk]))
+    o = np.zeros(n, np.uint8)
+    hs.hs_orbit(P(s), ctypes.c_size_t(n), P(o))
+    assert np.array_equal(o, d["orbit"])
+
+
+def test_d4_maps_all_masks(hs):
+    for d4 in range(8):
+        for v in range(0, 65536, 3):
+            assert hs.hs_d4(v, d4) == O.lib().qo_permute16(v, d4)
+
+
+def test_apply_symmetry_images(hs):
+    g = np.load(os.path.join(G, "symmetry_images.npz"))
+    s = np.ascontiguousarray(g["states"])
+    out = np.zeros_like(s)
+    hs.hs_apply_symmetry(P(s), P(enc(g["transform"])), ctypes.c_size_t(len(s)), P(out))
+    assert np.array_equal(out, g["image"])
+
+
+def test_select_kth_bit(hs):
+    rng = random.Random(7)
+    for _ in range(5000):
+        m = rng.getrandbits(64) & rng.getrandbits(64)
+        if not m:
+            continue
+        k = rng.randrange(bin(m).count("1"))
+        assert hs.hs_select(m & 0xFFFFFFFF, m >> 32, k) == [b for b in range(64) if m >> b & 1][k]
+
+
+def test_playout_step_vs_reference_rules(hs):
+    p = np.load(os.path.join(G, "playouts_philox.npz"))
+    seed = int(p["seed"])
+    e = np.zeros((1, 8), np.uint16)
+
+    def run(roots, R, first, base, mp):
+        oc, pl = np.zeros((len(roots), R), np.int8), np.zeros((len(roots), R), np.uint8)
+        hs.hs_playouts(P(roots), ctypes.c_size_t(len(roots)), ctypes.c_uint32(R), ctypes.c_uint64(seed),
+                       ctypes.c_uint64(first), ctypes.c_uint32(base), ctypes.c_int(mp), P(oc), P(pl))
+        return oc, pl
+
+    oc, pl = run(e, len(p["empty_outcome"]), 0, 0, -1)
+    assert np.array_equal(oc[0], p["empty_outcome"]) and np.array_equal(pl[0], p["empty_plies"])
+    r = np.ascontiguousarray(p["roots"])
+    oc, pl = run(r, p["roots_outcome"].shape[1], int(p["roots_first_rollout"]), int(p["roots_index_base"]), -1)
+    assert np.array_equal(oc, p["roots_outcome"]) and np.array_equal(pl, p["roots_plies"])
+    for mp in (16, 12, 5, 0):
+        oc, pl = run(e, len(p[f"cut{mp}_outcome"]), 0, 0, mp)
+        assert np.array_equal(oc[0], p[f"cut{mp}_outcome"]) and np.array_equal(pl[0], p[f"cut{mp}_plies"])
+
+
+def test_leaf_parent_bulk_counts(hs):
+    d = np.load(os.path.join(G, "states_reference.npz"))
+    nv = int(d["n_valid"])
+    s = np.ascontiguousarray(d["states"][:nv][d["win"][:nv] == 0][:600])
+    n = len(s)
+    mv, mo, wi = np.zeros(n, np.uint8), np.zeros(n, np.uint8), np.zeros(n, np.uint8)
+    hs.hs_leaf_parent(P(s), ctypes.c_size_t(n), P(mv), P(mo), P(wi))
+    for i in range(n):
+        r = O.perft(s[i:i + 1], 1)
+        assert int(r["nodes"][1]) == mo[i]
+        assert int(r["wins_p0"][1]) + int(r["wins_p1"][1]) == wi[i]
+        assert (int(r["wins_p0"][1]) > 0) <= (mv[i] == 0) and (int(r["wins_p1"][1]) > 0) <= (mv[i] == 1)

@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(kBlock) k_prepare_roots(const uint4 *__restric
 __device__ __forceinline__ void fill_tables(SquareLut *lut, uint8_t *sel8)
 {
     if (threadIdx.x < 16) lut[threadIdx.x] = square_lut((int)threadIdx.x);
-    for (uint32_t i = threadIdx.x; i < 2048; i += blockDim.x) sel8[i] = (uint8_t)kth_in_byte(i >> 3, i & 7);
+    for (uint32_t i = threadIdx.x; i < 2048; i += blockDim.x) sel8[i] = (uint8_t)sel8_entry(i);
     __syncthreads();
 }
 
@@ -68,7 +68,7 @@ __device__ __forceinline__ void flush_tallies(const PlayoutArgs &a, uint32_t roo
 template <bool CUTOFF, bool PER_PLAYOUT>
 __global__ void __launch_bounds__(kBlock) k_playout(const PlayoutArgs a)
 {
-    __shared__ SquareLut s_lut[16];
+    __shared__ __align__(16) SquareLut s_lut[16];
     __shared__ __align__(16) uint8_t s_sel8[2048];
     fill_tables(s_lut, s_sel8);
 
@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(kBlock) k_playout(const PlayoutArgs a)
 
     PlayState st = {};
     bool active = false;
-    int a_wins = 1;                        // result (P0 view) if role A, the root's mover, wins
+    bool a_is_p0 = true;                   // role A (the root's mover) is player 0
     uint32_t ply = 0, block = 0;
     uint32_t cur_root = root, cur_j = 0;   // the playout in flight
     uint32_t acc_root = root, acc_n = 0, acc_p0 = 0, acc_dr = 0;
@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(kBlock) k_playout(const PlayoutArgs a)
             st.rb_hi = r1.x; st.ta_lo = r1.y; st.ta_hi = r1.z; st.tb_lo = r1.w;
             st.tb_hi = r2.x; st.lp_lo = r2.y; st.lp_hi = r2.z;
             uint32_t flags = r2.w;
-            a_wins = (flags & 1u) ? -1 : 1;
+            a_is_p0 = (flags & 1u) == 0;
             cur_root = root; cur_j = j;
             ply = 0; block = 0;
             --remaining;
@@ -136,27 +136,24 @@ __global__ void __launch_bounds__(kBlock) k_playout(const PlayoutArgs a)
             bool blocked, win;
             if (q & 1) ply_step<1>(st, rnd.v[q], s_lut, s_sel8, blocked, win);
             else       ply_step<0>(st, rnd.v[q], s_lut, s_sel8, blocked, win);
-            if (active) {
-                const int mover_wins = (q & 1) ? -a_wins : a_wins;
-                int res = 0;
-                bool fin;
-                if (blocked) { res = -mover_wins; fin = true; }            // beam_search.py:641-642
-                else {
-                    ++ply;
-                    if (CUTOFF && ply >= (uint32_t)a.max_plies) { res = 0; fin = true; }   // mcts.py:412,436-437
-                    else { res = mover_wins; fin = win; }                   // beam_search.py:633-635
-                }
-                if (fin) {
-                    active = false;
-                    ++acc_n; acc_p0 += res > 0;
-                    if (CUTOFF) acc_dr += res == 0;
-                    if (PER_PLAYOUT) {
-                        size_t o = (size_t)cur_root * a.rollouts + cur_j;
-                        if (a.per_playout) a.per_playout[o] = (int8_t)res;
-                        if (a.per_plies) a.per_plies[o] = (uint8_t)ply;
-                    }
-                }
+            // outcome bookkeeping without branches: a blocked mover loses (beam_search.py:641-642),
+            // otherwise the move is made and may hit the cut-off (mcts.py:412,436-437) or complete a
+            // line (beam_search.py:633-635)
+            const bool mover_is_p0 = (q & 1) ? !a_is_p0 : a_is_p0;
+            bool cut = false;
+            if (CUTOFF || PER_PLAYOUT) ply += blocked ? 0u : 1u;
+            if (CUTOFF) cut = !blocked && ply >= (uint32_t)a.max_plies;
+            const bool fin = active && (blocked || win || cut);
+            const bool p0_wins = (mover_is_p0 != blocked) && !cut;
+            acc_n += fin ? 1u : 0u;
+            acc_p0 += (fin && p0_wins) ? 1u : 0u;
+            if (CUTOFF) acc_dr += (fin && cut) ? 1u : 0u;
+            if (PER_PLAYOUT && fin) {
+                size_t o = (size_t)cur_root * a.rollouts + cur_j;
+                if (a.per_playout) a.per_playout[o] = (int8_t)(cut ? 0 : (p0_wins ? 1 : -1));
+                if (a.per_plies) a.per_plies[o] = (uint8_t)ply;
             }
+            active = active && !fin;
         }
     }
     flush_tallies(a, acc_root, acc_n, acc_p0, acc_dr);
@@ -179,19 +176,20 @@ int launch_playouts(const uint4 *roots, size_t n_roots, uint32_t rollouts, uint6
     a.max_plies = max_plies;
     a.wins_p0 = wins_p0; a.wins_p1 = wins_p1; a.draws = draws; a.per_playout = per_playout; a.per_plies = per_plies;
 
-    // persistent-style grid: every SM fully populated (8 CTAs x 256 threads = 64 warps),
-    // fewer CTAs only when there are not enough playouts to give each thread one
-    uint64_t max_threads = (uint64_t)c->sms * 8 * kBlock;
+    const bool cutoff = max_plies >= 0, pp = per_playout || per_plies;
+    void (*kernel)(const PlayoutArgs) = cutoff ? (pp ? k_playout<true, true> : k_playout<true, false>)
+                                               : (pp ? k_playout<false, true> : k_playout<false, false>);
+    // persistent grid: exactly as many CTAs as are resident at once (no second wave), fewer only
+    // when there are not enough playouts to give each thread one
+    int per_sm = 0;
+    QK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, (int)kBlock, 0));
+    if (per_sm < 1) per_sm = 1;
+    uint64_t max_threads = (uint64_t)c->sms * per_sm * kBlock;
     uint64_t threads = a.total < max_threads ? a.total : max_threads;
     unsigned grid = (unsigned)((threads + kBlock - 1) / kBlock);
     a.chunk = (a.total + (uint64_t)grid * kBlock - 1) / ((uint64_t)grid * kBlock);
     if (a.chunk >= (1ull << 32)) { set_error("qk_playouts: more than 2^32 playouts per thread"); return QK_E_BAD_ARG; }
-
-    const bool cutoff = max_plies >= 0, pp = per_playout || per_plies;
-    if (cutoff && pp) k_playout<true, true><<<grid, kBlock, 0, s>>>(a);
-    else if (cutoff) k_playout<true, false><<<grid, kBlock, 0, s>>>(a);
-    else if (pp) k_playout<false, true><<<grid, kBlock, 0, s>>>(a);
-    else k_playout<false, false><<<grid, kBlock, 0, s>>>(a);
+    kernel<<<grid, kBlock, 0, s>>>(a);
     QK_CUDA(cudaGetLastError());
     return QK_OK;
 }
@@ -202,7 +200,7 @@ int launch_playouts(const uint4 *roots, size_t n_roots, uint32_t rollouts, uint6
 __global__ void __launch_bounds__(kBlock) k_random_roots(uint64_t seed, uint64_t first, size_t n, int min_plies, int span,
                                                           uint4 *__restrict__ out)
 {
-    __shared__ SquareLut s_lut[16];
+    __shared__ __align__(16) SquareLut s_lut[16];
     __shared__ __align__(16) uint8_t s_sel8[2048];
     fill_tables(s_lut, s_sel8);
     size_t ii = blockIdx.x * (size_t)kBlock + threadIdx.x;

@@ -53,17 +53,21 @@ QK_HD Philox4 stream_block(uint64_t seed, uint64_t rollout, uint32_t root_index,
 }
 
 // ---------------------------------------------------------------- per-square table
-// x = scope of square p (its row | column | zone), y = its three line bits; both
-// replicated in the two 16-bit lanes so one AND with the lane mask routes them.
-struct SquareLut { uint32_t scope2, lines2; };
+// scope2 = scope of square p (its row | column | zone), lines2 = its three line bits,
+// bit2 = the square itself; all replicated in the two 16-bit lanes so one AND with the
+// lane mask routes them.  16 bytes: one LDS.128 per ply.
+struct __attribute__((aligned(16))) SquareLut { uint32_t scope2, lines2, bit2, pad; };
 
 QK_HD SquareLut square_lut(int p)
 {
     uint32_t scope = (0xFu << (p & 12)) | (0x1111u << (p & 3)) | (0x33u << (p & 10));
     uint32_t lines = (1u << (p >> 2)) | (16u << (p & 3)) | (256u << (((p >> 3) << 1) | ((p >> 1) & 1)));
-    SquareLut e = { (scope & 0xFFFFu) * 0x10001u, lines * 0x10001u };
+    SquareLut e = { (scope & 0xFFFFu) * 0x10001u, lines * 0x10001u, 0x00010001u << p, 0u };
     return e;
 }
+// sel8 table entry: byte offset (16 * position) into the SquareLut table of the k-th set bit
+// of a byte (k < popcount), else 0
+QK_HD uint32_t sel8_entry(uint32_t index) ;
 // position of the k-th set bit of a byte (k < popcount), else 0
 QK_HD uint32_t kth_in_byte(uint32_t byte, uint32_t k)
 {
@@ -71,6 +75,8 @@ QK_HD uint32_t kth_in_byte(uint32_t byte, uint32_t k)
         if ((byte >> b) & 1u) { if (k == 0) return b; --k; }
     return 0;
 }
+
+QK_HD uint32_t sel8_entry(uint32_t index) { return 16u * kth_in_byte(index >> 3, index & 7u); }
 
 // ---------------------------------------------------------------- root record
 // What k_prepare_roots writes and k_playout reloads at every refill (48 B = 3 x uint4).
@@ -160,13 +166,14 @@ QK_HD void ply_step(PlayState &st, uint32_t rnd, const SquareLut *lut, const uin
     bool hib = k >= c;                                    // squares 8..15
     k -= hib ? c : 0;
     uint32_t byte = (hib ? (w >> 8) : w) & 0xFFu;
-    uint32_t p = (uint32_t)sel8[(byte << 3) | (uint32_t)(k & 7)] + (hib ? 8u : 0u);
+    // byte offset of the chosen square's entry in the SquareLut table (16 B per square)
+    uint32_t off = ((uint32_t)sel8[(byte << 3) | (uint32_t)(k & 7)] + (hib ? 128u : 0u)) & 0xF0u;
 
     // apply_move + incremental rule state
     uint32_t lane = odd ? 0xFFFF0000u : 0x0000FFFFu;
     uint32_t l_lo = up ? 0u : lane, l_hi = up ? lane : 0u;
-    SquareLut e = lut[p & 15u];
-    st.occ2 |= 0x00010001u << (p & 15u);
+    const SquareLut e = *reinterpret_cast<const SquareLut *>(reinterpret_cast<const char *>(lut) + off);
+    st.occ2 |= e.bit2;
     ro_lo |= e.scope2 & l_lo;  ro_hi |= e.scope2 & l_hi;  // opponent may no longer use this shape in my scope
     rm_lo |= tm_lo & l_lo;     rm_hi |= tm_hi & l_hi;     // second piece of the shape: lane exhausted for me
     tm_lo |= l_lo;             tm_hi |= l_hi;
@@ -175,7 +182,7 @@ QK_HD void ply_step(PlayState &st, uint32_t rnd, const SquareLut *lut, const uin
     // has_winning_line: a line holding all four shapes
     uint32_t all4 = st.lp_lo & st.lp_hi;
     win = (all4 & (all4 >> 16)) != 0;
-    if (action) *action = (int)(p & 15u) + (odd ? 16 : 0) + (up ? 32 : 0);
+    if (action) *action = (int)(off >> 4) + (odd ? 16 : 0) + (up ? 32 : 0);
 }
 
 // ---------------------------------------------------------------- scalar playout
@@ -191,7 +198,7 @@ QK_HD int playout_one(const RootRec &root, uint64_t seed, uint64_t rollout, uint
     static bool ready = false;
     if (!ready) {
         for (int p = 0; p < 16; ++p) h_lut[p] = square_lut(p);
-        for (uint32_t i = 0; i < 2048; ++i) h_sel8[i] = (uint8_t)kth_in_byte(i >> 3, i & 7);
+        for (uint32_t i = 0; i < 2048; ++i) h_sel8[i] = (uint8_t)sel8_entry(i);
         ready = true;
     }
     if (!lut) { lut = h_lut; sel8 = h_sel8; }

@@ -36,9 +36,11 @@ METRIC = "random playouts/sec (uniform random, empty board, to terminal)"
 UNIT = "playouts/s"
 PLAYOUTS_PER_STEP = 1 << 30
 SEED = 0x5155414E54494B31
-# SURVEY 8d fixed integer-op model (DESIGN.md "Roofline"): 230 lane-ops per ply, 11.08 plies per
-# empty-board playout; 120 per perft node; 1150 per canonical key (192 images)
-OPS_PER_PLY, PLIES_PER_PLAYOUT, OPS_PER_NODE, OPS_PER_KEY = 230.0, 11.08, 120.0, 1150.0
+# Integer-op model (which replaces the SURVEY 8d estimate made before the
+# incremental formulation existed): 60 lane-ops per ply (of which 46 on the 64-lane ALU pipe),
+# 11.08 plies per empty-board playout; 131 per visited perft leaf parent = 4.9 per counted node at
+# depth 6; 384 per canonical key (192-image mode).
+OPS_PER_PLY, ALU_OPS_PER_PLY, PLIES_PER_PLAYOUT, OPS_PER_NODE, OPS_PER_KEY = 60.0, 46.0, 11.08, 4.9, 384.0
 OPS_PER_PLAYOUT = OPS_PER_PLY * PLIES_PER_PLAYOUT
 
 
@@ -238,10 +240,15 @@ def main():
         "bound": "int_issue", "kernel": "k_playout<false,false>",
         "achieved": achieved / 1e12, "peak": nominal_peak / 1e12, "unit": "Tlane-op/s", "frac": achieved / nominal_peak,
         "traffic": None,
-        "model": f"{OPS_PER_PLY:.0f} int ops/ply x {PLIES_PER_PLAYOUT} plies/playout (SURVEY 8d); peak = SMs x 128 lanes x "
-                 f"SM clock under load ({sm_mhz:.0f} MHz)",
+        "model": f"{OPS_PER_PLY:.0f} int ops/ply x {PLIES_PER_PLAYOUT} plies/playout (DESIGN.md section 5); peak = SMs x 4 "
+                 f"schedulers x 32 lanes x SM clock under load ({sm_mhz:.0f} MHz)",
         "peak_measured_lop3": peak_issue["alu"] / 1e12, "peak_measured_lop3_imad_mix": peak_issue["mixed"] / 1e12,
         "frac_of_measured_mix": achieved / peak_issue["mixed"] if peak_issue["mixed"] else None,
+        "alu_pipe": {"ops_per_ply": ALU_OPS_PER_PLY, "achieved": value / world * PLIES_PER_PLAYOUT * ALU_OPS_PER_PLY / 1e12,
+                     "peak_measured": peak_issue["alu"] / 1e12,
+                     "frac": value / world * PLIES_PER_PLAYOUT * ALU_OPS_PER_PLY / peak_issue["alu"] if peak_issue["alu"] else None,
+                     "note": "LOP3/SEL/ISETP/SHF/IADD3 share one 64-lane/clk/SM pipe on sm_100: the binding sub-roofline "
+                             "(ncu: profiles/)"},
         "hbm": {"algorithmic_bytes_per_step": 16 + 12, "note": "one 16-byte root in, three u32 tallies out: not memory-bound"},
     }
 

@@ -12,5 +12,6 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-fil
 # the dominant kernel, full set
 ncu --set full --clock-control none --import-source on -k regex:k_playout -s 3 -c 1 -o gpurun_out/prof_playout_$TAG $CMD > gpurun_out/ncu_playout_$TAG.log 2>&1
 # the two other kernel families
-ncu --set full --clock-control none --import-source on -k "regex:k_perft_dfs|k_canonical" -c 2 -o gpurun_out/prof_perft_canon_$TAG $CMD > gpurun_out/ncu_perft_canon_$TAG.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_perft_dfs -s 1 -c 1 -o gpurun_out/prof_perft_$TAG $CMD > gpurun_out/ncu_perft_$TAG.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_canonical -s 1 -c 1 -o gpurun_out/prof_canon_$TAG $CMD > gpurun_out/ncu_canon_$TAG.log 2>&1
 ls -la gpurun_out

@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(kBlock) k_playout(const PlayoutArgs a)
             }
             const uint4 *rp = reinterpret_cast<const uint4 *>(a.roots + root);
             uint4 r0 = __ldg(rp), r1 = __ldg(rp + 1), r2 = __ldg(rp + 2);
-            st.occ2 = r0.x; st.ra_lo = r0.y; st.ra_hi = r0.z; st.rb_lo = r0.w;
+            st.free2 = ~r0.x; st.ra_lo = r0.y; st.ra_hi = r0.z; st.rb_lo = r0.w;
             st.rb_hi = r1.x; st.ta_lo = r1.y; st.ta_hi = r1.z; st.tb_lo = r1.w;
             st.tb_hi = r2.x; st.lp_lo = r2.y; st.lp_hi = r2.z;
             uint32_t flags = r2.w;
@@ -107,12 +107,13 @@ __global__ void __launch_bounds__(kBlock) k_playout(const PlayoutArgs a)
             cur_root = root; cur_j = j;
             ply = 0; block = 0;
             --remaining;
+            ++acc_n;                       // every started game finishes before its tallies are flushed
             if (++j == a.rollouts) { j = 0; ++root; }
             uint32_t immediate = (flags >> QK_ROOT_IMMEDIATE_SHIFT) & 3u;
             if ((CUTOFF && a.max_plies == 0) || immediate) {
                 // nothing to play (mcts.py:412 cut-off first, then the root's own result)
                 int res = (CUTOFF && a.max_plies == 0) ? 0 : (immediate == 1 ? 1 : -1);
-                ++acc_n; acc_p0 += res > 0; acc_dr += res == 0;
+                acc_p0 += res > 0; acc_dr += res == 0;
                 if (PER_PLAYOUT) {
                     size_t o = (size_t)cur_root * a.rollouts + cur_j;
                     if (a.per_playout) a.per_playout[o] = (int8_t)res;
@@ -145,7 +146,6 @@ __global__ void __launch_bounds__(kBlock) k_playout(const PlayoutArgs a)
             if (CUTOFF) cut = !blocked && ply >= (uint32_t)a.max_plies;
             const bool fin = active && (blocked || win || cut);
             const bool p0_wins = (mover_is_p0 != blocked) && !cut;
-            acc_n += fin ? 1u : 0u;
             acc_p0 += (fin && p0_wins) ? 1u : 0u;
             if (CUTOFF) acc_dr += (fin && cut) ? 1u : 0u;
             if (PER_PLAYOUT && fin) {
@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(kBlock) k_random_roots(uint64_t seed, uint64_t
         }
         if (ok) {   // the side to move at the root must still have a move
             uint32_t r_lo = (target & 1) ? st.rb_lo : st.ra_lo, r_hi = (target & 1) ? st.rb_hi : st.ra_hi;
-            ok = (~(st.occ2 | r_lo) | ~(st.occ2 | r_hi)) != 0;
+            ok = ((st.free2 & ~r_lo) | (st.free2 & ~r_hi)) != 0;
         }
         if (ok) { out[ii] = make_uint4(cur.x, cur.y, cur.z, cur.w); return; }
     }

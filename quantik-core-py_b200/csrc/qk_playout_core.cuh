@@ -8,7 +8,7 @@
 // The rules are not re-derived from the 8 bitboards every ply.  Instead each
 // playout carries 11 registers that are updated with a handful of LOP3s when a
 // piece lands:
-//     occ2            occupied squares (replicated in both 16-bit lanes)
+//     free2           EMPTY squares (replicated in both 16-bit lanes)
 //     ra_lo/ra_hi     squares+shapes closed to role A (= the root's mover): the
 //                     row/column/zone scope of B's pieces of that shape, plus
 //                     whole lanes of shapes A has already placed twice
@@ -17,7 +17,7 @@
 //     lp_lo/lp_hi     per shape (colour-blind) the 12-bit set of lines that
 //                     contain it: rows 0-3, columns 4-7, zones 8-11
 // lanes: lo = shape A | shape B << 16, hi = shape C | shape D << 16.
-// Legal moves of the mover = ~(occ2 | r?_lo), ~(occ2 | r?_hi)   (2 LOP3)
+// Legal moves of the mover = free2 & ~r?_lo, free2 & ~r?_hi     (2 LOP3)
 // A line is complete iff lp_A & lp_B & lp_C & lp_D != 0            (3 LOP3 + 1 SHF)
 #pragma once
 #include "qk_bits.cuh"
@@ -127,11 +127,11 @@ QK_HD RootRec make_root(const State4 &s)
 
 // ---------------------------------------------------------------- one ply
 struct PlayState {
-    uint32_t occ2, ra_lo, ra_hi, rb_lo, rb_hi, ta_lo, ta_hi, tb_lo, tb_hi, lp_lo, lp_hi;
+    uint32_t free2, ra_lo, ra_hi, rb_lo, rb_hi, ta_lo, ta_hi, tb_lo, tb_hi, lp_lo, lp_hi;
 };
 QK_HD PlayState load_play_state(const RootRec &r)
 {
-    PlayState p = { r.occ2, r.ra_lo, r.ra_hi, r.rb_lo, r.rb_hi, r.ta_lo, r.ta_hi, r.tb_lo, r.tb_hi, r.lp_lo, r.lp_hi };
+    PlayState p = { ~r.occ2, r.ra_lo, r.ra_hi, r.rb_lo, r.rb_hi, r.ta_lo, r.ta_hi, r.tb_lo, r.tb_hi, r.lp_lo, r.lp_hi };
     return p;
 }
 
@@ -149,7 +149,7 @@ QK_HD void ply_step(PlayState &st, uint32_t rnd, const SquareLut *lut, const uin
     uint32_t &tm_lo = ROLE ? st.tb_lo : st.ta_lo, &tm_hi = ROLE ? st.tb_hi : st.ta_hi;
 
     // generate_legal_moves: 64-bit action mask, bit = shape*16 + square
-    uint32_t legal_lo = ~(st.occ2 | rm_lo), legal_hi = ~(st.occ2 | rm_hi);
+    uint32_t legal_lo = st.free2 & ~rm_lo, legal_hi = st.free2 & ~rm_hi;
     int nlo = popc(legal_lo), n = nlo + popc(legal_hi);
     blocked = (n == 0);
 
@@ -167,13 +167,13 @@ QK_HD void ply_step(PlayState &st, uint32_t rnd, const SquareLut *lut, const uin
     k -= hib ? c : 0;
     uint32_t byte = (hib ? (w >> 8) : w) & 0xFFu;
     // byte offset of the chosen square's entry in the SquareLut table (16 B per square)
-    uint32_t off = ((uint32_t)sel8[(byte << 3) | (uint32_t)(k & 7)] + (hib ? 128u : 0u)) & 0xF0u;
+    uint32_t off = (uint32_t)sel8[(byte << 3) | (uint32_t)(k & 7)] + (hib ? 128u : 0u);   // <= 240: always inside the table
 
     // apply_move + incremental rule state
     uint32_t lane = odd ? 0xFFFF0000u : 0x0000FFFFu;
     uint32_t l_lo = up ? 0u : lane, l_hi = up ? lane : 0u;
     const SquareLut e = *reinterpret_cast<const SquareLut *>(reinterpret_cast<const char *>(lut) + off);
-    st.occ2 |= e.bit2;
+    st.free2 &= ~e.bit2;
     ro_lo |= e.scope2 & l_lo;  ro_hi |= e.scope2 & l_hi;  // opponent may no longer use this shape in my scope
     rm_lo |= tm_lo & l_lo;     rm_hi |= tm_hi & l_hi;     // second piece of the shape: lane exhausted for me
     tm_lo |= l_lo;             tm_hi |= l_hi;

@@ -296,7 +296,25 @@ int qk_canon_dedup(const uint16_t *states, const uint64_t *mult, size_t n, int c
     const uint4 *d_states = (const uint4 *)call.in(states, n * 16);
     const uint64_t *d_mult = (const uint64_t *)call.in(mult, n * 8);
     QK_CHECK(call);
-    int rc = run_dedup(call, d_states, d_mult, n, color_swap, uniq, uniq_mult, cap, n_uniq);
+    int rc = run_dedup(call, d_states, d_mult, n, color_swap, uniq, uniq_mult, cap ? cap : n, n_uniq);
+    if (rc != QK_OK) return rc;
+    return call.finish();
+}
+
+int qk_bfs_level(const uint16_t *states, const uint64_t *mult, size_t n, int color_swap, uint16_t *uniq,
+                 uint64_t *uniq_mult, size_t cap, size_t *n_uniq, uint64_t *stats, int dev, void *stream)
+{
+    QK_REQUIRE(n_uniq && stats, "qk_bfs_level: n_uniq / stats is NULL");
+    QK_REQUIRE(states || n == 0, "qk_bfs_level: states is NULL");
+    QK_REQUIRE(cap > 0, "qk_bfs_level: cap must be positive");
+    *n_uniq = 0;
+    for (int i = 0; i < 5; ++i) stats[i] = 0;
+    if (n == 0) return QK_OK;
+    QK_BEGIN(call);
+    const uint4 *d_states = (const uint4 *)call.in(states, n * 16);
+    const uint64_t *d_mult = (const uint64_t *)call.in(mult, n * 8);
+    QK_CHECK(call);
+    int rc = run_bfs_level(call, d_states, d_mult, n, color_swap, uniq, uniq_mult, cap, n_uniq, stats);
     if (rc != QK_OK) return rc;
     return call.finish();
 }

@@ -10,6 +10,7 @@
 //   k_bitonic_step   sorts the distinct keys in payload byte order (deterministic output)
 #include "qk_common.cuh"
 #include "qk_bits.cuh"
+#include "qk_perft_core.cuh"
 
 namespace qk {
 
@@ -54,6 +55,7 @@ __global__ void __launch_bounds__(kBlock) k_dedup_insert(const uint4 *__restrict
                                                           u64 *n_unique, u64 *all_ones_count, int *overflow, u64 max_unique)
 {
     for (size_t i = blockIdx.x * (size_t)kBlock + threadIdx.x; i < n; i += (size_t)gridDim.x * kBlock) {
+        if (*reinterpret_cast<volatile int *>(overflow)) break;     // table too small: give up early
         uint4 v = __ldg(states + i);
         State4 s = { v.x, v.y, v.z, v.w };
         State4 c = canonical<COLOR_SWAP>(s);
@@ -123,42 +125,108 @@ __global__ void __launch_bounds__(kBlock) k_emit(const Slot *keys, const u64 *mu
     }
 }
 
-int run_dedup(Call &call, const uint4 *states, const uint64_t *mult, size_t n, int color_swap,
-              uint16_t *uniq, uint64_t *uniq_mult, size_t cap, size_t *n_uniq)
+// ---------------------------------------------------------------------------------------------
+// One BFS level of game_stats.SymmetryTable._process_depth (game_stats.py:359-485), fused:
+// warp per parent; the parent's legal / winning-move masks are warp-uniform, lane l materialises
+// children l and l+32, canonicalises them in registers and inserts them into the table with the
+// parent's multiplicity.  Children are never written to HBM.
+// stats: [0] total_moves  [1] line wins by P0  [2] by P1  [3] parents with P0 blocked  [4] P1 blocked
+template <bool COLOR_SWAP>
+__global__ void __launch_bounds__(kBlock) k_bfs_expand_insert(const uint4 *__restrict__ parents, const u64 *__restrict__ mult,
+                                                               size_t n, Slot *table, u64 *counts, size_t slot_mask,
+                                                               u64 *n_unique, u64 *all_ones_count, int *overflow,
+                                                               u64 max_unique, u64 *stats)
+{
+    const unsigned lane = threadIdx.x & 31u;
+    const size_t warp = (blockIdx.x * (size_t)kBlock + threadIdx.x) >> 5, n_warps = ((size_t)gridDim.x * kBlock) >> 5;
+    u64 s_moves = 0, s_w0 = 0, s_w1 = 0, s_b0 = 0, s_b1 = 0;      // warp-uniform running sums
+    for (size_t i = warp; i < n; i += n_warps) {
+        if (*reinterpret_cast<volatile int *>(overflow)) break;     // table too small: the host retries with a larger one
+        const uint4 v = __ldg(parents + i);
+        const State4 parent = { v.x, v.y, v.z, v.w };
+        const u64 m = mult ? mult[i] : 1ull;
+        const int mover = piece_balance(parent);
+        uint32_t lo, hi, wab, wcd;
+        legal_masks(parent, mover, lo, hi);
+        const int n_moves = popc(lo) + popc(hi);
+        if (n_moves == 0) { if (mover == 0) s_b0 += m; else s_b1 += m; continue; }     // game_stats.py:426-443
+        winning_squares(parent, wab, wcd);
+        s_moves += (u64)n_moves * m;                                                   // :401
+        const u64 wins = (u64)(popc(lo & wab) + popc(hi & wcd)) * m;                   // :411-415
+        if (mover == 0) s_w0 += wins; else s_w1 += wins;
+        const uint32_t nl = lo & ~wab, nh = hi & ~wcd;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            if (!(((half ? nh : nl) >> lane) & 1u)) continue;
+            const State4 c = canonical<COLOR_SWAP>(apply_action(parent, mover, half * 32 + (int)lane));   // :453,:468
+            const u64 khi_new = ((u64)prmt(c.x, 0, 0x0123) << 32) | prmt(c.y, 0, 0x0123);
+            const u64 klo_new = ((u64)prmt(c.z, 0, 0x0123) << 32) | prmt(c.w, 0, 0x0123);
+            if ((khi_new & klo_new) == ~0ull) { atomicAdd(all_ones_count, m); continue; }
+            size_t slot = (size_t)mix(khi_new, klo_new) & slot_mask;
+            for (size_t probe = 0; probe <= slot_mask; ++probe, slot = (slot + 1) & slot_mask) {
+                const ulonglong2 raw = __ldcv(reinterpret_cast<const ulonglong2 *>(table + slot));
+                u64 khi = raw.x, klo = raw.y;
+                if (khi == ~0ull || klo == ~0ull) {
+                    cas128(table + slot, ~0ull, ~0ull, khi_new, klo_new, khi, klo);
+                    if (khi == ~0ull && klo == ~0ull) {
+                        if (atomicAdd(n_unique, 1ull) >= max_unique) *overflow = 1;
+                        khi = khi_new; klo = klo_new;
+                    }
+                }
+                if (khi == khi_new && klo == klo_new) { atomicAdd(counts + slot, m); break; }   // :487-505
+            }
+        }
+    }
+    if (lane == 0) {
+        if (s_moves) atomicAdd(stats + 0, s_moves);
+        if (s_w0) atomicAdd(stats + 1, s_w0);
+        if (s_w1) atomicAdd(stats + 2, s_w1);
+        if (s_b0) atomicAdd(stats + 3, s_b0);
+        if (s_b1) atomicAdd(stats + 4, s_b1);
+    }
+}
+
+// ------------------------------------------------------------------ host side
+struct DedupTable { Slot *table; u64 *counts; u64 *meta; size_t slots; u64 max_unique; };
+
+static int dedup_begin(Call &call, size_t expected_unique, DedupTable &t)
+{
+    cudaStream_t s = call.stream();
+    t.slots = 1024;
+    while (t.slots < 2 * expected_unique + 2) t.slots <<= 1;
+    t.table = (Slot *)call.temp(t.slots * sizeof(Slot));
+    t.counts = (u64 *)call.temp(t.slots * sizeof(u64));
+    t.meta = (u64 *)call.temp(10 * sizeof(u64), true);   // n_unique, all-ones mult, cursor, overflow, stats[5]
+    if (!t.table || !t.counts || !t.meta) return call.status();
+    t.max_unique = (u64)(t.slots / 2);
+    k_dedup_fill<<<grid_for(t.slots, kBlock, call.ctx()->sms, 8), kBlock, 0, s>>>(t.table, t.counts, t.slots);
+    QK_CUDA(cudaGetLastError());
+    return QK_OK;
+}
+
+// table -> sorted distinct payloads + multiplicities in the caller's buffers; h_stats (5 x u64, may be null)
+static int dedup_finish(Call &call, DedupTable &t, uint16_t *uniq, uint64_t *uniq_mult, size_t cap, size_t *n_uniq,
+                        uint64_t *h_stats, const char *who)
 {
     cudaStream_t s = call.stream();
     Ctx *c = call.ctx();
-    size_t want = n < cap || cap == 0 ? n : cap;
-    size_t slots = 1024;
-    while (slots < 2 * want + 2) slots <<= 1;
-    Slot *table = (Slot *)call.temp(slots * sizeof(Slot));
-    u64 *counts = (u64 *)call.temp(slots * sizeof(u64));
-    u64 *meta = (u64 *)call.temp(4 * sizeof(u64), true);   // n_unique, all-ones multiplicity, cursor, overflow flag
-    if (!table || !counts || !meta) return call.status();
-    k_dedup_fill<<<grid_for(slots, kBlock, c->sms, 8), kBlock, 0, s>>>(table, counts, slots);
-    const u64 max_unique = (u64)(slots / 2);
-    if (color_swap)
-        k_dedup_insert<true><<<grid_for(n, kBlock, c->sms, 8), kBlock, 0, s>>>(states, (const u64 *)mult, n, table, counts, slots - 1,
-                                                                             meta, meta + 1, (int *)(meta + 3), max_unique);
-    else
-        k_dedup_insert<false><<<grid_for(n, kBlock, c->sms, 8), kBlock, 0, s>>>(states, (const u64 *)mult, n, table, counts, slots - 1,
-                                                                              meta, meta + 1, (int *)(meta + 3), max_unique);
-    QK_CUDA(cudaGetLastError());
-    u64 h_meta[4];
-    QK_CUDA(cudaMemcpyAsync(h_meta, meta, sizeof h_meta, cudaMemcpyDeviceToHost, s));
+    u64 h_meta[10];
+    QK_CUDA(cudaMemcpyAsync(h_meta, t.meta, sizeof h_meta, cudaMemcpyDeviceToHost, s));
     QK_CUDA(cudaStreamSynchronize(s));
+    if (h_stats) for (int i = 0; i < 5; ++i) h_stats[i] = h_meta[4 + i];
     size_t nu = (size_t)h_meta[0];
-    bool special = h_meta[1] != 0;
-    if ((int)h_meta[3] != 0 || (cap && nu + (special ? 1 : 0) > cap && (uniq || uniq_mult))) {
-        set_error("qk_canon_dedup: more distinct canonical states than `cap`");
-        return QK_E_BAD_ARG;
+    const bool special = h_meta[1] != 0;
+    if ((int)h_meta[3] != 0 || (nu + (special ? 1 : 0) > cap && (uniq || uniq_mult))) {
+        *n_uniq = nu + (special ? 1 : 0);
+        set_error(std::string(who) + ": more distinct canonical states than `cap`");
+        return QK_E_NOMEM;
     }
     size_t padded = 1;
     while (padded < nu) padded <<= 1;
     Slot *keys = (Slot *)call.temp((padded + 1) * sizeof(Slot));
     u64 *mults = (u64 *)call.temp((padded + 1) * sizeof(u64));
     if (!keys || !mults) return call.status();
-    k_dedup_compact<<<grid_for(slots, kBlock, c->sms, 8), kBlock, 0, s>>>(table, counts, slots, keys, mults, meta + 2);
+    k_dedup_compact<<<grid_for(t.slots, kBlock, c->sms, 8), kBlock, 0, s>>>(t.table, t.counts, t.slots, keys, mults, t.meta + 2);
     k_pad<<<grid_for(padded - nu + 1, kBlock, c->sms, 8), kBlock, 0, s>>>(keys, mults, nu, padded);
     for (size_t k = 2; k <= padded; k <<= 1)
         for (size_t j = k >> 1; j > 0; j >>= 1)
@@ -180,6 +248,44 @@ int run_dedup(Call &call, const uint4 *states, const uint64_t *mult, size_t n, i
         QK_CUDA(cudaGetLastError());
     }
     return QK_OK;
+}
+
+int run_dedup(Call &call, const uint4 *states, const uint64_t *mult, size_t n, int color_swap,
+              uint16_t *uniq, uint64_t *uniq_mult, size_t cap, size_t *n_uniq)
+{
+    cudaStream_t s = call.stream();
+    Ctx *c = call.ctx();
+    DedupTable t;
+    int rc = dedup_begin(call, n < cap ? n : cap, t);
+    if (rc != QK_OK) return rc;
+    if (color_swap)
+        k_dedup_insert<true><<<grid_for(n, kBlock, c->sms, 8), kBlock, 0, s>>>(states, (const u64 *)mult, n, t.table, t.counts, t.slots - 1,
+                                                                             t.meta, t.meta + 1, (int *)(t.meta + 3), t.max_unique);
+    else
+        k_dedup_insert<false><<<grid_for(n, kBlock, c->sms, 8), kBlock, 0, s>>>(states, (const u64 *)mult, n, t.table, t.counts, t.slots - 1,
+                                                                              t.meta, t.meta + 1, (int *)(t.meta + 3), t.max_unique);
+    QK_CUDA(cudaGetLastError());
+    return dedup_finish(call, t, uniq, uniq_mult, cap, n_uniq, nullptr, "qk_canon_dedup");
+}
+
+int run_bfs_level(Call &call, const uint4 *parents, const uint64_t *mult, size_t n, int color_swap,
+                  uint16_t *uniq, uint64_t *uniq_mult, size_t cap, size_t *n_uniq, uint64_t *h_stats)
+{
+    cudaStream_t s = call.stream();
+    Ctx *c = call.ctx();
+    DedupTable t;
+    int rc = dedup_begin(call, cap, t);
+    if (rc != QK_OK) return rc;
+    // one warp per parent, grid-stride; 8 resident CTAs per SM
+    const unsigned grid = grid_for(n * 32, kBlock, c->sms, 8);
+    if (color_swap)
+        k_bfs_expand_insert<true><<<grid, kBlock, 0, s>>>(parents, (const u64 *)mult, n, t.table, t.counts, t.slots - 1, t.meta, t.meta + 1,
+                                                         (int *)(t.meta + 3), t.max_unique, t.meta + 4);
+    else
+        k_bfs_expand_insert<false><<<grid, kBlock, 0, s>>>(parents, (const u64 *)mult, n, t.table, t.counts, t.slots - 1, t.meta, t.meta + 1,
+                                                          (int *)(t.meta + 3), t.max_unique, t.meta + 4);
+    QK_CUDA(cudaGetLastError());
+    return dedup_finish(call, t, uniq, uniq_mult, cap, n_uniq, h_stats, "qk_bfs_level");
 }
 
 }  // namespace qk

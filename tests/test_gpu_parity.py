@@ -294,6 +294,50 @@ def test_perft_is_symmetry_invariant():
         assert np.array_equal(base[k], img[k])
 
 
+# ----------------------------------------------------------------------------- canonical BFS
+def test_symmetry_table_bfs_reproduces_published_table_with_unique_counts():
+    # GAME_TREE_ANALYSIS.md:4-11: total legal moves, unique canonical, P0 wins, P1 wins, ongoing
+    table = [[64, 3, 0, 0, 64], [3392, 51, 0, 0, 3392], [167552, 726, 0, 0, 167552], [6776960, 10946, 0, 6912, 6770048],
+             [231883776, 105632, 1050624, 0, 230833152], [6241600512, 901916, 0, 81653760, 6159946752],
+             [132400548864, 4658465, 3886838784, 0, 128513710080],
+             [2097048766464, 17900160, 0, 118862401536, 1978186364928]]
+    assert B.symmetry_table(8) == table
+    assert B.symmetry_table(5, on_device=False) == table[:5]          # host-buffer path of the same call
+    assert [r[1] for r in table] == [3, 51, 726, 10946, 105632, 901916, 4658465, 17900160]   # beam_search.py:210-219
+    # the depth-4 frontier equals the reference's own (states and multiplicities)
+    f, m = np.zeros((1, 8), np.uint16), np.ones(1, np.uint64)
+    for _ in range(4):
+        f, m, _ = B.bfs_level(f, m)
+    d = _npz("depth4_canonical.npz")
+    assert np.array_equal(f, d["states"]) and np.array_equal(m, d["mult"])
+
+
+def test_bfs_level_vs_oracle_composition():
+    parents = np.unique(O.canonical(O.make_roots(3000, seed=5, min_plies=6, span=6)), axis=0)
+    mult = np.random.default_rng(8).integers(1, 50, len(parents)).astype(np.uint64)
+    f, m, st = B.bfs_level(parents, mult)
+    mask, to_move, _ = O.movegen_masks(parents)
+    want, tot, w = {}, 0, [0, 0]
+    blocked = [0, 0]
+    for i in range(len(parents)):
+        mk = int(mask[i])
+        if mk == 0:
+            blocked[int(to_move[i])] += int(mult[i])
+            continue
+        acts = np.array([b for b in range(64) if (mk >> b) & 1], np.uint8)
+        kids = O.apply_moves(np.repeat(parents[i:i + 1], len(acts), 0), acts)
+        wins = O.win_status(kids)
+        tot += len(acts) * int(mult[i])
+        w[int(to_move[i])] += int((wins != 0).sum()) * int(mult[i])
+        for c in O.canonical(kids[wins == 0]):
+            want[c.astype("<u2").tobytes()] = want.get(c.astype("<u2").tobytes(), 0) + int(mult[i])
+    assert st == {"total_moves": tot, "line_wins_p0": w[0], "line_wins_p1": w[1], "blocked_p0": blocked[0], "blocked_p1": blocked[1]}
+    keys = sorted(want)
+    assert [r.astype("<u2").tobytes() for r in f] == keys and m.tolist() == [want[k] for k in keys]
+    f2, m2, _ = B.bfs_level(parents, mult, cap=16)               # forces the grow-and-retry path
+    assert np.array_equal(f2, f) and np.array_equal(m2, m)
+
+
 # ----------------------------------------------------------------------------- device buffers, engines
 def test_device_tensor_path_matches_host_path():
     import torch

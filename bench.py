@@ -89,6 +89,7 @@ def cpu_baseline(seconds: float = 12.0):
     """Oracle port (C, OpenMP over all host threads) of the reference's rollout loop on a bounded
     sample of the same workload: playouts from the empty board."""
     import oracle as O
+    O.set_num_threads(len(os.sched_getaffinity(0)))            # torchrun exports OMP_NUM_THREADS=1
     empty = np.zeros((1, 8), np.uint16)
     O.playouts(empty, 2000)
     t = time.perf_counter()
@@ -111,6 +112,7 @@ def run_reference(args):
     if rank != 0:
         return
     import oracle as O
+    O.set_num_threads(len(os.sched_getaffinity(0)))            # torchrun exports OMP_NUM_THREADS=1
     empty = np.zeros((1, 8), np.uint16)
     O.playouts(empty, 20000, SEED)
     t = time.perf_counter()

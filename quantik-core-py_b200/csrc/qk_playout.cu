@@ -66,7 +66,7 @@ __device__ __forceinline__ void flush_tallies(const PlayoutArgs &a, uint32_t roo
 }
 
 template <bool CUTOFF, bool PER_PLAYOUT>
-__global__ void __maxnreg__((CUTOFF || PER_PLAYOUT) ? 48 : 38) k_playout(const PlayoutArgs a)   // 38 (+2 reserved) -> 6 CTAs/SM
+__global__ void __launch_bounds__(kBlock) k_playout(const PlayoutArgs a)
 {
     __shared__ __align__(16) SquareLut s_lut[16];
     __shared__ __align__(16) uint8_t s_sel8[2048];

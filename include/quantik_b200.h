@@ -123,11 +123,12 @@ QK_API int qk_canon_dedup(const uint16_t *states, const uint64_t *mult, size_t n
  *                      (examples/generate_opening_book.py:185-280): for n non-won parent states
  *                      with multiplicities, generate every child, drop the ones that complete a
  *                      line, canonicalise the rest and merge them with summed multiplicity.
- *                      uniq / uniq_mult (capacity cap) receive the next canonical frontier sorted
- *                      in byte order, *n_uniq its size; stats (host, 5 values) = total moves,
+ *                      uniq / uniq_mult (capacity cap + 1) receive the next canonical frontier
+ *                      (sorted in byte order when sort_output != 0, else in table order), *n_uniq
+ *                      its size; stats (host, 5 values) = total moves,
  *                      line wins by P0, by P1, parents where P0 / P1 is to move and blocked, all
  *                      weighted.  QK_E_NOMEM when the frontier exceeds cap.  Synchronous.         */
-QK_API int qk_bfs_level(const uint16_t *states, const uint64_t *mult, size_t n, int color_swap,
+QK_API int qk_bfs_level(const uint16_t *states, const uint64_t *mult, size_t n, int color_swap, int sort_output,
                         uint16_t *uniq, uint64_t *uniq_mult, size_t cap, size_t *n_uniq,
                         uint64_t *stats, int dev, void *stream);
 

@@ -301,7 +301,7 @@ int qk_canon_dedup(const uint16_t *states, const uint64_t *mult, size_t n, int c
     return call.finish();
 }
 
-int qk_bfs_level(const uint16_t *states, const uint64_t *mult, size_t n, int color_swap, uint16_t *uniq,
+int qk_bfs_level(const uint16_t *states, const uint64_t *mult, size_t n, int color_swap, int sort_output, uint16_t *uniq,
                  uint64_t *uniq_mult, size_t cap, size_t *n_uniq, uint64_t *stats, int dev, void *stream)
 {
     QK_REQUIRE(n_uniq && stats, "qk_bfs_level: n_uniq / stats is NULL");
@@ -314,7 +314,7 @@ int qk_bfs_level(const uint16_t *states, const uint64_t *mult, size_t n, int col
     const uint4 *d_states = (const uint4 *)call.in(states, n * 16);
     const uint64_t *d_mult = (const uint64_t *)call.in(mult, n * 8);
     QK_CHECK(call);
-    int rc = run_bfs_level(call, d_states, d_mult, n, color_swap, uniq, uniq_mult, cap, n_uniq, stats);
+    int rc = run_bfs_level(call, d_states, d_mult, n, color_swap, sort_output, uniq, uniq_mult, cap, n_uniq, stats);
     if (rc != QK_OK) return rc;
     return call.finish();
 }

@@ -81,7 +81,7 @@ int launch_random_roots(uint64_t seed, uint64_t first, size_t n, int min_plies, 
 int run_perft(Call &call, const uint4 *roots, const uint64_t *mult, size_t n_roots, int depth, uint64_t *host_out /*5 x (depth+1)*/);
 int run_dedup(Call &call, const uint4 *states, const uint64_t *mult, size_t n, int color_swap,
               uint16_t *uniq_host_or_dev, uint64_t *uniq_mult, size_t cap, size_t *n_uniq);
-int run_bfs_level(Call &call, const uint4 *parents, const uint64_t *mult, size_t n, int color_swap,
+int run_bfs_level(Call &call, const uint4 *parents, const uint64_t *mult, size_t n, int color_swap, int sort_output,
                   uint16_t *uniq, uint64_t *uniq_mult, size_t cap, size_t *n_uniq, uint64_t *h_stats);
 int run_issue_peak(Ctx *c, double *alu, double *mixed);
 

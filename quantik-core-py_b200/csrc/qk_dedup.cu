@@ -93,6 +93,20 @@ __global__ void __launch_bounds__(kBlock) k_dedup_compact(const Slot *table, con
     }
 }
 
+// unsorted path: table -> caller's payload / multiplicity arrays directly (no intermediate copy)
+__global__ void __launch_bounds__(kBlock) k_dedup_compact_emit(const Slot *table, const u64 *counts, size_t slots,
+                                                                uint4 *uniq, u64 *uniq_mult, u64 *cursor)
+{
+    for (size_t i = blockIdx.x * (size_t)kBlock + threadIdx.x; i < slots; i += (size_t)gridDim.x * kBlock) {
+        Slot k = table[i];
+        if (k.hi == ~0ull && k.lo == ~0ull) continue;
+        u64 o = atomicAdd(cursor, 1ull);
+        uniq[o] = make_uint4(prmt((uint32_t)(k.hi >> 32), 0, 0x0123), prmt((uint32_t)k.hi, 0, 0x0123),
+                             prmt((uint32_t)(k.lo >> 32), 0, 0x0123), prmt((uint32_t)k.lo, 0, 0x0123));
+        uniq_mult[o] = counts[i];
+    }
+}
+
 __global__ void __launch_bounds__(kBlock) k_pad(Slot *keys, u64 *mults, size_t from, size_t to)
 {
     for (size_t i = from + blockIdx.x * (size_t)kBlock + threadIdx.x; i < to; i += (size_t)gridDim.x * kBlock) {
@@ -206,7 +220,7 @@ static int dedup_begin(Call &call, size_t expected_unique, DedupTable &t)
 
 // table -> sorted distinct payloads + multiplicities in the caller's buffers; h_stats (5 x u64, may be null)
 static int dedup_finish(Call &call, DedupTable &t, uint16_t *uniq, uint64_t *uniq_mult, size_t cap, size_t *n_uniq,
-                        uint64_t *h_stats, const char *who)
+                        uint64_t *h_stats, const char *who, bool sort_output = true)
 {
     cudaStream_t s = call.stream();
     Ctx *c = call.ctx();
@@ -220,6 +234,23 @@ static int dedup_finish(Call &call, DedupTable &t, uint16_t *uniq, uint64_t *uni
         *n_uniq = nu + (special ? 1 : 0);
         set_error(std::string(who) + ": more distinct canonical states than `cap`");
         return QK_E_NOMEM;
+    }
+    if (!sort_output && uniq && uniq_mult) {
+        // arbitrary order: straight from the table into the caller's arrays
+        uint4 *d_uniq = (uint4 *)call.out(uniq, (nu + 1) * 16);
+        u64 *d_um = (u64 *)call.out(uniq_mult, (nu + 1) * 8);
+        if (call.status() != QK_OK) return call.status();
+        k_dedup_compact_emit<<<grid_for(t.slots, kBlock, c->sms, 8), kBlock, 0, s>>>(t.table, t.counts, t.slots, d_uniq, d_um, t.meta + 2);
+        QK_CUDA(cudaGetLastError());
+        if (special) {
+            const uint32_t ones[4] = { ~0u, ~0u, ~0u, ~0u };
+            QK_CUDA(cudaMemcpyAsync(d_uniq + nu, ones, 16, cudaMemcpyHostToDevice, s));
+            QK_CUDA(cudaMemcpyAsync(d_um + nu, &h_meta[1], sizeof(u64), cudaMemcpyHostToDevice, s));
+            QK_CUDA(cudaStreamSynchronize(s));
+            ++nu;
+        }
+        *n_uniq = nu;
+        return QK_OK;
     }
     size_t padded = 1;
     while (padded < nu) padded <<= 1;
@@ -268,7 +299,7 @@ int run_dedup(Call &call, const uint4 *states, const uint64_t *mult, size_t n, i
     return dedup_finish(call, t, uniq, uniq_mult, cap, n_uniq, nullptr, "qk_canon_dedup");
 }
 
-int run_bfs_level(Call &call, const uint4 *parents, const uint64_t *mult, size_t n, int color_swap,
+int run_bfs_level(Call &call, const uint4 *parents, const uint64_t *mult, size_t n, int color_swap, int sort_output,
                   uint16_t *uniq, uint64_t *uniq_mult, size_t cap, size_t *n_uniq, uint64_t *h_stats)
 {
     cudaStream_t s = call.stream();
@@ -285,7 +316,7 @@ int run_bfs_level(Call &call, const uint4 *parents, const uint64_t *mult, size_t
         k_bfs_expand_insert<false><<<grid, kBlock, 0, s>>>(parents, (const u64 *)mult, n, t.table, t.counts, t.slots - 1, t.meta, t.meta + 1,
                                                           (int *)(t.meta + 3), t.max_unique, t.meta + 4);
     QK_CUDA(cudaGetLastError());
-    return dedup_finish(call, t, uniq, uniq_mult, cap, n_uniq, h_stats, "qk_bfs_level");
+    return dedup_finish(call, t, uniq, uniq_mult, cap, n_uniq, h_stats, "qk_bfs_level", sort_output != 0);
 }
 
 }  // namespace qk

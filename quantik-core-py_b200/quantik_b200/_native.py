@@ -42,7 +42,7 @@ PROTOTYPES = {
     "qk_apply_symmetry": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_int, c_void_p]),
     "qk_canon_dedup": (c_int, [c_void_p, c_void_p, c_size_t, c_int, c_void_p, c_void_p, c_size_t,
                                POINTER(c_size_t), c_int, c_void_p]),
-    "qk_bfs_level": (c_int, [c_void_p, c_void_p, c_size_t, c_int, c_void_p, c_void_p, c_size_t, POINTER(c_size_t),
+    "qk_bfs_level": (c_int, [c_void_p, c_void_p, c_size_t, c_int, c_int, c_void_p, c_void_p, c_size_t, POINTER(c_size_t),
                              c_void_p, c_int, c_void_p]),
     "qk_playouts": (c_int, [c_void_p, c_size_t, c_uint32, c_uint64, c_int, c_void_p, c_void_p, c_void_p,
                             c_void_p, c_int, c_void_p]),

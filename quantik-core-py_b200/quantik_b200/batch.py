@@ -193,23 +193,25 @@ def canon_dedup(states, mult=None, color_swap: bool = False, cap: Optional[int] 
     return uniq.obj[:nu.value], um.obj[:nu.value]
 
 
-def bfs_level(states, mult=None, color_swap: bool = False, cap: int = 1 << 20, device: Optional[int] = None):
+def bfs_level(states, mult=None, color_swap: bool = False, cap: int = 1 << 20, sort_output: bool = True,
+              device: Optional[int] = None):
     """One depth of the reference's SymmetryTable / opening-book BFS (game_stats.py:359-485), fused on the
     GPU: expand every parent, drop line-completing moves, canonicalise + merge the rest.
-    -> (next frontier (U, 8) sorted in byte order, multiplicities (U,), stats dict)."""
+    -> (next frontier (U, 8) [sorted in byte order], multiplicities (U,), stats dict)."""
     s, on_dev, d = _states_in(states)
     d = _dev(device, on_dev, d)
     lib = N.init(d)
     m = _aux_in(mult, np.uint64, on_dev, d)
     while True:
-        uniq = _out((cap, 8), np.uint16, on_dev, d)
-        um = _out((cap,), np.uint64, on_dev, d)
+        uniq = _out((cap + 1, 8), np.uint16, on_dev, d)
+        um = _out((cap + 1,), np.uint64, on_dev, d)
         nu = ctypes.c_size_t(0)
         stats = np.zeros(5, np.uint64)
-        rc = lib.qk_bfs_level(s.ptr, m.ptr, s.n, int(bool(color_swap)), uniq.ptr, um.ptr, cap, ctypes.byref(nu),
-                              stats.ctypes.data, d, _stream(on_dev, d))
+        rc = lib.qk_bfs_level(s.ptr, m.ptr, s.n, int(bool(color_swap)), int(bool(sort_output)), uniq.ptr, um.ptr, cap,
+                              ctypes.byref(nu), stats.ctypes.data, d, _stream(on_dev, d))
         if rc == -4:            # QK_E_NOMEM: frontier larger than cap -> retry with a bigger table
-            cap *= 4
+            del uniq, um
+            cap *= 2
             continue
         N.check(rc)
         break
@@ -217,27 +219,35 @@ def bfs_level(states, mult=None, color_swap: bool = False, cap: int = 1 << 20, d
     return uniq.obj[:nu.value], um.obj[:nu.value], {k: int(v) for k, v in zip(names, stats)}
 
 
-def symmetry_table(max_depth: int, device: Optional[int] = None, on_device: bool = True):
+def symmetry_table(max_depth: int, device: Optional[int] = None, on_device: bool = True, sort_output: bool = False,
+                   verbose: bool = False):
     """The reference's SymmetryTable.analyze_game_tree (game_stats.py:276-296) from the empty board:
     rows [total_legal_moves, unique_canonical, p0_wins, p1_wins, ongoing] for depth 1..max_depth, in the
     reference's convention (a blocked mover is booked as a win of the other player, :397-398)."""
+    import time as _time
     d = 0 if device is None else int(device)
     frontier, mult = np.zeros((1, 8), np.uint16), np.ones(1, np.uint64)
     if on_device and torch is not None:
         frontier = torch.zeros((1, 8), dtype=torch.int16, device=f"cuda:{d}")
         mult = torch.ones(1, dtype=torch.int64, device=f"cuda:{d}")
     rows = []
-    cap = 1 << 12
-    for _ in range(max_depth):
+    growth = 64.0
+    for depth in range(1, max_depth + 1):
         n = int(frontier.shape[0])
         if n == 0:
             rows.append([0, 0, 0, 0, 0])
             continue
-        cap = max(cap, min(64 * n, 8 * n + (1 << 16)))
-        frontier, mult, st = bfs_level(frontier, mult, cap=cap, device=d)
+        t0 = _time.perf_counter()
+        cap = int(min(64 * n, max(1 << 12, 1.6 * growth * n)))
+        nxt, nmult, st = bfs_level(frontier, mult, cap=cap, sort_output=sort_output, device=d)
+        del frontier, mult
+        frontier, mult = nxt, nmult
         ongoing = int(mult.sum()) if len(mult) else 0
         rows.append([st["total_moves"], int(frontier.shape[0]), st["line_wins_p0"] + st["blocked_p1"],
                      st["line_wins_p1"] + st["blocked_p0"], ongoing])
+        growth = max(0.05, int(frontier.shape[0]) / n)
+        if verbose:
+            print(f"depth {depth:2d}: {rows[-1]}  ({_time.perf_counter() - t0:.2f} s)", flush=True)
     return rows
 
 

@@ -18,6 +18,8 @@
 #include "qk_common.cuh"
 #include "qk_perft_core.cuh"
 
+#include <stdlib.h>
+
 namespace qk {
 
 static constexpr unsigned kBlock = 256;
@@ -253,6 +255,131 @@ __global__ void __launch_bounds__(kBlock) k_perft_dfs(const uint4 *__restrict__ 
         if (ws.cnt[k]) atomicAdd(counters + k, ws.cnt[k]);
 }
 
+// ------------------------------------------------------------------ lane-parallel DFS
+// One frontier item per LANE.  Every loop iteration each busy lane handles exactly one node
+// (descend to the next unvisited child of its top frame, evaluate it, push or return), so all
+// lanes run the same instruction stream no matter how deep they are: the right shape for the
+// narrow, deep subtrees of the late game, where the warp-cooperative kernel above would spend a
+// whole warp on nodes with two or three children.  Frames are just the 64-bit masks of unvisited
+// non-winning children (the in-flight child is the lowest set bit of its parent's mask); the
+// position itself lives in registers and is rebuilt on the way up by clearing the square.
+// Idle lanes pull new items from a global counter (one aggregated atomic per warp and refill).
+static constexpr int kLaneWarps = 4;                  // 128 threads per CTA
+static constexpr int kLaneFrames = 13;                // plies below an item with their own frame
+static constexpr int kLaneLevels = kLaneFrames + 2;   // counter rows, relative to the item depth
+
+struct LaneScratch {
+    u64 frame[kLaneFrames][32];                       // [level][lane]
+    unsigned cnt[3][kLaneLevels][32];                 // nodes / wins / blocked per relative depth, unweighted
+    u64 acc[5 * kRows];                               // this warp's weighted share of the counters
+};
+
+__device__ __forceinline__ State4 clear_square(State4 s, int action)
+{
+    const uint32_t b = ~(0x00010001u << (action & 15));
+    s.x &= b; s.y &= b; s.z &= b; s.w &= b;
+    return s;
+}
+
+__global__ void __launch_bounds__(kLaneWarps * 32) k_perft_lane(const uint4 *__restrict__ items, const u64 *__restrict__ mult,
+                                                                 u64 n_items, int d0, int depth, u64 *__restrict__ next_item,
+                                                                 u64 *__restrict__ counters)
+{
+    __shared__ LaneScratch s_scratch[kLaneWarps];
+    LaneScratch &ws = s_scratch[threadIdx.x >> 5];
+    const unsigned lane = threadIdx.x & 31u;
+    for (int k = lane; k < 5 * kRows; k += 32) ws.acc[k] = 0;
+    for (int k = 0; k < 3 * kLaneLevels; ++k) (&ws.cnt[0][0][0])[k * 32 + lane] = 0;
+    __syncwarp();
+
+    const int rem0 = depth - d0;          // 1 <= rem0 <= kLaneFrames + 1
+    State4 cur = { 0, 0, 0, 0 };          // position of the top frame
+    int sp = -1;                          // top frame (= plies below the item); -1: no item
+    int parity = 0;                       // player to move at the item
+    u64 m = 0;                            // multiplicity of the item
+    unsigned since_flush = 0;
+    bool more = true;                     // the global queue may still have items
+
+    for (;;) {
+        // ---- idle lanes take the next items
+        State4 node = cur;
+        int level = sp + 1;
+        bool have = sp >= 0;
+        const unsigned idle = __ballot_sync(kFull, sp < 0);
+        if (idle && more) {
+            u64 base = 0;
+            if (lane == (unsigned)(__ffs((int)idle) - 1)) base = atomicAdd(next_item, (u64)__popc(idle));
+            base = __shfl_sync(kFull, base, __ffs((int)idle) - 1);
+            if (sp < 0) {
+                const u64 idx = base + __popc(idle & ((1u << lane) - 1u));
+                if (idx < n_items) {
+                    node = to_state(__ldg(items + idx));
+                    m = mult[idx];
+                    parity = piece_balance(node);
+                    level = 0;
+                    have = true;
+                }
+            }
+            more = base + __popc(idle) < n_items;
+        }
+        if (!__any_sync(kFull, have)) break;
+
+        if (have) {
+            if (level > 0) {   // descend: the in-flight child is the lowest set bit of the parent's mask
+                const u64 fm = ws.frame[sp][lane];
+                node = apply_action(cur, (parity + sp) & 1, __ffsll((long long)fm) - 1);
+            }
+            // ---- evaluate the node: its moves, its winning moves (game_stats.py:384-424)
+            const int mover = (parity + level) & 1;
+            uint32_t lo, hi, wab, wcd;
+            legal_masks(node, mover, lo, hi);
+            winning_squares(node, wab, wcd);
+            const int n_moves = popc(lo) + popc(hi);
+            const int n_wins = popc(lo & wab) + popc(hi & wcd);
+            const uint32_t nl = lo & ~wab, nh = hi & ~wcd;
+            ws.cnt[0][level + 1][lane] += (unsigned)n_moves;
+            ws.cnt[1][level + 1][lane] += (unsigned)n_wins;
+            ws.cnt[2][level][lane] += n_moves == 0 ? 1u : 0u;
+            since_flush += 64;
+            bool done = false;                                   // item finished
+            if (rem0 - level >= 2 && (nl | nh)) {
+                cur = node; sp = level;                          // push
+                ws.frame[level][lane] = ((u64)nh << 32) | nl;
+            } else if (level == 0) {
+                done = true;                                     // nothing to visit below the item
+            } else {
+                // return from the child, then from every frame it exhausts
+                u64 fm = ws.frame[sp][lane];
+                fm &= fm - 1;
+                ws.frame[sp][lane] = fm;
+                while (fm == 0) {
+                    if (--sp < 0) { done = true; break; }
+                    fm = ws.frame[sp][lane];
+                    cur = clear_square(cur, __ffsll((long long)fm) - 1);
+                    fm &= fm - 1;
+                    ws.frame[sp][lane] = fm;
+                }
+            }
+            // ---- fold the lane's unweighted tallies into the warp's weighted counters
+            if (done || since_flush >= 0x70000000u) {
+                for (int r = 0; r <= rem0; ++r) {
+                    const unsigned c_nodes = ws.cnt[0][r][lane], c_wins = ws.cnt[1][r][lane], c_blk = ws.cnt[2][r][lane];
+                    ws.cnt[0][r][lane] = 0; ws.cnt[1][r][lane] = 0; ws.cnt[2][r][lane] = 0;
+                    const int e = d0 + r;                        // absolute depth; ply e was played by (parity + r - 1) & 1
+                    if (c_nodes) atomicAdd(&ws.acc[0 * kRows + e], (u64)c_nodes * m);
+                    if (c_wins) atomicAdd(&ws.acc[(1 + ((parity + r + 1) & 1)) * kRows + e], (u64)c_wins * m);
+                    if (c_blk) atomicAdd(&ws.acc[(3 + ((parity + r) & 1)) * kRows + e], (u64)c_blk * m);
+                }
+                since_flush = 0;
+            }
+            if (done) sp = -1;
+        }
+    }
+    __syncwarp();
+    for (int k = lane; k < 5 * kRows; k += 32)
+        if (ws.acc[k]) atomicAdd(counters + k, ws.acc[k]);
+}
+
 // ------------------------------------------------------------------ host driver
 int run_perft(Call &call, const uint4 *roots, const uint64_t *mult, size_t n_roots, int depth, uint64_t *host_out)
 {
@@ -273,8 +400,12 @@ int run_perft(Call &call, const uint4 *roots, const uint64_t *mult, size_t n_roo
     QK_CUDA(cudaMemcpyAsync(&n_cur, d_count, sizeof(u64), cudaMemcpyDeviceToHost, s));
     QK_CUDA(cudaStreamSynchronize(s));
 
-    // widen until every warp of a full machine has several items (or the target is near)
-    const u64 want_items = (u64)c->sms * 4 * kWarps * 8;
+    // Widen level by level until there is enough independent work, then walk depth-first:
+    //  * shallow, wide remainders (<= 3 plies from early positions): one item per WARP (k_perft_dfs)
+    //  * anything deeper: one item per LANE (k_perft_lane), which needs many more items
+    const u64 want_warp_items = (u64)c->sms * 4 * kWarps * 8;
+    const u64 want_lane_items = (u64)c->sms * 2048 * 8;
+    const char *force = getenv("QK_PERFT_KERNEL");              // "warp" / "lane": benchmarking aid
     int d = 0;
     while (n_cur > 0 && d < depth) {
         const int rem = depth - d;
@@ -283,9 +414,19 @@ int run_perft(Call &call, const uint4 *roots, const uint64_t *mult, size_t n_roo
             QK_CUDA(cudaGetLastError());
             break;
         }
-        if (n_cur >= want_items || n_cur * 64 > (1ull << 26)) {
+        const bool lane_mode = force ? force[0] == 'l' : rem > 3;
+        const bool can_lane = rem <= kLaneFrames + 1;
+        const bool enough = lane_mode ? (n_cur >= want_lane_items && can_lane) : n_cur >= want_warp_items;
+        const bool too_big = n_cur * 64 > (1ull << 28);        // next frontier would not be worth materialising
+        if (enough || (too_big && (can_lane || !lane_mode))) {
             QK_CUDA(cudaMemsetAsync(d_next, 0, sizeof(u64), s));
-            k_perft_dfs<<<c->sms * 4, kBlock, 0, s>>>(cur_s, cur_m, n_cur, d, depth, d_next, d_ctr);
+            if (lane_mode && can_lane) {
+                int per_sm = 0;
+                QK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_perft_lane, kLaneWarps * 32, 0));
+                k_perft_lane<<<c->sms * (per_sm > 0 ? per_sm : 1), kLaneWarps * 32, 0, s>>>(cur_s, cur_m, n_cur, d, depth, d_next, d_ctr);
+            } else {
+                k_perft_dfs<<<c->sms * 4, kBlock, 0, s>>>(cur_s, cur_m, n_cur, d, depth, d_next, d_ctr);
+            }
             QK_CUDA(cudaGetLastError());
             break;
         }

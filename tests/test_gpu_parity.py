@@ -285,6 +285,36 @@ def test_perft_weighted_canonical_roots_and_oracle():
         assert np.array_equal(g[k], o[k]), k
 
 
+def test_perft_lane_kernel_matches_warp_kernel_and_oracle(monkeypatch):
+    e = np.zeros((1, 8), np.uint16)
+    roots = O.make_roots(64, seed=4242, min_plies=8, span=4)
+    mult = np.arange(1, 65, dtype=np.uint64)
+    mid = O.make_roots(3000, seed=17, min_plies=4, span=5)
+    ref6 = None
+    for mode in ("warp", "lane"):
+        monkeypatch.setenv("QK_PERFT_KERNEL", mode)
+        p = B.perft(e, 6)
+        assert B.symmetry_table_rows(p) == PUBLISHED, mode
+        for depth in (2, 3, 5, 7):
+            g, o = B.perft(roots, depth, mult), O.perft(roots, depth, mult)
+            for k in o:
+                assert np.array_equal(g[k], o[k]), (mode, depth, k)
+        g = B.perft(mid, 4)
+        ref6 = ref6 or g
+        for k in g:
+            assert np.array_equal(g[k], ref6[k]), (mode, k)
+    monkeypatch.delenv("QK_PERFT_KERNEL")
+    # the automatic choice (lane kernel below wide frontiers) on a deep job: depth-4 classes + 6 = depth 10
+    d = _npz("depth4_canonical.npz")
+    p = B.perft(d["states"], 6, d["mult"])
+    rows = B.symmetry_table(10)
+    for r in range(1, 7):
+        want = rows[4 + r - 1]
+        assert [int(p["nodes"][r]), int(p["wins_p0"][r]) + int(p["blocked_p1_loses"][r - 1]),
+                int(p["wins_p1"][r]) + int(p["blocked_p0_loses"][r - 1]),
+                int(p["nodes"][r]) - int(p["wins_p0"][r]) - int(p["wins_p1"][r])] == [want[0], want[2], want[3], want[4]]
+
+
 def test_perft_is_symmetry_invariant():
     roots = O.make_roots(16, seed=31, min_plies=4, span=3)
     base = B.perft(roots, 4)

@@ -37,10 +37,10 @@ UNIT = "playouts/s"
 PLAYOUTS_PER_STEP = 1 << 30
 SEED = 0x5155414E54494B31
 # Integer-op model (which replaces the SURVEY 8d estimate made before the
-# incremental formulation existed): 60 lane-ops per ply (of which 46 on the 64-lane ALU pipe),
-# 11.08 plies per empty-board playout; 131 per visited perft leaf parent = 4.9 per counted node at
-# depth 6; 384 per canonical key (192-image mode).
-OPS_PER_PLY, ALU_OPS_PER_PLY, PLIES_PER_PLAYOUT, OPS_PER_NODE, OPS_PER_KEY = 60.0, 46.0, 11.08, 4.9, 384.0
+# incremental formulation existed): 60 lane-ops per ply, of which 36 issue to the 64-lane ALU pipe
+# and 24 to the FMA-heavy pipe (IMAD; IMAD.WIDE counts double); 11.08 plies per empty-board playout;
+# 131 per visited perft leaf parent = 4.9 per counted node at depth 6; 384 per canonical key.
+OPS_PER_PLY, ALU_OPS_PER_PLY, PLIES_PER_PLAYOUT, OPS_PER_NODE, OPS_PER_KEY = 60.0, 36.0, 11.08, 4.9, 384.0
 OPS_PER_PLAYOUT = OPS_PER_PLY * PLIES_PER_PLAYOUT
 
 
@@ -269,6 +269,15 @@ def main():
         extra["perft_depth6_nodes_per_s"] = nodes / dt
         extra["perft_depth6_ms"] = dt * 1e3
         extra["perft_frac_int_issue"] = nodes / dt * OPS_PER_NODE / nominal_peak
+        # config 5 / SURVEY 8f-1: the complete canonical game tree (depth 1..16) with the fused BFS
+        B.symmetry_table(6, device=dev)
+        t0 = time.perf_counter()
+        rows = B.symmetry_table(16, device=dev)
+        dt = time.perf_counter() - t0
+        assert [r[1] for r in rows[:8]] == [3, 51, 726, 10946, 105632, 901916, 4658465, 17900160]
+        extra["full_game_tree_bfs_s"] = dt
+        extra["full_game_tree_canonical_states"] = int(sum(r[1] for r in rows))
+        extra["full_game_tree_legal_moves"] = int(sum(r[0] for r in rows))
         # config 3: canonical keys over 2^26 device-resident states (random positions x random symmetries)
         n_keys = 1 << 26
         base = B.random_roots(1 << 20, seed=SEED, min_plies=0, span=13, device=dev, as_torch=True)

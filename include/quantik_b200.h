@@ -180,6 +180,9 @@ QK_API int qk_perft(const uint16_t *roots, const uint64_t *mult, size_t n_roots,
  * second for (a) a pure LOP3/IADD3 stream and (b) a LOP3 + IMAD mix: the measured
  * integer-issue roofline denominators used by bench.py.                                   */
 QK_API int qk_int_issue_peak(int dev, double *alu_lane_ops_per_s, double *mixed_lane_ops_per_s);
+/* Per-instruction-class issue rates (8 doubles, lane-ops/s): LOP3, IMAD, IMAD.HI, IMAD.WIDE, POPC,
+ * LOP3+IMAD 1:1, LOP3+IMAD.HI 1:1, SHF+LOP3 1:1.  The machine model behind DESIGN.md section 5. */
+QK_API int qk_pipe_rates(int dev, double *lane_ops_per_s);
 
 #ifdef __cplusplus
 }

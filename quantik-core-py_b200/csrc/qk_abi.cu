@@ -403,4 +403,12 @@ int qk_int_issue_peak(int dev, double *alu_lane_ops_per_s, double *mixed_lane_op
     return QK_OK;
 }
 
+int qk_pipe_rates(int dev, double *lane_ops_per_s)
+{
+    void *stream = nullptr;
+    QK_REQUIRE(lane_ops_per_s, "qk_pipe_rates: NULL output");
+    QK_BEGIN(call);
+    return run_pipe_rates(call.ctx(), lane_ops_per_s);
+}
+
 }  // extern "C"

@@ -191,9 +191,9 @@ QK_HD void ply_step(PlayState &st, uint32_t rnd, const SquareLut *lut, const uin
 // IADD3 all issue to one 64-lane ALU pipe (0.5 warp-instructions per clock per scheduler) while IMAD
 // goes to the FMA pipe, so a ply written with compares and selects is ALU-pipe bound at half the issue
 // rate (ncu, profiles/r01b_playout_ncu.txt: ALU 72 %, FMA 15 %).  Here the popcount descent is integer
-// multiply-add arithmetic instead: "k >= c" is the sign of k - c obtained with one IMAD.HI
-// (mul.hi(d, 2) = d >> 31), and every conditional update is  x = flag * a + b.  `two` must be a value
-// the compiler cannot see (kernel argument) or ptxas turns the multiply back into a shift.
+// multiply-add arithmetic instead: "k < c" is the sign bit of k - c (one SHF) and every conditional
+// update is  x = flag * a + b  (one IMAD, 2 cycles on the FMA-heavy pipe; IMAD.HI / IMAD.WIDE cost 4,
+// measured with qk_pipe_rates).  The split keeps both pipes near 75 cycles per warp-ply.
 __device__ __forceinline__ uint32_t qk_mulhi(uint32_t a, uint32_t b)
 {
     uint32_t d;
@@ -228,28 +228,28 @@ __device__ __forceinline__ void ply_step_fma(PlayState &st, uint32_t rnd, const 
 
     // 64 -> 32: lo if k < nlo
     uint32_t d = k - nlo;
-    const uint32_t in_lo = qk_mulhi(d, two);                       // 1: shapes A,B   0: shapes C,D
+    const uint32_t in_lo = d >> 31;                                // 1: shapes A,B   0: shapes C,D
     uint32_t w = qk_mad(in_lo, legal_lo - legal_hi, legal_hi);
     k = qk_mad(in_lo, nlo, d);
     // 32 -> 16: lower lane if k < c
     uint32_t c = (uint32_t)__popc(w << 16);
     d = k - c;
-    const uint32_t even = qk_mulhi(d, two);                        // 1: shape A / C   0: shape B / D
+    const uint32_t even = d >> 31;                                 // 1: shape A / C   0: shape B / D
     k = qk_mad(even, c, d);
     w >>= qk_mad(even, 0xFFFFFFF0u, 16u);                          // 16 - 16 * even
     // 16 -> 8
     c = (uint32_t)__popc(w << 24);
     d = k - c;
-    const uint32_t low8 = qk_mulhi(d, two);                        // 1: squares 0..7
+    const uint32_t low8 = d >> 31;                                 // 1: squares 0..7
     k = qk_mad(low8, c, d);
     w >>= qk_mad(low8, 0xFFFFFFF8u, 8u);                           // 8 - 8 * low8
     // last three levels from the byte table; off = 16 * square
-    const uint32_t idx = qk_madhi(w << 24, two << 10, k);          // (w & 0xFF) << 3 | k
+    const uint32_t idx = ((w & 0xFFu) << 3) | k;
     const uint32_t off = qk_mad(low8, 0xFFFFFF80u, 128u) + (uint32_t)sel8[idx];
 
     // lane masks: which 16-bit lane of which half receives the piece
     const uint32_t lane = qk_mad(even, 0x0000FFFFu - 0xFFFF0000u, 0xFFFF0000u);
-    const uint32_t l_lo = in_lo * lane, l_hi = lane - l_lo;
+    const uint32_t l_lo = qk_mad(in_lo, lane, 0u), l_hi = lane - l_lo;
     const SquareLut e = *reinterpret_cast<const SquareLut *>(reinterpret_cast<const char *>(lut) + off);
     st.free2 &= ~e.bit2;
     ro_lo |= e.scope2 & l_lo;  ro_hi |= e.scope2 & l_hi;

@@ -52,6 +52,7 @@ PROTOTYPES = {
     "qk_perft": (c_int, [c_void_p, c_void_p, c_size_t, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                          c_int, c_void_p]),
     "qk_int_issue_peak": (c_int, [c_int, POINTER(c_double), POINTER(c_double)]),
+    "qk_pipe_rates": (c_int, [c_int, POINTER(c_double)]),
 }
 
 _lib = None

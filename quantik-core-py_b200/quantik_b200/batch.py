@@ -322,3 +322,12 @@ def int_issue_peak(device: int = 0):
     a, m = ctypes.c_double(), ctypes.c_double()
     N.check(lib.qk_int_issue_peak(device, ctypes.byref(a), ctypes.byref(m)))
     return {"alu": a.value, "mixed": m.value}
+
+
+def pipe_rates(device: int = 0):
+    """Measured issue rate (lane-ops/s) per instruction class; see include/quantik_b200.h qk_pipe_rates."""
+    lib = N.init(device)
+    out = (ctypes.c_double * 8)()
+    N.check(lib.qk_pipe_rates(device, out))
+    names = ["lop3", "imad", "imad_hi", "imad_wide", "popc", "lop3_imad", "lop3_imad_hi", "shf_lop3"]
+    return dict(zip(names, [float(x) for x in out]))

@@ -132,6 +132,18 @@ QK_API int qk_bfs_level(const uint16_t *states, const uint64_t *mult, size_t n, 
                         uint16_t *uniq, uint64_t *uniq_mult, size_t cap, size_t *n_uniq,
                         uint64_t *stats, int dev, void *stream);
 
+/* qk_book_level     <- one depth of the opening-book BFS (examples/generate_opening_book.py:185-280
+ *                      _expand_chunk, :458-496 dedup) counted like opening_book_summary.build_summary
+ *                      (opening_book_summary.py:36-93).  states = the canonical classes of one depth,
+ *                      finished ones included.  stats (host, 2 values) = terminal classes (line complete,
+ *                      or mover without a move: not expanded) and edges (distinct parent-class /
+ *                      child-class pairs).  uniq (capacity cap + 1) receives the classes of the next
+ *                      depth in table order, uniq_indegree their number of distinct parents, *n_uniq the
+ *                      count.  QK_E_NOMEM when the next depth exceeds cap.  Synchronous.               */
+QK_API int qk_book_level(const uint16_t *states, size_t n, int color_swap, uint16_t *uniq,
+                         uint64_t *uniq_indegree, size_t cap, size_t *n_uniq, uint64_t *stats,
+                         int dev, void *stream);
+
 /* ---- random playouts ---------------------------------------------------------------
  * qk_playouts       <- BeamSearchEngine._rollout/_default_evaluate (beam_search.py:614-645)
  *                      when max_plies < 0 (play to a true terminal; result +-1), and

@@ -330,6 +330,19 @@ def main():
         api.append(_case_report({"case_id": cid, "qfen": q, "move": {"shape": mv[0], "position": mv[1]}}))
     meta["api_portability_cases"] = api
     json.dump(meta, open(os.path.join(OUT, "reference_meta.json"), "w"), indent=1)
+
+    # ---- 9. opening-book-summary.v1 of a full-width depth-5 book built by the reference's own generator
+    #         (examples/generate_opening_book.py -> sqlite -> opening_book_summary.build_summary; ~3 min, 8 workers)
+    if "--book" in sys.argv:
+        import tempfile
+        from pathlib import Path
+        sys.path.insert(0, os.path.join(REF, "examples"))
+        import generate_opening_book as GB
+        from quantik_core.opening_book_summary import build_summary
+        tmp = Path(tempfile.mkdtemp())
+        GB.DATA_DIR = tmp
+        GB.generate(max_depth=5, db_path=tmp / "book_d5.sqlite", num_workers=8)
+        json.dump(build_summary(tmp / "book_d5.sqlite", 5), open(os.path.join(OUT, "opening_book_summary_d5.json"), "w"), indent=1)
     print(f"all golden fixtures written to {os.path.normpath(OUT)}  [{time.time()-t0:.1f}s]")
 
 

@@ -201,4 +201,11 @@ def symmetry_table(max_depth: int, emit_depth: int = 0, cap: int = 0):
     return stats
 
 
+def opening_book_summary(max_depth: int) -> np.ndarray:
+    """rows (positions, terminal, edges) for depth 0..max_depth, as opening_book_summary.build_summary counts them."""
+    out = np.zeros((max_depth + 1, 3), np.uint64)
+    lib().qo_opening_book_summary(ctypes.c_int(max_depth), _p(out))
+    return out
+
+
 __all__ = [n for n in dir() if not n.startswith("_")]

@@ -600,6 +600,49 @@ QO_API long qo_symmetry_table(int max_depth, uint64_t *stats, int emit_depth,
     return emitted;
 }
 
+/* ------------------------------------------------------------------------ */
+/* Opening-book BFS (examples/generate_opening_book.py:185-280 _expand_chunk +   */
+/* :458-496 main-process dedup) summarised like opening_book_summary.build_summary */
+/* (opening_book_summary.py:36-93): per depth d                                   */
+/*   positions = distinct canonical keys first reached at depth d (won ones too)  */
+/*   terminal  = those that are won, or whose mover has no legal move             */
+/*   edges     = distinct (parent key, child key) pairs of the expanded parents   */
+/* out[(d)*3 + {0,1,2}].                                                          */
+/* ------------------------------------------------------------------------ */
+QO_API void qo_opening_book_summary(int max_depth, uint64_t *out)
+{
+    build_perms();
+    bfs_level cur; level_init(&cur, 1024);
+    uint16_t empty[8] = {0};
+    level_add(&cur, empty, empty, 1);
+    for (int d = 0; d <= max_depth; ++d) {
+        bfs_level nxt; level_init(&nxt, cur.n * 8);
+        uint64_t terminal = 0, edges = 0;
+        for (size_t j = 0; j < cur.n; ++j) {
+            const uint16_t *bb = cur.v[j].rep;
+            if (qo_check_game_winner(bb)) { ++terminal; continue; }          /* :205-211 */
+            int player, st;
+            uint64_t mask = qo_legal_mask(bb, &player, &st);
+            if (mask == 0) { ++terminal; continue; }                          /* :212-223 */
+            uint16_t kids[64][8]; int nk = 0;
+            for (int a = 0; a < 64; ++a) {
+                if (!((mask >> a) & 1ull)) continue;
+                uint16_t child[8], canon[8];
+                qo_apply(bb, player, a >> 4, a & 15, child);                  /* :237-242 */
+                qo_find_canonical(child, 0, canon, NULL);
+                int dup = 0;
+                for (int k = 0; k < nk; ++k) if (!memcmp(kids[k], canon, 16)) { dup = 1; break; }
+                if (!dup) { memcpy(kids[nk++], canon, 16); }                  /* PRIMARY KEY (parent_key, child_key) */
+                if (d < max_depth) level_add(&nxt, canon, child, 1);
+            }
+            edges += (uint64_t)nk;
+        }
+        out[d * 3 + 0] = cur.n; out[d * 3 + 1] = terminal; out[d * 3 + 2] = edges;
+        level_free(&cur); cur = nxt;
+    }
+    level_free(&cur);
+}
+
 QO_API int qo_num_threads(void)
 {
 #ifdef _OPENMP

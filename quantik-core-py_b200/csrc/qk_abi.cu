@@ -319,6 +319,23 @@ int qk_bfs_level(const uint16_t *states, const uint64_t *mult, size_t n, int col
     return call.finish();
 }
 
+int qk_book_level(const uint16_t *states, size_t n, int color_swap, uint16_t *uniq, uint64_t *uniq_indegree, size_t cap,
+                  size_t *n_uniq, uint64_t *stats, int dev, void *stream)
+{
+    QK_REQUIRE(n_uniq && stats && uniq && uniq_indegree, "qk_book_level: NULL output");
+    QK_REQUIRE(states || n == 0, "qk_book_level: states is NULL");
+    QK_REQUIRE(cap > 0, "qk_book_level: cap must be positive");
+    *n_uniq = 0;
+    stats[0] = stats[1] = 0;
+    if (n == 0) return QK_OK;
+    QK_BEGIN(call);
+    const uint4 *d_states = (const uint4 *)call.in(states, n * 16);
+    QK_CHECK(call);
+    int rc = run_book_level(call, d_states, n, color_swap, uniq, uniq_indegree, cap, n_uniq, stats);
+    if (rc != QK_OK) return rc;
+    return call.finish();
+}
+
 int qk_playouts_ex(const uint16_t *roots, size_t n_roots, uint32_t rollouts_per_root, uint64_t seed,
                    uint64_t first_rollout, uint32_t root_index_base, int max_plies, uint32_t *wins_p0,
                    uint32_t *wins_p1, uint32_t *draws, int8_t *per_playout, uint8_t *per_plies, int dev, void *stream)

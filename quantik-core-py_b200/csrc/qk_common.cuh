@@ -83,6 +83,8 @@ int run_dedup(Call &call, const uint4 *states, const uint64_t *mult, size_t n, i
               uint16_t *uniq_host_or_dev, uint64_t *uniq_mult, size_t cap, size_t *n_uniq);
 int run_bfs_level(Call &call, const uint4 *parents, const uint64_t *mult, size_t n, int color_swap, int sort_output,
                   uint16_t *uniq, uint64_t *uniq_mult, size_t cap, size_t *n_uniq, uint64_t *h_stats);
+int run_book_level(Call &call, const uint4 *parents, size_t n, int color_swap, uint16_t *uniq, uint64_t *uniq_mult,
+                   size_t cap, size_t *n_uniq, uint64_t *h_stats);
 int run_issue_peak(Ctx *c, double *alu, double *mixed);
 int run_pipe_rates(Ctx *c, double *out8);
 

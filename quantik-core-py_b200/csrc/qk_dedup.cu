@@ -200,6 +200,82 @@ __global__ void __launch_bounds__(kBlock) k_bfs_expand_insert(const uint4 *__res
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// One depth of the opening-book BFS (examples/generate_opening_book.py:185-280,458-496) with the
+// counting of opening_book_summary.build_summary (opening_book_summary.py:36-93): positions are
+// canonical classes INCLUDING finished ones; a finished position (line complete, or mover without a
+// move) is terminal and not expanded; an edge is a distinct (parent class, child class) pair.
+// Warp per parent; the distinct children of a parent are found with match.any on both key halves
+// (lanes l / l+32 hold children l / l+32; the second batch is checked against the first through
+// shared memory).  Only one lane per distinct child inserts, so the stored multiplicity of a class is
+// its in-degree in position_edges.    stats: [0] terminal parents  [1] edges
+template <bool COLOR_SWAP>
+__global__ void __launch_bounds__(kBlock) k_book_expand_insert(const uint4 *__restrict__ parents, size_t n, Slot *table, u64 *counts,
+                                                                size_t slot_mask, u64 *n_unique, u64 *all_ones_count, int *overflow,
+                                                                u64 max_unique, u64 *stats)
+{
+    __shared__ Slot s_first[kBlock / 32][32];
+    Slot *first = s_first[threadIdx.x >> 5];
+    const unsigned lane = threadIdx.x & 31u;
+    const size_t warp = (blockIdx.x * (size_t)kBlock + threadIdx.x) >> 5, n_warps = ((size_t)gridDim.x * kBlock) >> 5;
+    u64 s_terminal = 0, s_edges = 0;
+    for (size_t i = warp; i < n; i += n_warps) {
+        if (*reinterpret_cast<volatile int *>(overflow)) break;
+        const uint4 v = __ldg(parents + i);
+        const State4 parent = { v.x, v.y, v.z, v.w };
+        if (has_winning_line(parent)) { ++s_terminal; continue; }                       // generate_opening_book.py:205-211
+        const int mover = piece_balance(parent);
+        uint32_t lo, hi;
+        legal_masks(parent, mover, lo, hi);
+        if ((lo | hi) == 0) { ++s_terminal; continue; }                                 // :212-223
+        Slot key[2];
+        bool leader[2];
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const bool has = ((half ? hi : lo) >> lane) & 1u;
+            key[half].hi = ~0ull; key[half].lo = ~0ull;
+            leader[half] = false;
+            const unsigned mask = __ballot_sync(0xFFFFFFFFu, has);
+            if (has) {
+                const State4 c = canonical<COLOR_SWAP>(apply_action(parent, mover, half * 32 + (int)lane));   // :237-242
+                key[half].hi = ((u64)prmt(c.x, 0, 0x0123) << 32) | prmt(c.y, 0, 0x0123);
+                key[half].lo = ((u64)prmt(c.z, 0, 0x0123) << 32) | prmt(c.w, 0, 0x0123);
+                const unsigned same = __match_any_sync(mask, key[half].hi) & __match_any_sync(mask, key[half].lo);
+                leader[half] = (unsigned)(__ffs((int)same) - 1) == lane;
+            }
+            if (half == 0) { first[lane] = key[0]; __syncwarp(); }
+        }
+        if (leader[1])                                                   // already among the first 32 children?
+            for (int j = 0; j < 32; ++j)
+                if (first[j].hi == key[1].hi && first[j].lo == key[1].lo) { leader[1] = false; break; }
+        __syncwarp();
+        s_edges += (u64)(__popc(__ballot_sync(0xFFFFFFFFu, leader[0])) + __popc(__ballot_sync(0xFFFFFFFFu, leader[1])));
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            if (!leader[half]) continue;
+            const u64 khi_new = key[half].hi, klo_new = key[half].lo;
+            if ((khi_new & klo_new) == ~0ull) { atomicAdd(all_ones_count, 1ull); continue; }
+            size_t slot = (size_t)mix(khi_new, klo_new) & slot_mask;
+            for (size_t probe = 0; probe <= slot_mask; ++probe, slot = (slot + 1) & slot_mask) {
+                const ulonglong2 raw = __ldcv(reinterpret_cast<const ulonglong2 *>(table + slot));
+                u64 khi = raw.x, klo = raw.y;
+                if (khi == ~0ull || klo == ~0ull) {
+                    cas128(table + slot, ~0ull, ~0ull, khi_new, klo_new, khi, klo);
+                    if (khi == ~0ull && klo == ~0ull) {
+                        if (atomicAdd(n_unique, 1ull) >= max_unique) *overflow = 1;
+                        khi = khi_new; klo = klo_new;
+                    }
+                }
+                if (khi == khi_new && klo == klo_new) { atomicAdd(counts + slot, 1ull); break; }
+            }
+        }
+    }
+    if (lane == 0) {
+        if (s_terminal) atomicAdd(stats + 0, s_terminal);
+        if (s_edges) atomicAdd(stats + 1, s_edges);
+    }
+}
+
 // ------------------------------------------------------------------ host side
 struct DedupTable { Slot *table; u64 *counts; u64 *meta; size_t slots; u64 max_unique; };
 
@@ -317,6 +393,28 @@ int run_bfs_level(Call &call, const uint4 *parents, const uint64_t *mult, size_t
                                                           (int *)(t.meta + 3), t.max_unique, t.meta + 4);
     QK_CUDA(cudaGetLastError());
     return dedup_finish(call, t, uniq, uniq_mult, cap, n_uniq, h_stats, "qk_bfs_level", sort_output != 0);
+}
+
+int run_book_level(Call &call, const uint4 *parents, size_t n, int color_swap, uint16_t *uniq, uint64_t *uniq_mult,
+                   size_t cap, size_t *n_uniq, uint64_t *h_stats)
+{
+    cudaStream_t s = call.stream();
+    Ctx *c = call.ctx();
+    DedupTable t;
+    int rc = dedup_begin(call, cap, t);
+    if (rc != QK_OK) return rc;
+    const unsigned grid = grid_for(n * 32, kBlock, c->sms, 8);
+    if (color_swap)
+        k_book_expand_insert<true><<<grid, kBlock, 0, s>>>(parents, n, t.table, t.counts, t.slots - 1, t.meta, t.meta + 1,
+                                                          (int *)(t.meta + 3), t.max_unique, t.meta + 4);
+    else
+        k_book_expand_insert<false><<<grid, kBlock, 0, s>>>(parents, n, t.table, t.counts, t.slots - 1, t.meta, t.meta + 1,
+                                                           (int *)(t.meta + 3), t.max_unique, t.meta + 4);
+    QK_CUDA(cudaGetLastError());
+    uint64_t st[5] = { 0, 0, 0, 0, 0 };
+    rc = dedup_finish(call, t, uniq, uniq_mult, cap, n_uniq, st, "qk_book_level", false);
+    h_stats[0] = st[0]; h_stats[1] = st[1];
+    return rc;
 }
 
 }  // namespace qk

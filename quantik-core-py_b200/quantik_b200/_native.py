@@ -44,6 +44,8 @@ PROTOTYPES = {
                                POINTER(c_size_t), c_int, c_void_p]),
     "qk_bfs_level": (c_int, [c_void_p, c_void_p, c_size_t, c_int, c_int, c_void_p, c_void_p, c_size_t, POINTER(c_size_t),
                              c_void_p, c_int, c_void_p]),
+    "qk_book_level": (c_int, [c_void_p, c_size_t, c_int, c_void_p, c_void_p, c_size_t, POINTER(c_size_t), c_void_p,
+                              c_int, c_void_p]),
     "qk_playouts": (c_int, [c_void_p, c_size_t, c_uint32, c_uint64, c_int, c_void_p, c_void_p, c_void_p,
                             c_void_p, c_int, c_void_p]),
     "qk_playouts_ex": (c_int, [c_void_p, c_size_t, c_uint32, c_uint64, c_uint64, c_uint32, c_int, c_void_p,

@@ -251,6 +251,54 @@ def symmetry_table(max_depth: int, device: Optional[int] = None, on_device: bool
     return rows
 
 
+def book_level(states, color_swap: bool = False, cap: int = 1 << 20, device: Optional[int] = None):
+    """One depth of the opening-book BFS (examples/generate_opening_book.py:185-280): finished classes are
+    terminal and not expanded, every other class contributes its distinct canonical children.
+    -> (classes of the next depth (U, 8), their in-degree (U,), {"terminal": ..., "edges": ...})."""
+    s, on_dev, d = _states_in(states)
+    d = _dev(device, on_dev, d)
+    lib = N.init(d)
+    while True:
+        uniq = _out((cap + 1, 8), np.uint16, on_dev, d)
+        deg = _out((cap + 1,), np.uint64, on_dev, d)
+        nu = ctypes.c_size_t(0)
+        stats = np.zeros(2, np.uint64)
+        rc = lib.qk_book_level(s.ptr, s.n, int(bool(color_swap)), uniq.ptr, deg.ptr, cap, ctypes.byref(nu),
+                               stats.ctypes.data, d, _stream(on_dev, d))
+        if rc == -4:
+            del uniq, deg
+            cap *= 2
+            continue
+        N.check(rc)
+        break
+    return uniq.obj[:nu.value], deg.obj[:nu.value], {"terminal": int(stats[0]), "edges": int(stats[1])}
+
+
+def opening_book_summary(depth: int, device: Optional[int] = None) -> dict:
+    """The ``opening-book-summary.v1`` record (opening_book_summary.py:36-93; the cross-stack contract
+    of .github/workflows/contracts.yml:20-75) of a full-width book built from the empty board to
+    ``depth``, computed by the GPU BFS instead of sqlite."""
+    if depth < 0:
+        raise ValueError("depth must be non-negative")          # opening_book_summary.py:38-39
+    d = 0 if device is None else int(device)
+    frontier = np.zeros((1, 8), np.uint16)
+    if torch is not None:
+        frontier = torch.zeros((1, 8), dtype=torch.int16, device=f"cuda:{d}")
+    per_depth = []
+    growth = 64.0
+    for cur in range(depth + 1):
+        n = int(frontier.shape[0])
+        cap = int(min(64 * max(n, 1), max(1 << 12, 1.6 * growth * n)))
+        nxt, _deg, st = book_level(frontier, cap=cap, device=d) if n else (frontier, None, {"terminal": 0, "edges": 0})
+        per_depth.append({"depth": cur, "positions": n, "terminal": st["terminal"], "edges": st["edges"]})
+        growth = max(0.05, int(nxt.shape[0]) / max(n, 1))
+        frontier = nxt
+    return {"schema": "opening-book-summary.v1", "contract_version": "1.1.0", "depth": depth,
+            "total_positions": sum(r["positions"] for r in per_depth),
+            "terminal_positions": sum(r["terminal"] for r in per_depth),
+            "total_edges": sum(r["edges"] for r in per_depth), "per_depth": per_depth}
+
+
 # ----------------------------------------------------------------------------- playouts
 def playouts(roots, rollouts: int, seed: int = SEED_DEFAULT, max_plies: int = -1, first_rollout: int = 0,
              root_index_base: int = 0, per_playout: bool = False, device: Optional[int] = None) -> Dict[str, object]:

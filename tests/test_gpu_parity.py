@@ -368,6 +368,24 @@ def test_bfs_level_vs_oracle_composition():
     assert np.array_equal(f2, f) and np.array_equal(m2, m)
 
 
+def test_opening_book_summary_contract():
+    # opening-book-summary.v1 written by the reference itself (generate_opening_book.generate -> sqlite ->
+    # opening_book_summary.build_summary, depth 5, 181 s) must be reproduced field for field
+    want = json.load(open(os.path.join(G, "opening_book_summary_d5.json")))
+    assert B.opening_book_summary(5) == want
+    assert B.opening_book_summary(3) == {**{k: want[k] for k in ("schema", "contract_version")}, "depth": 3,
+                                         "total_positions": 781, "terminal_positions": 0, "total_edges": 22998,
+                                         "per_depth": want["per_depth"][:4]}
+    # non-terminal classes per depth are exactly SymmetryTable's unique canonical states
+    s = B.opening_book_summary(8)
+    uniq = [3, 51, 726, 10946, 105632, 901916, 4658465, 17900160]
+    rows = B.symmetry_table(8)
+    for d in range(1, 9):
+        won = s["per_depth"][d]["positions"] - uniq[d - 1]
+        assert won >= 0 and s["per_depth"][d]["terminal"] >= won
+        assert rows[d - 1][1] == uniq[d - 1]
+
+
 # ----------------------------------------------------------------------------- device buffers, engines
 def test_device_tensor_path_matches_host_path():
     import torch

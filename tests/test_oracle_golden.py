@@ -196,3 +196,10 @@ def test_perft_raw_matches_table():
     d = _npz("depth4_canonical.npz")
     r = O.perft(d["states"], 1, d["mult"])
     assert int(r["nodes"][0]) == 6770048 and int(r["nodes"][1]) == 231883776 and int(r["wins_p0"][1]) == 1050624
+
+
+def test_opening_book_summary_vs_reference():
+    # tests/golden/opening_book_summary_d5.json was written by the reference's own generator + build_summary
+    want = json.load(open(os.path.join(G, "opening_book_summary_d5.json")))
+    got = O.opening_book_summary(4)
+    assert got.tolist() == [[r["positions"], r["terminal"], r["edges"]] for r in want["per_depth"][:5]]

@@ -150,6 +150,35 @@ def test_symmetry_images_and_single_state_api():
     assert len(uniq) == 3 and sorted(mult.tolist()) == [16, 16, 32]
 
 
+def test_canonical_properties_at_full_size():
+    """size-independent properties on 2^23 device-resident states (tests/test_core.py:159-181 at scale):
+    idempotence, invariance under every symmetry, orbit-size invariance, multiplicity conservation"""
+    import torch
+    n = 1 << 23
+    base = B.random_roots(1 << 18, seed=77, min_plies=0, span=14, as_torch=True)
+    states = base.repeat(n // (1 << 18), 1)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    d4 = torch.randint(0, 8, (n,), device="cuda", generator=g)
+    perms = torch.tensor([B.encode_transform(0, False, O.perm(i)) for i in range(24)], device="cuda")
+    codes = (perms[torch.randint(0, 24, (n,), device="cuda", generator=g)] | d4).to(torch.int16)
+    images = B.apply_symmetry(states, codes)
+    c0, c1 = B.canonical_payloads(states), B.canonical_payloads(images)
+    assert torch.equal(c0, c1)                                   # invariance: one key per orbit
+    assert torch.equal(B.canonical_payloads(c0), c0)             # idempotence
+    assert torch.equal(B.orbit_sizes(states), B.orbit_sizes(images))
+    # 384-image mode: additionally invariant under the colour swap
+    swapped = B.apply_symmetry(states[: 1 << 20], (codes[: 1 << 20] | 8))
+    assert torch.equal(B.canonical_payloads(states[: 1 << 20], color_swap=True), B.canonical_payloads(swapped, color_swap=True))
+    # dedup conserves multiplicity and returns exactly the distinct canonical payloads
+    uniq, mult = B.canon_dedup(images, cap=1 << 19)
+    assert int(mult.sum()) == n
+    ref = torch.unique(c0.view(torch.int64).reshape(-1, 2), dim=0)
+    assert len(uniq) == len(ref)
+    # spot-check against the oracle
+    idx = torch.randint(0, n, (4096,), device="cuda", generator=g).cpu().numpy()
+    assert np.array_equal(c1.cpu().numpy().view(np.uint16)[idx], O.canonical(images.cpu().numpy().view(np.uint16)[idx]))
+
+
 def test_canon_dedup_vs_oracle_with_multiplicities():
     s = _random_positions(120_000, seed=77)[:60_000]      # reachable states: many symmetric duplicates
     mult = np.random.default_rng(3).integers(1, 1000, len(s)).astype(np.uint64)
@@ -384,6 +413,42 @@ def test_opening_book_summary_contract():
         won = s["per_depth"][d]["positions"] - uniq[d - 1]
         assert won >= 0 and s["per_depth"][d]["terminal"] >= won
         assert rows[d - 1][1] == uniq[d - 1]
+
+
+def test_abi_error_paths_and_degenerate_sizes():
+    import ctypes
+    from quantik_b200 import _native as N
+    lib = N.init(0)
+    s = np.zeros((4, 8), np.uint16)
+    out = np.zeros(4, np.uint8)
+    assert lib.qk_win_status(None, 4, out.ctypes.data, 0, None) == -1 and b"NULL" in lib.qk_last_error()
+    assert lib.qk_win_status(s.ctypes.data, 4, out.ctypes.data, 7, None) == -3          # device never initialised
+    assert lib.qk_init(99) == -1
+    arrs = [np.zeros(20, np.uint64) for _ in range(5)]
+    assert lib.qk_perft(s.ctypes.data, None, 4, 17, *[a.ctypes.data for a in arrs], 0, None) == -1   # depth > 16
+    assert lib.qk_random_roots(1, 0, 4, 10, 8, s.ctypes.data, 0, None) == -1             # 10 + 8 - 1 > 15 plies
+    with pytest.raises(Q.QuantikB200Error):
+        B.canon_dedup(O.make_roots(500), cap=3)                                          # more classes than cap
+    with pytest.raises(ValueError):
+        B.apply_moves(s, np.zeros(3, np.uint8))
+    with pytest.raises(ValueError):
+        B.movegen_masks(np.zeros(7, np.uint16))
+    # zero-sized work is fine everywhere
+    e = np.zeros((0, 8), np.uint16)
+    r = B.playouts(e, 16)
+    assert len(r["wins_p0"]) == 0
+    r = B.playouts(s, 0)
+    assert r["wins_p0"].shape == (4,)
+    p = B.perft(e, 3)
+    assert p["nodes"].tolist() == [0, 0, 0, 0]
+    assert B.perft(s, 0)["nodes"].tolist() == [4]
+    assert len(B.canon_dedup(e)[0]) == 0 and len(B.bfs_level(e)[0]) == 0
+    # full boards and positions without moves
+    full = O.make_roots(2000, seed=3, min_plies=13, span=3)
+    g, o = B.playouts(full, 32, SEED, per_playout=True), O.playouts(full, 32, SEED, per_playout=True)
+    assert np.array_equal(g["outcome"], o["outcome"]) and np.array_equal(g["plies"], o["plies"])
+    for k, v in O.perft(full, 3).items():
+        assert np.array_equal(B.perft(full, 3)[k], v), k
 
 
 # ----------------------------------------------------------------------------- device buffers, engines

@@ -342,7 +342,7 @@ int qk_playouts_ex(const uint16_t *roots, size_t n_roots, uint32_t rollouts_per_
 {
     QK_REQUIRE(roots || n_roots == 0, "qk_playouts: roots is NULL");
     QK_REQUIRE(n_roots < (1ull << 32), "qk_playouts: n_roots must be < 2^32");
-    if (n_roots == 0 || rollouts_per_root == 0) return QK_OK;
+    if (n_roots == 0) return QK_OK;
     QK_BEGIN(call);
     size_t total = n_roots * (size_t)rollouts_per_root;
     const uint4 *d_roots = (const uint4 *)call.in(roots, n_roots * 16);
@@ -353,6 +353,7 @@ int qk_playouts_ex(const uint16_t *roots, size_t n_roots, uint32_t rollouts_per_
     uint8_t *d_pl = (uint8_t *)call.out(per_plies, total);
     void *scratch = call.temp(playout_scratch_bytes(n_roots));
     QK_CHECK(call);
+    if (rollouts_per_root == 0) return call.finish();          // tallies are zero
     int rc = launch_playouts(d_roots, n_roots, rollouts_per_root, seed, first_rollout, root_index_base, max_plies,
                              d_w0, d_w1, d_dr, d_pp, d_pl, scratch, call.ctx(), call.stream());
     if (rc != QK_OK) return rc;

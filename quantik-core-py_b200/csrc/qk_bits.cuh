@@ -53,14 +53,36 @@ QK_HD uint32_t mulhi(uint32_t a, uint32_t b)
 #endif
 }
 
+// ---------------------------------------------------------------- right shift, optionally on the FMA pipe
+// The canonicalisation and perft kernels are bound by the 64-lane ALU pipe (ncu: 96 % / 90 % busy, FMA pipe
+// 6 % / 14 %).  A right shift by a constant is also  mul.hi(x, 2^(32-s)) , which issues to the FMA-heavy pipe
+// (IMAD.HI; the multiplier must be opaque to ptxas, hence the __constant__ table).  MEASURED AND REJECTED
+// (round 1): with all 48 transform shifts moved, canonical keys/s stayed at 4.49e10 and perft(6) went from
+// 3.65 to 3.89 ms -- IMAD.HI is half rate (qk_pipe_rates) and the ALU pipe was not relieved enough to pay
+// for it.  Kept behind QK_IMADHI_SHIFTS for the record; the default is the plain shift.
+#if defined(__CUDACC__) && defined(QK_IMADHI_SHIFTS)
+__constant__ static uint32_t qk_pow2[32] = {
+    1u << 0, 1u << 1, 1u << 2, 1u << 3, 1u << 4, 1u << 5, 1u << 6, 1u << 7, 1u << 8, 1u << 9, 1u << 10, 1u << 11, 1u << 12,
+    1u << 13, 1u << 14, 1u << 15, 1u << 16, 1u << 17, 1u << 18, 1u << 19, 1u << 20, 1u << 21, 1u << 22, 1u << 23, 1u << 24,
+    1u << 25, 1u << 26, 1u << 27, 1u << 28, 1u << 29, 1u << 30, 1u << 31 };
+#endif
+template <int S> QK_HD uint32_t shr(uint32_t x)
+{
+#if defined(__CUDA_ARCH__) && defined(QK_IMADHI_SHIFTS)
+    return __umulhi(x, qk_pow2[32 - S]);
+#else
+    return x >> S;
+#endif
+}
+
 // ---------------------------------------------------------------- line fills
 // For a pair of boards packed in one register: every square that shares a row /
 // column / 2x2 zone with a set square.  (move.py:169-196 tests each square
 // against the 12 WIN_MASKS of commons.py:24-48; this is the closed form.)
-QK_HD uint32_t pair_or1(uint32_t u) { return u | (u >> 1); }
-QK_HD uint32_t row_presence(uint32_t t1) { return (t1 | (t1 >> 2)) & 0x11111111u; }   // bit 4r   of each lane
-QK_HD uint32_t zone_presence(uint32_t t1) { return (t1 | (t1 >> 4)) & 0x05050505u; }  // bits 0,2,8,10
-QK_HD uint32_t col_presence(uint32_t u) { uint32_t t = u | (u >> 4); return (t | (t >> 8)) & 0x000F000Fu; }  // bits 0..3
+QK_HD uint32_t pair_or1(uint32_t u) { return u | shr<1>(u); }
+QK_HD uint32_t row_presence(uint32_t t1) { return (t1 | shr<2>(t1)) & 0x11111111u; }   // bit 4r   of each lane
+QK_HD uint32_t zone_presence(uint32_t t1) { return (t1 | shr<4>(t1)) & 0x05050505u; }  // bits 0,2,8,10
+QK_HD uint32_t col_presence(uint32_t u) { uint32_t t = u | shr<4>(u); return (t | shr<8>(t)) & 0x000F000Fu; }  // bits 0..3
 
 QK_HD uint32_t scope_fill(uint32_t u)
 {
@@ -175,19 +197,19 @@ QK_HD State4 apply_action(State4 s, int player, int action)
 // product of three bit-reversal style generators, applied to both lanes at once.
 QK_HD uint32_t flip_cols(uint32_t v)   // reflV: (r,c) -> (r,3-c): reverse bits inside nibbles
 {
-    v = ((v & 0x55555555u) << 1) | ((v >> 1) & 0x55555555u);
-    return ((v & 0x33333333u) << 2) | ((v >> 2) & 0x33333333u);
+    v = ((v & 0x55555555u) << 1) | (shr<1>(v) & 0x55555555u);
+    return ((v & 0x33333333u) << 2) | (shr<2>(v) & 0x33333333u);
 }
 QK_HD uint32_t flip_rows(uint32_t v)   // reflH: (r,c) -> (3-r,c): reverse nibbles inside lanes
 {
-    v = ((v & 0x0F0F0F0Fu) << 4) | ((v >> 4) & 0x0F0F0F0Fu);
+    v = ((v & 0x0F0F0F0Fu) << 4) | (shr<4>(v) & 0x0F0F0F0Fu);
     return prmt(v, 0, 0x2301);
 }
 QK_HD uint32_t transpose(uint32_t v)   // reflD: (r,c) -> (c,r)
 {
-    uint32_t t = (v ^ (v >> 3)) & 0x0A0A0A0Au;
+    uint32_t t = (v ^ shr<3>(v)) & 0x0A0A0A0Au;
     v ^= t ^ (t << 3);
-    t = (v ^ (v >> 6)) & 0x00CC00CCu;
+    t = (v ^ shr<6>(v)) & 0x00CC00CCu;
     return v ^ t ^ (t << 6);
 }
 // d4 index as in symmetry.py:101-110: id rot90 rot180 rot270 reflV reflH reflD reflAD

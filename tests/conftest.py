@@ -16,6 +16,11 @@ for p in (ROOT, PKG):
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
+# a fresh checkout has no built artefacts (they are git-ignored): build them once
+if not os.path.exists(os.path.join(PKG, "quantik_b200", "_lib", "libquantik_b200.so")):
+    import __graft_entry__
+    __graft_entry__.build()
+
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")

@@ -444,7 +444,7 @@ def test_abi_error_paths_and_degenerate_sizes():
     assert B.perft(s, 0)["nodes"].tolist() == [4]
     assert len(B.canon_dedup(e)[0]) == 0 and len(B.bfs_level(e)[0]) == 0
     # full boards and positions without moves
-    full = O.make_roots(2000, seed=3, min_plies=13, span=3)
+    full = O.make_roots(1000, seed=3, min_plies=12, span=3)
     g, o = B.playouts(full, 32, SEED, per_playout=True), O.playouts(full, 32, SEED, per_playout=True)
     assert np.array_equal(g["outcome"], o["outcome"]) and np.array_equal(g["plies"], o["plies"])
     for k, v in O.perft(full, 3).items():

@@ -269,6 +269,13 @@ def main():
         extra["perft_depth6_nodes_per_s"] = nodes / dt
         extra["perft_depth6_ms"] = dt * 1e3
         extra["perft_frac_int_issue"] = nodes / dt * OPS_PER_NODE / nominal_peak
+        B.perft(e, 7, device=dev)
+        t0 = time.perf_counter()
+        p7 = B.perft(e, 7, device=dev)                 # deeper: the lane-parallel DFS kernel takes over
+        dt7 = time.perf_counter() - t0
+        assert int(p7["nodes"][7]) == 132400548864
+        extra["perft_depth7_nodes_per_s"] = float(p7["nodes"][1:].sum()) / dt7
+        extra["perft_depth7_ms"] = dt7 * 1e3
         # config 5 / SURVEY 8f-1: the complete canonical game tree (depth 1..16) with the fused BFS
         B.symmetry_table(6, device=dev)
         t0 = time.perf_counter()

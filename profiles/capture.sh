@@ -8,10 +8,12 @@ CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --playouts-per-step 
 # plain run first: must exit 0 before anything is profiled
 $CMD > gpurun_out/plain_$TAG.log 2>&1 || { echo "plain run failed"; tail -20 gpurun_out/plain_$TAG.log; exit 1; }
 # every launch with its device time (cold-cache, serialised: compare SHARES)
-ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-file gpurun_out/launches_$TAG.csv $CMD > gpurun_out/ncu_launches_$TAG.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$TAG.csv $CMD > gpurun_out/ncu_launches_$TAG.log 2>&1
 # the dominant kernel, full set
 ncu --set full --clock-control none --import-source on -k regex:k_playout -s 3 -c 1 -o gpurun_out/prof_playout_$TAG $CMD > gpurun_out/ncu_playout_$TAG.log 2>&1
 # the two other kernel families
 ncu --set full --clock-control none --import-source on -k regex:k_perft_dfs -s 1 -c 1 -o gpurun_out/prof_perft_$TAG $CMD > gpurun_out/ncu_perft_$TAG.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_perft_lane -s 1 -c 1 -o gpurun_out/prof_perft_lane_$TAG $CMD > gpurun_out/ncu_perft_lane_$TAG.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_bfs_expand_insert -s 15 -c 1 -o gpurun_out/prof_bfs_$TAG $CMD > gpurun_out/ncu_bfs_$TAG.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:k_canonical -s 1 -c 1 -o gpurun_out/prof_canon_$TAG $CMD > gpurun_out/ncu_canon_$TAG.log 2>&1
 ls -la gpurun_out

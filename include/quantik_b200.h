@@ -163,6 +163,24 @@ QK_API int qk_playouts_ex(const uint16_t *roots, size_t n_roots, uint32_t rollou
                    uint64_t first_rollout, uint32_t root_index_base, int max_plies,
                    uint32_t *wins_p0, uint32_t *wins_p1, uint32_t *draws,
                    int8_t *per_playout, uint8_t *per_plies, int dev, void *stream);
+/* qk_eval_features  <- evaluation.features (evaluation.py:130-194): the six handcrafted features
+ *                      (threat_own, threat_opp, threat_shared, mobility_diff, build_two, build_one) of
+ *                      VALID positions from player[i]'s perspective, as float64 [n][6]; evaluate() is
+ *                      weights @ features.
+ * qk_playouts_guided<- MCTSEngine._simulate with the eval-guided policy of _select_rollout_move
+ *                      (mcts.py:345-383): with probability epsilon a uniform move, else the first move
+ *                      that wins or leaves the opponent without a reply, else the move whose child
+ *                      scores highest under evaluate(child, mover, weights) (first maximum).  weights =
+ *                      6 doubles in HOST memory (EvalConfig.weights).  Stream: Philox4x32-10 block
+ *                      (rollout, 0x80000000 | ply/2, root index), word 2*(ply%2) = epsilon draw (explore
+ *                      iff word * 2^-32 < epsilon), word 2*(ply%2)+1 = uniform pick.  Outputs as in
+ *                      qk_playouts_ex.                                                                */
+QK_API int qk_eval_features(const uint16_t *states, const uint8_t *player, size_t n, double *features,
+                            int dev, void *stream);
+QK_API int qk_playouts_guided(const uint16_t *roots, size_t n_roots, uint32_t rollouts_per_root, uint64_t seed,
+                              uint64_t first_rollout, uint32_t root_index_base, int max_plies, double epsilon,
+                              const double *weights, uint32_t *wins_p0, uint32_t *wins_p1, uint32_t *draws,
+                              int8_t *per_playout, uint8_t *per_plies, int dev, void *stream);
 /* qk_random_roots   <- benchmarks/dataset.py:38-51 (random non-terminal mid-game
  *                      positions by rejection): root i = empty board + (min_plies +
  *                      i % span) uniform-random plies, stream key seed ^ "ROOTS",

@@ -201,6 +201,36 @@ def symmetry_table(max_depth: int, emit_depth: int = 0, cap: int = 0):
     return stats
 
 
+SEEDED_WEIGHTS = (100.0, -100.0, 20.0, 3.0, 2.0, 0.0)     # evaluation.py:40
+
+
+def features(states, players) -> np.ndarray:
+    """evaluation.features (evaluation.py:130-194) -> (N, 6) float64."""
+    s = _states(states)
+    pl = np.ascontiguousarray(players, dtype=np.uint8)
+    out = np.zeros((len(s), 6), np.float64)
+    lib().qo_features_batch(_p(s), _p(pl), ctypes.c_size_t(len(s)), _p(out))
+    return out
+
+
+def guided_playouts(roots, rollouts: int, seed: int = SEED_DEFAULT, epsilon: float = 0.2, weights=SEEDED_WEIGHTS,
+                    first_rollout: int = 0, root_index_base: int = 0, max_plies: int = -1, per_playout: bool = False):
+    """Playouts with MCTSEngine._select_rollout_move's eval-guided policy (mcts.py:345-383)."""
+    s = _states(roots)
+    n = len(s)
+    w = np.ascontiguousarray(weights, dtype=np.float64)
+    w0, w1, dr = np.zeros(n, np.uint32), np.zeros(n, np.uint32), np.zeros(n, np.uint32)
+    oc = np.zeros((n, rollouts), np.int8) if per_playout else None
+    pl = np.zeros((n, rollouts), np.uint8) if per_playout else None
+    lib().qo_guided_playouts(_p(s), ctypes.c_size_t(n), ctypes.c_uint32(rollouts), ctypes.c_uint64(seed),
+                             ctypes.c_uint64(first_rollout), ctypes.c_uint32(root_index_base), ctypes.c_int(max_plies),
+                             ctypes.c_double(epsilon), _p(w), _p(w0), _p(w1), _p(dr), _p(oc), _p(pl))
+    out = {"wins_p0": w0, "wins_p1": w1, "draws": dr}
+    if per_playout:
+        out["outcome"], out["plies"] = oc, pl
+    return out
+
+
 def opening_book_summary(max_depth: int) -> np.ndarray:
     """rows (positions, terminal, edges) for depth 0..max_depth, as opening_book_summary.build_summary counts them."""
     out = np.zeros((max_depth + 1, 3), np.uint64)

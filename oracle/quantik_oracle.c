@@ -643,6 +643,133 @@ QO_API void qo_opening_book_summary(int max_depth, uint64_t *out)
     level_free(&cur);
 }
 
+/* ------------------------------------------------------------------------ */
+/* evaluation.features / evaluate  (evaluation.py:130-212) and the eval-guided  */
+/* rollout policy MCTSEngine._select_rollout_move (mcts.py:345-383).            */
+/* ------------------------------------------------------------------------ */
+static int placement_is_legal(const uint16_t bb[8], int player, int shape, int position)
+{   /* evaluation.py:99-112 */
+    unsigned opp = bb[(1 - player) * 4 + shape], pm = 1u << position;
+    for (int l = 0; l < 12; ++l) if ((pm & WIN_MASKS[l]) && (opp & WIN_MASKS[l])) return 0;
+    return 1;
+}
+static int count_legal_moves_for(const uint16_t bb[8], int player)
+{   /* evaluation.py:115-127: generate_legal_moves_list(bb, player) -> [] when it is not player's turn */
+    int cur, st;
+    uint64_t mask = qo_legal_mask(bb, &cur, &st);
+    if (st != V_OK || cur != player) return 0;
+    return popcount64(mask);
+}
+QO_API void qo_features(const uint16_t bb[8], int player, double out[6])
+{
+    int counts[2][4], t0 = 0, t1 = 0;
+    for (int s = 0; s < 4; ++s) { counts[0][s] = bit_count16(bb[s]); counts[1][s] = bit_count16(bb[4 + s]); t0 += counts[0][s]; t1 += counts[1][s]; }
+    int side_to_move = (t0 - t1 == 0) ? 0 : 1;                       /* game_utils.py:226-231 (valid states only) */
+    double sign = side_to_move == player ? 1.0 : -1.0;
+    unsigned union_all = 0, su[4];
+    for (int i = 0; i < 8; ++i) union_all |= bb[i];
+    for (int s = 0; s < 4; ++s) su[s] = bb[s] | bb[s + 4];
+    double threat_own = 0, threat_opp = 0, threat_shared = 0, build_two = 0, build_one = 0;
+    for (int l = 0; l < 12; ++l) {
+        unsigned mask = WIN_MASKS[l];
+        int n_present = 0, missing = -1;
+        for (int s = 0; s < 4; ++s) { if (su[s] & mask) ++n_present; }
+        int occupied = bit_count16(union_all & mask);
+        if (n_present < occupied) continue;                          /* dead line */
+        if (occupied == 3) {
+            for (int s = 0; s < 4; ++s) if (!(su[s] & mask)) { missing = s; break; }
+            unsigned e = mask & ~union_all;
+            int empty_position = 0; while (!((e >> empty_position) & 1u)) ++empty_position;
+            int comp[2];
+            for (int side = 0; side < 2; ++side)
+                comp[side] = counts[side][missing] < 2 && placement_is_legal(bb, side, missing, empty_position);
+            if (comp[player]) threat_own += 1.0;
+            if (comp[1 - player]) threat_opp += 1.0;
+            if (comp[0] && comp[1]) threat_shared += sign;
+        } else if (occupied == 2) build_two += sign;
+        else if (occupied == 1) build_one += sign;
+    }
+    out[0] = threat_own; out[1] = threat_opp; out[2] = threat_shared;
+    out[3] = (double)(count_legal_moves_for(bb, player) - count_legal_moves_for(bb, 1 - player));
+    out[4] = build_two; out[5] = build_one;
+}
+QO_API double qo_evaluate(const uint16_t bb[8], int player, const double w[6])
+{
+    double f[6], acc = 0.0;
+    qo_features(bb, player, f);
+    for (int i = 0; i < 6; ++i) acc += w[i] * f[i];
+    return acc;
+}
+QO_API void qo_features_batch(const uint16_t *states, const uint8_t *player, size_t n, double *out)
+{
+    for (size_t i = 0; i < n; ++i) qo_features(states + 8 * i, player[i], out + 6 * i);
+}
+
+/* Guided-stream contract: ply p of a guided playout uses Philox block
+ * (rollout lo, rollout hi, 0x80000000 | p/2, root_index); word 2*(p%2) is the epsilon draw
+ * (explore iff epsilon > 0 and word * 2^-32 < epsilon), word 2*(p%2)+1 the uniform pick. */
+QO_API int qo_guided_playout(const uint16_t root[8], uint64_t seed, uint64_t rollout, uint32_t root_index,
+                             int max_plies, double epsilon, const double weights[6], int *plies_out)
+{
+    uint16_t cur[8], nxt[8];
+    memcpy(cur, root, 16);
+    int ply = 0, result;
+    for (;;) {
+        if (max_plies >= 0 && ply >= max_plies) { result = 0; break; }
+        int w = qo_check_game_winner(cur);
+        if (w) { result = (w == 1) ? 1 : -1; break; }
+        int player, st;
+        uint64_t mask = qo_legal_mask(cur, &player, &st);
+        int n = popcount64(mask);
+        if (n == 0) { result = (player == 0) ? -1 : 1; break; }
+        uint32_t ctr[4] = { (uint32_t)rollout, (uint32_t)(rollout >> 32), 0x80000000u | (uint32_t)(ply / 2), root_index };
+        uint32_t key[2] = { (uint32_t)seed, (uint32_t)(seed >> 32) }, r[4];
+        qo_philox4x32_10(ctr, key, r);
+        uint32_t r_eps = r[2 * (ply % 2)], r_pick = r[2 * (ply % 2) + 1];
+        int a = -1;
+        if (epsilon > 0 && (double)r_eps * (1.0 / 4294967296.0) < epsilon) {          /* mcts.py:371-374 */
+            a = kth_set_bit(mask, (int)(((uint64_t)r_pick * (uint64_t)n) >> 32));
+        } else {
+            double best = 0; int have = 0;
+            for (int m = 0; m < 64; ++m) {
+                if (!((mask >> m) & 1ull)) continue;
+                uint16_t child[8];
+                qo_apply(cur, player, m >> 4, m & 15, child);
+                int cp, cs;
+                if (qo_has_winning_line(child) || qo_legal_mask(child, &cp, &cs) == 0) { a = m; break; }   /* :378-379 */
+                double sc = qo_evaluate(child, player, weights);
+                if (!have) { a = m; best = sc; have = 1; }           /* best_move = all_moves[0], best_score = -inf */
+                else if (sc > best) { best = sc; a = m; }
+            }
+        }
+        qo_apply(cur, player, a >> 4, a & 15, nxt);
+        memcpy(cur, nxt, 16);
+        ++ply;
+    }
+    if (plies_out) *plies_out = ply;
+    return result;
+}
+QO_API void qo_guided_playouts(const uint16_t *roots, size_t n_roots, uint32_t rollouts, uint64_t seed, uint64_t first_rollout,
+                               uint32_t root_index_base, int max_plies, double epsilon, const double *weights,
+                               uint32_t *wins_p0, uint32_t *wins_p1, uint32_t *draws, int8_t *per_playout, uint8_t *per_plies)
+{
+    for (size_t r = 0; r < n_roots; ++r) {
+        long w0 = 0, w1 = 0, dr = 0;
+        #pragma omp parallel for schedule(dynamic, 16) reduction(+:w0,w1,dr)
+        for (long j = 0; j < (long)rollouts; ++j) {
+            int plies;
+            int res = qo_guided_playout(roots + 8 * r, seed, first_rollout + (uint64_t)j, root_index_base + (uint32_t)r,
+                                        max_plies, epsilon, weights, &plies);
+            if (res > 0) ++w0; else if (res < 0) ++w1; else ++dr;
+            if (per_playout) per_playout[r * (size_t)rollouts + j] = (int8_t)res;
+            if (per_plies) per_plies[r * (size_t)rollouts + j] = (uint8_t)plies;
+        }
+        if (wins_p0) wins_p0[r] = (uint32_t)w0;
+        if (wins_p1) wins_p1[r] = (uint32_t)w1;
+        if (draws) draws[r] = (uint32_t)dr;
+    }
+}
+
 QO_API int qo_num_threads(void)
 {
 #ifdef _OPENMP

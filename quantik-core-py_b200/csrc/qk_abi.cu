@@ -367,6 +367,45 @@ int qk_playouts(const uint16_t *roots, size_t n_roots, uint32_t rollouts_per_roo
                           per_playout, nullptr, dev, stream);
 }
 
+int qk_eval_features(const uint16_t *states, const uint8_t *player, size_t n, double *features, int dev, void *stream)
+{
+    QK_REQUIRE((states && player && features) || n == 0, "qk_eval_features: NULL argument");
+    if (n == 0) return QK_OK;
+    QK_BEGIN(call);
+    const uint4 *d_states = (const uint4 *)call.in(states, n * 16);
+    const uint8_t *d_pl = (const uint8_t *)call.in(player, n);
+    double *d_out = (double *)call.out(features, n * 6 * sizeof(double));
+    QK_CHECK(call);
+    int rc = launch_eval_features(d_states, d_pl, n, d_out, call.ctx(), call.stream());
+    if (rc != QK_OK) return rc;
+    return call.finish();
+}
+
+int qk_playouts_guided(const uint16_t *roots, size_t n_roots, uint32_t rollouts_per_root, uint64_t seed, uint64_t first_rollout,
+                       uint32_t root_index_base, int max_plies, double epsilon, const double *weights, uint32_t *wins_p0,
+                       uint32_t *wins_p1, uint32_t *draws, int8_t *per_playout, uint8_t *per_plies, int dev, void *stream)
+{
+    QK_REQUIRE(roots || n_roots == 0, "qk_playouts_guided: roots is NULL");
+    QK_REQUIRE(weights, "qk_playouts_guided: weights is NULL (6 doubles, host memory)");
+    QK_REQUIRE(epsilon >= 0.0 && epsilon <= 1.0, "rollout_epsilon must be in [0.0, 1.0]");     // mcts.py:70-76
+    QK_REQUIRE(n_roots < (1ull << 32), "qk_playouts_guided: n_roots must be < 2^32");
+    if (n_roots == 0) return QK_OK;
+    QK_BEGIN(call);
+    size_t total = n_roots * (size_t)rollouts_per_root;
+    const uint4 *d_roots = (const uint4 *)call.in(roots, n_roots * 16);
+    uint32_t *d_w0 = (uint32_t *)call.out(wins_p0, n_roots * 4, true);
+    uint32_t *d_w1 = (uint32_t *)call.out(wins_p1, n_roots * 4, true);
+    uint32_t *d_dr = (uint32_t *)call.out(draws, n_roots * 4, true);
+    int8_t *d_pp = (int8_t *)call.out(per_playout, total);
+    uint8_t *d_pl = (uint8_t *)call.out(per_plies, total);
+    QK_CHECK(call);
+    if (rollouts_per_root == 0) return call.finish();
+    int rc = launch_playouts_guided(d_roots, n_roots, rollouts_per_root, seed, first_rollout, root_index_base, max_plies, epsilon,
+                                    weights, d_w0, d_w1, d_dr, d_pp, d_pl, call.ctx(), call.stream());
+    if (rc != QK_OK) return rc;
+    return call.finish();
+}
+
 int qk_random_roots(uint64_t seed, uint64_t first, size_t n, int min_plies, int span, uint16_t *out_states,
                     int dev, void *stream)
 {

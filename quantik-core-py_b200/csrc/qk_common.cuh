@@ -85,6 +85,10 @@ int run_bfs_level(Call &call, const uint4 *parents, const uint64_t *mult, size_t
                   uint16_t *uniq, uint64_t *uniq_mult, size_t cap, size_t *n_uniq, uint64_t *h_stats);
 int run_book_level(Call &call, const uint4 *parents, size_t n, int color_swap, uint16_t *uniq, uint64_t *uniq_mult,
                    size_t cap, size_t *n_uniq, uint64_t *h_stats);
+int launch_eval_features(const uint4 *states, const uint8_t *player, size_t n, double *features, Ctx *c, cudaStream_t s);
+int launch_playouts_guided(const uint4 *roots, size_t n_roots, uint32_t rollouts, uint64_t seed, uint64_t first_rollout,
+                           uint32_t root_index_base, int max_plies, double epsilon, const double *weights, uint32_t *wins_p0,
+                           uint32_t *wins_p1, uint32_t *draws, int8_t *per_playout, uint8_t *per_plies, Ctx *c, cudaStream_t s);
 int run_issue_peak(Ctx *c, double *alu, double *mixed);
 int run_pipe_rates(Ctx *c, double *out8);
 

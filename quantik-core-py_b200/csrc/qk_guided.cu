@@ -1,0 +1,70 @@
+// qk_guided.cu -- SURVEY 8f-4: the reference's fitted-linear evaluation (evaluation.py:130-212) in batch,
+// and playouts under MCTSEngine._select_rollout_move's eval-guided epsilon-greedy policy (mcts.py:345-383).
+// One position / one playout per thread.  A guided ply scores every child of the position (up to 64
+// evaluations of 12 lines each), so this policy is ~100x the work of a uniform ply and is not the
+// throughput path; it exists so that MCTSConfig(rollout_eval_config=...) has a drop-in too.
+#include "qk_common.cuh"
+#include "qk_eval_core.cuh"
+
+namespace qk {
+
+static constexpr unsigned kBlock = 128;
+
+struct EvalWeights { double w[6]; };
+
+__global__ void __launch_bounds__(kBlock) k_eval_features(const uint4 *__restrict__ states, const uint8_t *__restrict__ player,
+                                                           size_t n, double *__restrict__ features)
+{
+    for (size_t i = blockIdx.x * (size_t)kBlock + threadIdx.x; i < n; i += (size_t)gridDim.x * kBlock) {
+        const uint4 v = __ldg(states + i);
+        const State4 s = { v.x, v.y, v.z, v.w };
+        int f[6];
+        eval_features(s, player[i] & 1, f);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) features[6 * i + k] = (double)f[k];
+    }
+}
+
+__global__ void __launch_bounds__(kBlock) k_playout_guided(const uint4 *__restrict__ roots, uint64_t n_roots, uint32_t rollouts,
+                                                            uint64_t seed, uint64_t first_rollout, uint32_t root_index_base,
+                                                            int max_plies, double epsilon, const EvalWeights weights,
+                                                            uint32_t *wins_p0, uint32_t *wins_p1, uint32_t *draws,
+                                                            int8_t *per_playout, uint8_t *per_plies)
+{
+    const uint64_t total = n_roots * rollouts;
+    for (uint64_t id = blockIdx.x * (uint64_t)kBlock + threadIdx.x; id < total; id += (uint64_t)gridDim.x * kBlock) {
+        const uint32_t root = (uint32_t)(id / rollouts), j = (uint32_t)(id % rollouts);
+        const uint4 v = __ldg(roots + root);
+        const State4 s = { v.x, v.y, v.z, v.w };
+        int plies;
+        const int res = guided_playout_one(s, seed, first_rollout + j, root_index_base + root, max_plies, epsilon, weights.w, &plies);
+        if (res > 0) { if (wins_p0) atomicAdd(wins_p0 + root, 1u); }
+        else if (res < 0) { if (wins_p1) atomicAdd(wins_p1 + root, 1u); }
+        else if (draws) atomicAdd(draws + root, 1u);
+        if (per_playout) per_playout[id] = (int8_t)res;
+        if (per_plies) per_plies[id] = (uint8_t)plies;
+    }
+}
+
+int launch_eval_features(const uint4 *states, const uint8_t *player, size_t n, double *features, Ctx *c, cudaStream_t s)
+{
+    k_eval_features<<<grid_for(n, kBlock, c->sms, 16), kBlock, 0, s>>>(states, player, n, features);
+    QK_CUDA(cudaGetLastError());
+    return QK_OK;
+}
+
+int launch_playouts_guided(const uint4 *roots, size_t n_roots, uint32_t rollouts, uint64_t seed, uint64_t first_rollout,
+                           uint32_t root_index_base, int max_plies, double epsilon, const double *weights, uint32_t *wins_p0,
+                           uint32_t *wins_p1, uint32_t *draws, int8_t *per_playout, uint8_t *per_plies, Ctx *c, cudaStream_t s)
+{
+    EvalWeights w;
+    for (int i = 0; i < 6; ++i) w.w[i] = weights[i];
+    const size_t total = n_roots * (size_t)rollouts;
+    k_playout_guided<<<grid_for(total, kBlock, c->sms, 16), kBlock, 0, s>>>(roots, n_roots, rollouts, seed, first_rollout,
+                                                                            root_index_base, max_plies, epsilon, w, wins_p0,
+                                                                            wins_p1, draws, per_playout, per_plies);
+    QK_CUDA(cudaGetLastError());
+    return QK_OK;
+}
+
+}  // namespace qk

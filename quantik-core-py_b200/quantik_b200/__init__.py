@@ -15,8 +15,8 @@ from .api import (  # noqa: F401
     portability_case_report, validate_game_state, validate_move,
 )
 from .batch import (  # noqa: F401
-    SEED_DEFAULT, apply_moves, apply_symmetry, bfs_level, book_level, canon_dedup, canonical_keys, canonical_payloads,
-    decode_transform, encode_transform, int_issue_peak, movegen_masks, opening_book_summary, orbit_sizes, perft,
+    FEATURE_NAMES, SEED_DEFAULT, SEEDED_WEIGHTS, apply_moves, apply_symmetry, bfs_level, book_level, canon_dedup, canonical_keys, canonical_payloads,
+    decode_transform, encode_transform, eval_features, evaluate, guided_playouts, int_issue_peak, movegen_masks, opening_book_summary, orbit_sizes, perft,
     pipe_rates, playouts,
     random_roots, symmetry_table, symmetry_table_rows, win_status,
 )

@@ -324,6 +324,63 @@ def playouts(roots, rollouts: int, seed: int = SEED_DEFAULT, max_plies: int = -1
     return out
 
 
+SEEDED_WEIGHTS = (100.0, -100.0, 20.0, 3.0, 2.0, 0.0)     # evaluation.py:40 (_SEEDED_WEIGHTS)
+FEATURE_NAMES = ["threat_own", "threat_opp", "threat_shared", "mobility_diff", "build_two", "build_one"]   # evaluation.py:32-39
+
+
+def eval_features(states, players, device: Optional[int] = None):
+    """evaluation.features (evaluation.py:130-194) for a batch of valid positions -> (N, 6) float64."""
+    s, on_dev, d = _states_in(states)
+    d = _dev(device, on_dev, d)
+    lib = N.init(d)
+    pl = _aux_in(players, np.uint8, on_dev, d)
+    if pl.n != s.n:
+        raise ValueError("one player per state required")
+    if on_dev:
+        t = torch.empty((s.n, 6), dtype=torch.float64, device=f"cuda:{d}")
+        out = _Buf(t.data_ptr(), t, s.n)
+    else:
+        a = np.empty((s.n, 6), np.float64)
+        out = _Buf(a.ctypes.data, a, s.n)
+    N.check(lib.qk_eval_features(s.ptr, pl.ptr, s.n, out.ptr, d, _stream(on_dev, d)))
+    return out.obj
+
+
+def evaluate(states, players, weights=SEEDED_WEIGHTS, device: Optional[int] = None):
+    """evaluation.evaluate (evaluation.py:197-212): weights @ features, one score per position."""
+    f = eval_features(states, players, device=device)
+    w = np.asarray(weights, np.float64)
+    if _is_torch(f):
+        return f @ torch.from_numpy(w).to(f.device)
+    return f @ w
+
+
+def guided_playouts(roots, rollouts: int, seed: int = SEED_DEFAULT, epsilon: float = 0.2, weights=SEEDED_WEIGHTS,
+                    max_plies: int = -1, first_rollout: int = 0, root_index_base: int = 0, per_playout: bool = False,
+                    device: Optional[int] = None) -> Dict[str, object]:
+    """Playouts under the reference's eval-guided epsilon-greedy rollout policy
+    (MCTSConfig.rollout_eval_config / rollout_epsilon; mcts.py:345-383).  Same outputs as :func:`playouts`."""
+    if not 0.0 <= epsilon <= 1.0:
+        raise ValueError(f"rollout_epsilon must be in [0.0, 1.0], got {epsilon}")     # mcts.py:70-76
+    s, on_dev, d = _states_in(roots)
+    d = _dev(device, on_dev, d)
+    lib = N.init(d)
+    n = s.n
+    w = np.ascontiguousarray(weights, dtype=np.float64)
+    if w.shape != (6,):
+        raise ValueError("weights must have 6 entries (FEATURE_NAMES order)")
+    w0, w1, dr = (_out((n,), np.uint32, on_dev, d) for _ in range(3))
+    oc = _out((n, rollouts), np.int8, on_dev, d) if per_playout else _Buf(None, None, 0)
+    pl = _out((n, rollouts), np.uint8, on_dev, d) if per_playout else _Buf(None, None, 0)
+    N.check(lib.qk_playouts_guided(s.ptr, n, int(rollouts), int(seed) & 0xFFFFFFFFFFFFFFFF, int(first_rollout),
+                                   int(root_index_base), int(max_plies), float(epsilon), w.ctypes.data, w0.ptr, w1.ptr,
+                                   dr.ptr, oc.ptr, pl.ptr, d, _stream(on_dev, d)))
+    out = {"wins_p0": w0.obj, "wins_p1": w1.obj, "draws": dr.obj}
+    if per_playout:
+        out["outcome"], out["plies"] = oc.obj, pl.obj
+    return out
+
+
 def random_roots(n: int, seed: int = SEED_DEFAULT, first: int = 0, min_plies: int = 5, span: int = 7,
                  device: Optional[int] = None, as_torch: bool = False):
     """Mid-game root generator of BASELINE config 4 (benchmarks/dataset.py:38-51 rejection rule)."""

@@ -8,6 +8,7 @@
 #include "qk_playout_core.cuh"
 #endif
 #include "qk_perft_core.cuh"
+#include "qk_eval_core.cuh"
 
 using namespace qk;
 static State4 ld(const uint16_t *p) { State4 s = { (uint32_t)p[0] | ((uint32_t)p[1] << 16), (uint32_t)p[2] | ((uint32_t)p[3] << 16),
@@ -33,6 +34,18 @@ void hs_apply(const uint16_t *s, const uint8_t *a, size_t n, uint16_t *out)
 { for (size_t i = 0; i < n; ++i) { State4 x = ld(s + 8 * i); int p = 0; if (validate(x, &p) != 0) p = 0; st(out + 8 * i, apply_action(x, p, a[i])); } }
 void hs_leaf_parent(const uint16_t *s, size_t n, uint8_t *mover, uint8_t *moves, uint8_t *wins)
 { for (size_t i = 0; i < n; ++i) { int m, w; mover[i] = leaf_parent_counts(ld(s + 8 * i), m, w); moves[i] = m; wins[i] = w; } }
+void hs_features(const uint16_t *s, const uint8_t *pl, size_t n, double *out)
+{ for (size_t i = 0; i < n; ++i) { int f[6]; eval_features(ld(s + 8 * i), pl[i], f); for (int k = 0; k < 6; ++k) out[6 * i + k] = f[k]; } }
+void hs_guided(const uint16_t *roots, size_t n_roots, uint32_t rollouts, uint64_t seed, uint64_t first, uint32_t root_base,
+               int max_plies, double eps, const double *w, int8_t *outcome, uint8_t *plies)
+{
+    for (size_t r = 0; r < n_roots; ++r)
+        for (uint32_t j = 0; j < rollouts; ++j) {
+            int pl;
+            outcome[r * rollouts + j] = (int8_t)guided_playout_one(ld(roots + 8 * r), seed, first + j, root_base + (uint32_t)r, max_plies, eps, w, &pl);
+            plies[r * rollouts + j] = (uint8_t)pl;
+        }
+}
 int hs_select(uint32_t lo, uint32_t hi, int k) { return select_bit64(lo, hi, popc(lo), k); }
 #ifdef QK_HOSTSIM_PLAYOUT
 void hs_playouts(const uint16_t *roots, size_t n_roots, uint32_t rollouts, uint64_t seed, uint64_t first, uint32_t root_base,

@@ -110,3 +110,22 @@ def test_leaf_parent_bulk_counts(hs):
         assert int(r["nodes"][1]) == mo[i]
         assert int(r["wins_p0"][1]) + int(r["wins_p1"][1]) == wi[i]
         assert (int(r["wins_p0"][1]) > 0) <= (mv[i] == 0) and (int(r["wins_p1"][1]) > 0) <= (mv[i] == 1)
+
+
+def test_eval_features_and_guided_policy(hs):
+    g = np.load(os.path.join(G, "guided_rollouts.npz"))
+    st = np.ascontiguousarray(g["states"])
+    n = len(st)
+    for pl, key in ((0, "features_p0"), (1, "features_p1")):
+        out = np.zeros((n, 6))
+        hs.hs_features(P(st), P(np.full(n, pl, np.uint8)), ctypes.c_size_t(n), P(out))
+        assert np.array_equal(out, g[key])
+    e = np.zeros((1, 8), np.uint16)
+    seed = int(np.load(os.path.join(G, "playouts_philox.npz"))["seed"])
+    for name, wkey, eps in (("seeded_eps02", "seeded_weights", 0.2), ("fitted_eps02", "fitted_weights", 0.2),
+                            ("fitted_eps0", "fitted_weights", 0.0), ("seeded_eps1", "seeded_weights", 1.0)):
+        m = len(g[name + "_outcome"])
+        oc, pl, w = np.zeros(m, np.int8), np.zeros(m, np.uint8), np.ascontiguousarray(g[wkey])
+        hs.hs_guided(P(e), ctypes.c_size_t(1), ctypes.c_uint32(m), ctypes.c_uint64(seed), ctypes.c_uint64(0), ctypes.c_uint32(3),
+                     ctypes.c_int(-1), ctypes.c_double(eps), P(w), P(oc), P(pl))
+        assert np.array_equal(oc, g[name + "_outcome"]) and np.array_equal(pl, g[name + "_plies"]), name

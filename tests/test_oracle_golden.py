@@ -203,3 +203,25 @@ def test_opening_book_summary_vs_reference():
     want = json.load(open(os.path.join(G, "opening_book_summary_d5.json")))
     got = O.opening_book_summary(4)
     assert got.tolist() == [[r["positions"], r["terminal"], r["edges"]] for r in want["per_depth"][:5]]
+
+
+def test_evaluation_features_and_guided_rollouts_vs_reference():
+    # tests/golden/guided_rollouts.npz: evaluation.features / evaluate and playouts under
+    # MCTSEngine._select_rollout_move's eval-guided policy, produced with the reference (oracle/gen_golden.py --guided)
+    g = _npz("guided_rollouts.npz")
+    st = g["states"]
+    n = len(st)
+    f0, f1 = O.features(st, np.zeros(n, np.uint8)), O.features(st, np.ones(n, np.uint8))
+    assert np.array_equal(f0, g["features_p0"]) and np.array_equal(f1, g["features_p1"])
+    # floating point: numpy's dot and a left-to-right sum differ by rounding only (tolerance 1e-12 absolute)
+    assert np.abs(f0 @ g["fitted_weights"] - g["evaluate_p0_fitted"]).max() < 1e-12
+    seed = O.SEED_DEFAULT
+    e = np.zeros((1, 8), np.uint16)
+    for name, w, eps in (("seeded_eps02", g["seeded_weights"], 0.2), ("fitted_eps02", g["fitted_weights"], 0.2),
+                         ("fitted_eps0", g["fitted_weights"], 0.0), ("seeded_eps1", g["seeded_weights"], 1.0)):
+        r = O.guided_playouts(e, len(g[name + "_outcome"]), seed, eps, w, root_index_base=3, per_playout=True)
+        assert np.array_equal(r["outcome"][0], g[name + "_outcome"]) and np.array_equal(r["plies"][0], g[name + "_plies"]), name
+    r = O.guided_playouts(g["roots"], 24, seed, 0.2, g["fitted_weights"], first_rollout=500, root_index_base=40, per_playout=True)
+    assert np.array_equal(r["outcome"], g["roots_outcome"]) and np.array_equal(r["plies"], g["roots_plies"])
+    r = O.guided_playouts(e, 80, seed, 0.2, g["fitted_weights"], root_index_base=3, max_plies=9, per_playout=True)
+    assert np.array_equal(r["outcome"][0], g["cut9_outcome"]) and np.array_equal(r["plies"][0], g["cut9_plies"])

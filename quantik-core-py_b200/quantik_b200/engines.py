@@ -71,7 +71,9 @@ def gpu_simulate(rollouts_per_leaf: int = 256, seed: int = B.SEED_DEFAULT, devic
 
     Terminal flags are honoured exactly as the reference does (:396-403); otherwise the leaf is
     evaluated by ``rollouts_per_leaf`` playouts cut off after ``config.max_depth - node.depth``
-    moves (:412,436-437) and the mean outcome is returned."""
+    moves (:412,436-437) and the mean outcome is returned.  When the engine's config carries
+    ``rollout_eval_config`` (mcts.py:47-52) the playouts use the eval-guided epsilon-greedy policy of
+    ``_select_rollout_move`` (:345-383) with its weights and ``rollout_epsilon``."""
     counter = itertools.count()
     NODE_FLAG_TERMINAL, NODE_FLAG_WINNING_P0, NODE_FLAG_WINNING_P1 = 1, 2, 4   # memory/compact_tree.py
 
@@ -86,8 +88,14 @@ def gpu_simulate(rollouts_per_leaf: int = 256, seed: int = B.SEED_DEFAULT, devic
             return 0.0
         bb = self.tree.get_state(node_id).bb
         left = max(0, int(self.config.max_depth) - int(node.depth))
-        r = B.playouts(np.array([bb], np.uint16), rollouts_per_leaf, seed=seed, max_plies=left,
-                       root_index_base=next(counter), device=device)
+        cfg = getattr(self.config, "rollout_eval_config", None)
+        if cfg is not None:
+            r = B.guided_playouts(np.array([bb], np.uint16), rollouts_per_leaf, seed=seed, max_plies=left,
+                                  epsilon=float(getattr(self.config, "rollout_epsilon", 0.2)),
+                                  weights=np.asarray(cfg.weights, np.float64), root_index_base=next(counter), device=device)
+        else:
+            r = B.playouts(np.array([bb], np.uint16), rollouts_per_leaf, seed=seed, max_plies=left,
+                           root_index_base=next(counter), device=device)
         return (float(r["wins_p0"][0]) - float(r["wins_p1"][0])) / rollouts_per_leaf
 
     return _simulate

@@ -547,3 +547,11 @@ def test_engine_plugins():
     eng.tree = Tree(Node(0, 0), np.zeros(8, np.uint16))
     o = O.playouts(np.zeros((1, 8), np.uint16), 256, SEED, root_index_base=1, max_plies=16)
     assert abs(sim(eng, 0) - (float(o["wins_p0"][0]) - float(o["wins_p1"][0])) / 256) < 1e-12
+
+    class EvalCfg:                                            # EvalConfig stand-in (evaluation.py:46-62)
+        weights = np.array(Q.SEEDED_WEIGHTS)
+
+    Cfg.rollout_eval_config, Cfg.rollout_epsilon = EvalCfg(), 0.1
+    o = O.guided_playouts(np.zeros((1, 8), np.uint16), 256, SEED, 0.1, Q.SEEDED_WEIGHTS, root_index_base=2, max_plies=16)
+    assert abs(sim(eng, 0) - (float(o["wins_p0"][0]) - float(o["wins_p1"][0])) / 256) < 1e-12
+    Cfg.rollout_eval_config = None

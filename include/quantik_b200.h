@@ -181,6 +181,16 @@ QK_API int qk_playouts_guided(const uint16_t *roots, size_t n_roots, uint32_t ro
                               uint64_t first_rollout, uint32_t root_index_base, int max_plies, double epsilon,
                               const double *weights, uint32_t *wins_p0, uint32_t *wins_p1, uint32_t *draws,
                               int8_t *per_playout, uint8_t *per_plies, int dev, void *stream);
+/* qk_solve          <- MinimaxEngine.solve (minimax.py:182-204; _negamax :330-453): the exact game value of
+ *                      each position with mate distance.  outcome = +1 / -1: the side to move wins /
+ *                      loses under optimal play; plies = number of plies until the game ends (a line
+ *                      is completed, or a mover has no move) when the winner hurries and the loser
+ *                      delays -- the reference's score is outcome * (EvalConfig.win - plies);
+ *                      best_action = the lowest action index among the optimal moves (255 when the
+ *                      position is already finished).  Exhaustive: meant for the endgame hand-off of
+ *                      HybridPlayer (hybrid.py:80-122), i.e. positions with at most ~8 empty squares. */
+QK_API int qk_solve(const uint16_t *states, size_t n, int8_t *outcome, uint8_t *plies, uint8_t *best_action,
+                    int dev, void *stream);
 /* qk_random_roots   <- benchmarks/dataset.py:38-51 (random non-terminal mid-game
  *                      positions by rejection): root i = empty board + (min_plies +
  *                      i % span) uniform-random plies, stream key seed ^ "ROOTS",

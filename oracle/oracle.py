@@ -231,6 +231,15 @@ def guided_playouts(roots, rollouts: int, seed: int = SEED_DEFAULT, epsilon: flo
     return out
 
 
+def solve(states):
+    """Exact game value of each position (minimax.py:330-453 at full depth): outcome +1 / -1 for the side to
+    move, plies until the end under optimal play, lowest optimal action (255 when the position is finished)."""
+    s = _states(states)
+    oc, pl, act = np.zeros(len(s), np.int8), np.zeros(len(s), np.uint8), np.zeros(len(s), np.uint8)
+    lib().qo_solve_batch(_p(s), ctypes.c_size_t(len(s)), _p(oc), _p(pl), _p(act))
+    return oc, pl, act
+
+
 def opening_book_summary(max_depth: int) -> np.ndarray:
     """rows (positions, terminal, edges) for depth 0..max_depth, as opening_book_summary.build_summary counts them."""
     out = np.zeros((max_depth + 1, 3), np.uint64)

@@ -770,6 +770,42 @@ QO_API void qo_guided_playouts(const uint16_t *roots, size_t n_roots, uint32_t r
     }
 }
 
+/* ------------------------------------------------------------------------ */
+/* Exact negamax with mate distance = MinimaxEngine._negamax (minimax.py:330-453) */
+/* at max_depth 16 (MinimaxEngine.solve, :182-204) without its accelerators       */
+/* (alpha-beta, transposition table, sibling dedup never change the value).       */
+/* Returns the value from the side to move's perspective as  +-(W - ply_of_end),  */
+/* W = 64;  *best = lowest action index among the optimal moves (-1 if terminal). */
+/* ------------------------------------------------------------------------ */
+static int negamax_rec(const uint16_t bb[8], int ply, int *best_action)
+{
+    if (best_action) *best_action = -1;
+    if (qo_has_winning_line(bb)) return -(64 - ply);                 /* :354-358 */
+    int player, st;
+    uint64_t mask = qo_legal_mask(bb, &player, &st);
+    if (mask == 0) return -(64 - ply);                               /* :366-369 */
+    int best = -1000;
+    for (int a = 0; a < 64; ++a) {
+        if (!((mask >> a) & 1ull)) continue;
+        uint16_t child[8];
+        qo_apply(bb, player, a >> 4, a & 15, child);
+        int v = -negamax_rec(child, ply + 1, NULL);                  /* :423-426 */
+        if (v > best) { best = v; if (best_action) *best_action = a; }
+    }
+    return best;
+}
+QO_API void qo_solve_batch(const uint16_t *states, size_t n, int8_t *outcome, uint8_t *plies, uint8_t *best_action)
+{
+    #pragma omp parallel for schedule(dynamic, 1)
+    for (long i = 0; i < (long)n; ++i) {
+        int act;
+        int v = negamax_rec(states + 8 * i, 0, &act);
+        outcome[i] = (int8_t)(v > 0 ? 1 : -1);
+        plies[i] = (uint8_t)(64 - (v > 0 ? v : -v));
+        best_action[i] = (uint8_t)(act < 0 ? 255 : act);
+    }
+}
+
 QO_API int qo_num_threads(void)
 {
 #ifdef _OPENMP

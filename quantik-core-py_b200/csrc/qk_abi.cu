@@ -406,6 +406,22 @@ int qk_playouts_guided(const uint16_t *roots, size_t n_roots, uint32_t rollouts_
     return call.finish();
 }
 
+int qk_solve(const uint16_t *states, size_t n, int8_t *outcome, uint8_t *plies, uint8_t *best_action, int dev, void *stream)
+{
+    QK_REQUIRE((states && outcome && plies && best_action) || n == 0, "qk_solve: NULL argument");
+    if (n == 0) return QK_OK;
+    QK_BEGIN(call);
+    const uint4 *d_states = (const uint4 *)call.in(states, n * 16);
+    int8_t *d_oc = (int8_t *)call.out(outcome, n);
+    uint8_t *d_pl = (uint8_t *)call.out(plies, n);
+    uint8_t *d_ba = (uint8_t *)call.out(best_action, n);
+    unsigned long long *counter = (unsigned long long *)call.temp(sizeof(unsigned long long));
+    QK_CHECK(call);
+    int rc = launch_solve(d_states, n, counter, d_oc, d_pl, d_ba, call.ctx(), call.stream());
+    if (rc != QK_OK) return rc;
+    return call.finish();
+}
+
 int qk_random_roots(uint64_t seed, uint64_t first, size_t n, int min_plies, int span, uint16_t *out_states,
                     int dev, void *stream)
 {

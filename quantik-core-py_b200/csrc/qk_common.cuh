@@ -89,6 +89,8 @@ int launch_eval_features(const uint4 *states, const uint8_t *player, size_t n, d
 int launch_playouts_guided(const uint4 *roots, size_t n_roots, uint32_t rollouts, uint64_t seed, uint64_t first_rollout,
                            uint32_t root_index_base, int max_plies, double epsilon, const double *weights, uint32_t *wins_p0,
                            uint32_t *wins_p1, uint32_t *draws, int8_t *per_playout, uint8_t *per_plies, Ctx *c, cudaStream_t s);
+int launch_solve(const uint4 *states, size_t n, unsigned long long *counter, int8_t *outcome, uint8_t *plies, uint8_t *best_action,
+                 Ctx *c, cudaStream_t s);
 int run_issue_peak(Ctx *c, double *alu, double *mixed);
 int run_pipe_rates(Ctx *c, double *out8);
 

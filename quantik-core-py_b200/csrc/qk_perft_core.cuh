@@ -13,6 +13,9 @@
 
 namespace qk {
 
+#ifdef __CUDACC__
+__device__ __forceinline__ State4 to_state4(const uint4 &v) { State4 s = { v.x, v.y, v.z, v.w }; return s; }
+#endif
 QK_HD uint32_t swap_lanes(uint32_t v) { return prmt(v, 0, 0x1032); }
 QK_HD uint32_t dup_low(uint32_t v) { return prmt(v, 0, 0x1010); }
 

@@ -53,6 +53,7 @@ PROTOTYPES = {
     "qk_eval_features": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_int, c_void_p]),
     "qk_playouts_guided": (c_int, [c_void_p, c_size_t, c_uint32, c_uint64, c_uint64, c_uint32, c_int, c_double, c_void_p,
                                    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "qk_solve": (c_int, [c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "qk_random_roots": (c_int, [c_uint64, c_uint64, c_size_t, c_int, c_int, c_void_p, c_int, c_void_p]),
     "qk_perft": (c_int, [c_void_p, c_void_p, c_size_t, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                          c_int, c_void_p]),

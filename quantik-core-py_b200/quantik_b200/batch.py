@@ -381,6 +381,19 @@ def guided_playouts(roots, rollouts: int, seed: int = SEED_DEFAULT, epsilon: flo
     return out
 
 
+def solve(states, device: Optional[int] = None):
+    """Exact game value with mate distance (MinimaxEngine.solve, minimax.py:182-204) for late-game positions.
+    -> (outcome int8 +1/-1 for the side to move, plies uint8 until the end under optimal play,
+        best_action uint8: lowest optimal action, 255 for finished positions).
+    The reference's ``MinimaxResult.score`` is ``outcome * (win - plies)`` with ``win = EvalConfig.win``."""
+    s, on_dev, d = _states_in(states)
+    d = _dev(device, on_dev, d)
+    lib = N.init(d)
+    oc, pl, act = _out((s.n,), np.int8, on_dev, d), _out((s.n,), np.uint8, on_dev, d), _out((s.n,), np.uint8, on_dev, d)
+    N.check(lib.qk_solve(s.ptr, s.n, oc.ptr, pl.ptr, act.ptr, d, _stream(on_dev, d)))
+    return oc.obj, pl.obj, act.obj
+
+
 def random_roots(n: int, seed: int = SEED_DEFAULT, first: int = 0, min_plies: int = 5, span: int = 7,
                  device: Optional[int] = None, as_torch: bool = False):
     """Mid-game root generator of BASELINE config 4 (benchmarks/dataset.py:38-51 rejection rule)."""

@@ -482,6 +482,27 @@ def test_evaluation_and_guided_rollouts():
         B.guided_playouts(e, 4, epsilon=1.5)                                                    # mcts.py:70-76
 
 
+def test_exact_endgame_solver():
+    g = _npz("solver.npz")
+    oc, pl, act = B.solve(g["states"])
+    assert np.array_equal(oc.astype(float) * (float(g["win"]) - pl), g["score"])          # MinimaxEngine.solve(...).score
+    o = O.solve(g["states"])
+    assert np.array_equal(oc, o[0]) and np.array_equal(pl, o[1]) and np.array_equal(act, o[2])
+    # 3000 positions with 4..9 empty squares + finished / blocked / invalid ones against the oracle negamax
+    roots = np.concatenate([O.make_roots(3000, seed=321, min_plies=7, span=6),
+                            np.array([Q.bb_from_qfen("A..C/bbd./CD.A/.adB"), Q.bb_from_qfen("AbCd/..../..../...."),
+                                      (1, 1, 0, 0, 0, 0, 0, 0)], np.uint16)])
+    a, b = B.solve(roots), O.solve(roots)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+    assert set(np.unique(a[0])) == {-1, 1} and a[1].max() >= 5
+    # consistency: playing the reported move flips the outcome and shortens the game by one ply
+    live = a[2] != 255
+    kids = B.apply_moves(roots[live], a[2][live])
+    k = B.solve(kids)
+    assert np.array_equal(-k[0], a[0][live]) and np.array_equal(k[1] + 1, a[1][live])
+
+
 # ----------------------------------------------------------------------------- device buffers, engines
 def test_device_tensor_path_matches_host_path():
     import torch

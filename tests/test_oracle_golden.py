@@ -225,3 +225,14 @@ def test_evaluation_features_and_guided_rollouts_vs_reference():
     assert np.array_equal(r["outcome"], g["roots_outcome"]) and np.array_equal(r["plies"], g["roots_plies"])
     r = O.guided_playouts(e, 80, seed, 0.2, g["fitted_weights"], root_index_base=3, max_plies=9, per_playout=True)
     assert np.array_equal(r["outcome"][0], g["cut9_outcome"]) and np.array_equal(r["plies"][0], g["cut9_plies"])
+
+
+def test_exact_solver_vs_reference_minimax():
+    # tests/golden/solver.npz: MinimaxEngine.solve(state).score of the reference on 180 late-game positions
+    g = _npz("solver.npz")
+    oc, pl, act = O.solve(g["states"])
+    assert np.array_equal(oc.astype(float) * (float(g["win"]) - pl), g["score"])
+    # the reference's best move is optimal too (its tie-break is its move ordering, ours is the lowest action)
+    kids = O.apply_moves(g["states"], g["best_action"])
+    koc, kpl, _ = O.solve(kids)
+    assert np.array_equal(-koc, oc) and np.array_equal(kpl + 1, pl)

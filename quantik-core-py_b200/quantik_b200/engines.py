@@ -75,7 +75,7 @@ def gpu_simulate(rollouts_per_leaf: int = 256, seed: int = B.SEED_DEFAULT, devic
     ``rollout_eval_config`` (mcts.py:47-52) the playouts use the eval-guided epsilon-greedy policy of
     ``_select_rollout_move`` (:345-383) with its weights and ``rollout_epsilon``."""
     counter = itertools.count()
-    NODE_FLAG_TERMINAL, NODE_FLAG_WINNING_P0, NODE_FLAG_WINNING_P1 = 1, 2, 4   # memory/compact_tree.py
+    NODE_FLAG_TERMINAL, NODE_FLAG_WINNING_P0, NODE_FLAG_WINNING_P1 = 0x01, 0x04, 0x08   # memory/compact_tree.py:54-57
 
     def _simulate(self, node_id: int) -> float:
         node = self.tree.get_node(node_id)

@@ -561,7 +561,7 @@ def test_engine_plugins():
 
     sim = Q.gpu_simulate(rollouts_per_leaf=256, seed=SEED)
     eng = Engine()
-    eng.tree = Tree(Node(1 | 2, 3), roots[0])
+    eng.tree = Tree(Node(0x01 | 0x04, 3), roots[0])
     assert sim(eng, 0) == 1.0                                 # terminal flag short-cut (mcts.py:396-403)
     eng.tree = Tree(Node(0, 16), roots[0])
     assert sim(eng, 0) == 0.0                                 # depth >= max_depth -> 0.0 (mcts.py:412,437)

@@ -98,12 +98,6 @@ QK_HD uint32_t lanes_with_two(uint32_t u)
     return ((lo & (lo - 1)) ? 0x0000FFFFu : 0u) | ((hi & (hi - 1)) ? 0xFFFF0000u : 0u);
 }
 
-QK_HD uint32_t occupancy2(const State4 &s)
-{   // occupied squares, replicated in both 16-bit lanes
-    uint32_t o = s.x | s.y | s.z | s.w;
-    return (o | (o >> 16)) & 0xFFFFu ? ((o | (o >> 16)) & 0xFFFFu) * 0x10001u : 0u;
-}
-
 // ---------------------------------------------------------------- win test
 // has_winning_line (game_utils.py:123-158): some row, column or zone holds all
 // four shapes, colours ignored.

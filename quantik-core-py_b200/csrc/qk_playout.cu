@@ -66,8 +66,13 @@ __device__ __forceinline__ void flush_tallies(const PlayoutArgs &a, uint32_t roo
     }
 }
 
+#ifdef QK_PLAYOUT_MAXNREG      // experiment knob: cap registers to raise occupancy (see NOTES.md)
+#define QK_PLAYOUT_BOUNDS __maxnreg__(QK_PLAYOUT_MAXNREG)
+#else
+#define QK_PLAYOUT_BOUNDS __launch_bounds__(kBlock)
+#endif
 template <bool CUTOFF, bool PER_PLAYOUT>
-__global__ void __launch_bounds__(kBlock) k_playout(const PlayoutArgs a)
+__global__ void QK_PLAYOUT_BOUNDS k_playout(const PlayoutArgs a)
 {
     __shared__ __align__(16) SquareLut s_lut[16];
     __shared__ __align__(16) uint8_t s_sel8[2048];

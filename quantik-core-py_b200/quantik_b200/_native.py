@@ -13,7 +13,7 @@ import threading
 from ctypes import POINTER, c_char_p, c_double, c_int, c_int8, c_size_t, c_uint8, c_uint16, c_uint32, c_uint64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_lib", "libquantik_b200.so")
+LIB_PATH = os.environ.get("QUANTIK_B200_LIB") or os.path.join(_HERE, "_lib", "libquantik_b200.so")
 
 ABI_VERSION = 1
 MAX_DEPTH = 16

@@ -129,3 +129,35 @@ def test_eval_features_and_guided_policy(hs):
         hs.hs_guided(P(e), ctypes.c_size_t(1), ctypes.c_uint32(m), ctypes.c_uint64(seed), ctypes.c_uint64(0), ctypes.c_uint32(3),
                      ctypes.c_int(-1), ctypes.c_double(eps), P(w), P(oc), P(pl))
         assert np.array_equal(oc, g[name + "_outcome"]) and np.array_equal(pl, g[name + "_plies"]), name
+
+
+def test_fuzz_random_boards_vs_oracle(hs):
+    """Hypothesis-style sweep (tests/test_core.py:126-181 of the reference): arbitrary 8 x 16-bit boards -- reachable,
+    sparse garbage and dense garbage -- through the kernels' rule code vs the oracle's literal loops."""
+    rng = np.random.default_rng(2026)
+    reach = O.make_roots(6000, seed=99, min_plies=0, span=14)
+    sparse = (rng.integers(0, 65536, (6000, 8)) & rng.integers(0, 65536, (6000, 8)) & rng.integers(0, 65536, (6000, 8))
+              & rng.integers(0, 65536, (6000, 8))).astype(np.uint16)
+    dense = rng.integers(0, 65536, (3000, 8)).astype(np.uint16)
+    mutated = reach[:3000].copy()
+    mutated[np.arange(3000), rng.integers(0, 8, 3000)] |= (1 << rng.integers(0, 16, 3000)).astype(np.uint16)
+    s = np.ascontiguousarray(np.concatenate([reach, sparse, dense, mutated]))
+    n = len(s)
+    mask, tm, st = np.zeros(n, np.uint64), np.zeros(n, np.uint8), np.zeros(n, np.uint8)
+    hs.hs_movegen(P(s), ctypes.c_size_t(n), P(mask), P(tm), P(st))
+    om, ot, os_ = O.movegen_masks(s)
+    assert np.array_equal(mask, om) and np.array_equal(tm, ot) and np.array_equal(st, os_)
+    assert set(np.unique(st)) >= {0, 1, 2, 4, 5}
+    w = np.zeros(n, np.uint8)
+    hs.hs_win(P(s), ctypes.c_size_t(n), P(w))
+    assert np.array_equal(w, O.win_status(s))
+    for cs in (0, 1):
+        out, tr = np.zeros_like(s), np.zeros(n, np.uint32)
+        hs.hs_canonical(P(s), ctypes.c_size_t(n), cs, P(out), P(tr))
+        oc, otr = O.canonical(s, bool(cs), True)
+        assert np.array_equal(out, oc)
+        code = (otr[:, 0] | (otr[:, 1] << 3) | (otr[:, 3] << 4) | (otr[:, 4] << 6) | (otr[:, 5] << 8) | (otr[:, 6] << 10)).astype(np.uint32)
+        assert np.array_equal(tr, code)
+    o = np.zeros(n, np.uint8)
+    hs.hs_orbit(P(s), ctypes.c_size_t(n), P(o))
+    assert np.array_equal(o, O.orbit_size(s))

@@ -370,6 +370,33 @@ class State:
             o |= v
         return o
 
+    # CBOR wrappers (core.py:194-228): { "v":1, "canon":bool, "bb": h'16 bytes', ? "mc":uint, ? "meta":{...} }
+    def to_cbor(self, canon: bool = False, mc: Optional[int] = None, meta: Optional[Dict] = None) -> bytes:
+        try:
+            import cbor2
+        except ImportError:
+            raise RuntimeError("Please install cbor2 (pip install cbor2)")
+        m = {"v": VERSION, "canon": bool(canon), "bb": struct.pack("<8H", *self._bb)}
+        if mc is not None:
+            m["mc"] = int(mc)
+        if meta:
+            m["meta"] = meta
+        return cbor2.dumps(m)
+
+    @staticmethod
+    def from_cbor(data: bytes) -> "State":
+        try:
+            import cbor2
+        except ImportError:
+            raise RuntimeError("Please install cbor2 (pip install cbor2)")
+        m = cbor2.loads(data)
+        if m.get("v") != VERSION:
+            raise ValueError("Unsupported CBOR version")
+        bb = m.get("bb")
+        if not isinstance(bb, (bytes, bytearray)) or len(bb) != 16:
+            raise ValueError("CBOR field 'bb' must be 16 bytes")
+        return State(tuple(int(x) & 0xFFFF for x in struct.unpack("<8H", bb)))
+
 
 # ------------------------------------------------------------------ conformance record
 def portability_case_report(case_id: str, qfen: str, shape: int, position: int) -> dict:

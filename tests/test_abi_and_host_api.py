@@ -92,6 +92,15 @@ def test_pack_qfen_roundtrip_and_layout():
     assert s.get_occupied_bb() == 1 | 2048 | 8 | 32768 | 4 | 256
 
 
+def test_cbor_roundtrip():
+    pytest.importorskip("cbor2")
+    s = Q.State.from_qfen("A.bC/..../d..B/...a")
+    assert Q.State.from_cbor(s.to_cbor(canon=True, mc=3, meta={"k": 1})) == s
+    with pytest.raises(ValueError):
+        import cbor2
+        Q.State.from_cbor(cbor2.dumps({"v": 2, "bb": b"\x00" * 16}))
+
+
 def test_transform_codec_and_move_mapping():
     import oracle as O
     g = np.load(os.path.join(ROOT, "tests", "golden", "symmetry_images.npz"))

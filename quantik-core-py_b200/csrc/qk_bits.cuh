@@ -44,6 +44,18 @@ QK_HD int popc(uint32_t v)
     return __builtin_popcount(v);
 #endif
 }
+QK_HD uint32_t brev(uint32_t v)
+{
+#ifdef __CUDA_ARCH__
+    return __brev(v);
+#else
+    v = ((v >> 1) & 0x55555555u) | ((v & 0x55555555u) << 1);
+    v = ((v >> 2) & 0x33333333u) | ((v & 0x33333333u) << 2);
+    v = ((v >> 4) & 0x0F0F0F0Fu) | ((v & 0x0F0F0F0Fu) << 4);
+    v = ((v >> 8) & 0x00FF00FFu) | ((v & 0x00FF00FFu) << 8);
+    return (v >> 16) | (v << 16);
+#endif
+}
 QK_HD uint32_t mulhi(uint32_t a, uint32_t b)
 {
 #ifdef __CUDA_ARCH__
@@ -199,6 +211,9 @@ QK_HD uint32_t flip_rows(uint32_t v)   // reflH: (r,c) -> (3-r,c): reverse nibbl
     v = ((v & 0x0F0F0F0Fu) << 4) | (shr<4>(v) & 0x0F0F0F0Fu);
     return prmt(v, 0, 0x2301);
 }
+// reflH WITHOUT its final byte swap inside the lanes: the canonicalisation only ever feeds such an image to
+// byte-selecting PRMTs (sorted_image<true>), which absorb the pending swap for free.
+QK_HD uint32_t flip_rows_pending(uint32_t v) { return ((v & 0x0F0F0F0Fu) << 4) | ((v >> 4) & 0x0F0F0F0Fu); }
 QK_HD uint32_t transpose(uint32_t v)   // reflD: (r,c) -> (c,r)
 {
     uint32_t t = (v ^ shr<3>(v)) & 0x0A0A0A0Au;
@@ -206,18 +221,20 @@ QK_HD uint32_t transpose(uint32_t v)   // reflD: (r,c) -> (c,r)
     t = (v ^ shr<6>(v)) & 0x00CC00CCu;
     return v ^ t ^ (t << 6);
 }
+// rot180: (r,c) -> (3-r,3-c) reverses the 16 bits of each lane = BREV (XU pipe, idle in these kernels) + lane swap
+QK_HD uint32_t rot180(uint32_t v) { return prmt(brev(v), 0, 0x1032); }
 // d4 index as in symmetry.py:101-110: id rot90 rot180 rot270 reflV reflH reflD reflAD
 QK_HD uint32_t d4_apply(uint32_t v, int d4)
 {
     switch (d4) {
     case 0: return v;
     case 1: return flip_cols(transpose(v));
-    case 2: return flip_rows(flip_cols(v));
+    case 2: return rot180(v);
     case 3: return flip_rows(transpose(v));
     case 4: return flip_cols(v);
     case 5: return flip_rows(v);
     case 6: return transpose(v);
-    default: return flip_rows(flip_cols(transpose(v)));
+    default: return rot180(transpose(v));
     }
 }
 QK_HD State4 d4_apply(const State4 &s, int d4)
@@ -242,15 +259,58 @@ QK_HD bool key_less(const Key128 &p, const Key128 &q)
     uint64_t pl = ((uint64_t)p.c << 32) | p.d, ql = ((uint64_t)q.c << 32) | q.d;
     return ph < qh || (ph == qh && pl < ql);
 }
+// all-ones when p < q as 128-bit numbers, else 0: one borrow chain (4 subtracts) instead of 64-bit compare pairs
+QK_HD uint32_t key_less_mask(const Key128 &p, const Key128 &q)
+{
+#ifdef __CUDA_ARCH__
+    uint32_t m;
+    asm("{\n\t.reg .u32 t;\n\t"
+        "sub.cc.u32 t, %1, %5;\n\t"
+        "subc.cc.u32 t, %2, %6;\n\t"
+        "subc.cc.u32 t, %3, %7;\n\t"
+        "subc.cc.u32 t, %4, %8;\n\t"
+        "subc.u32 %0, 0, 0;\n\t}"
+        : "=r"(m) : "r"(p.d), "r"(p.c), "r"(p.b), "r"(p.a), "r"(q.d), "r"(q.c), "r"(q.b), "r"(q.a));
+    return m;
+#else
+    return key_less(p, q) ? 0xFFFFFFFFu : 0u;
+#endif
+}
+QK_HD void key_min(Key128 &best, const Key128 &k)
+{
+#ifdef __CUDA_ARCH__
+    // 0/1 flag from the borrow chain, then  best += flag * (k - best)  per limb: the selects run on the FMA pipe
+    // (IMAD), which these ALU-bound kernels leave almost idle
+    uint32_t f;
+    asm("{\n\t.reg .u32 t;\n\t"
+        "sub.cc.u32 t, %1, %5;\n\t"
+        "subc.cc.u32 t, %2, %6;\n\t"
+        "subc.cc.u32 t, %3, %7;\n\t"
+        "subc.cc.u32 t, %4, %8;\n\t"
+        "subc.u32 %0, 0, 0;\n\t}"
+        : "=r"(f) : "r"(k.d), "r"(k.c), "r"(k.b), "r"(k.a), "r"(best.d), "r"(best.c), "r"(best.b), "r"(best.a));
+    f = 0u - f;                                  // all-ones -> 1
+    asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(best.a) : "r"(f), "r"(k.a - best.a));
+    asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(best.b) : "r"(f), "r"(k.b - best.b));
+    asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(best.c) : "r"(f), "r"(k.c - best.c));
+    asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(best.d) : "r"(f), "r"(k.d - best.d));
+#else
+    const uint32_t m = key_less_mask(k, best);
+    best.a = (k.a & m) | (best.a & ~m); best.b = (k.b & m) | (best.b & ~m);
+    best.c = (k.c & m) | (best.c & ~m); best.d = (k.d & m) | (best.d & ~m);
+#endif
+}
 QK_HD bool key_equal(const Key128 &p, const Key128 &q) { return p.a == q.a && p.b == q.b && p.c == q.c && p.d == q.d; }
 
 QK_HD void cswap(uint32_t &p, uint32_t &q) { uint32_t lo = p < q ? p : q, hi = p < q ? q : p; p = lo; q = hi; }
 
-// sorted-shape arrangement of one board image (c0 = first colour's two registers)
+// sorted-shape arrangement of one board image (c0 = first colour's two registers).  PENDING = the registers
+// still owe a byte swap inside each lane (flip_rows_pending): only the PRMT selectors change.
+template <bool PENDING = false>
 QK_HD Key128 sorted_image(uint32_t c0ab, uint32_t c0cd, uint32_t c1ab, uint32_t c1cd)
 {
-    uint32_t k0 = prmt(c0ab, c1ab, 0x0145), k1 = prmt(c0ab, c1ab, 0x2367);
-    uint32_t k2 = prmt(c0cd, c1cd, 0x0145), k3 = prmt(c0cd, c1cd, 0x2367);
+    uint32_t k0 = prmt(c0ab, c1ab, PENDING ? 0x1054 : 0x0145), k1 = prmt(c0ab, c1ab, PENDING ? 0x3276 : 0x2367);
+    uint32_t k2 = prmt(c0cd, c1cd, PENDING ? 0x1054 : 0x0145), k3 = prmt(c0cd, c1cd, PENDING ? 0x3276 : 0x2367);
     cswap(k0, k1); cswap(k2, k3); cswap(k0, k2); cswap(k1, k3); cswap(k1, k2);
     Key128 r = { prmt(k0, k1, 0x3276), prmt(k2, k3, 0x3276), prmt(k0, k1, 0x1054), prmt(k2, k3, 0x1054) };
     return r;
@@ -266,27 +326,32 @@ QK_HD State4 canonical(const State4 &s)
 {
     Key128 best;
     bool have = false;
-    // walk D4 with one generator per step: id, V, HV, H | T, VT, HVT, HT
+    // Walk D4 with 20 ops per register instead of 50:
+    //   id, rot180 = BREV(id) | H' = reflH with its byte swap pending, BREV(H') = reflV |
+    //   T = reflD, BREV(T) = reflAD | H'(T) = rot270, BREV(H'(T)) = rot90.
+    // BREV (XU pipe, otherwise idle here) reverses each lane = rot180 and also swaps the two lanes of a register,
+    // i.e. relabels shapes A<->B and C<->D in both colours at once -- irrelevant, the four shape keys get sorted.
+    // The pending byte swap of H' survives BREV as a pending byte swap and is absorbed by sorted_image<true>.
     State4 g = s;
-#define QK_CANDIDATE()                                                          \
+#define QK_CANDIDATE(PENDING)                                                   \
     {                                                                           \
-        Key128 k = sorted_image(g.x, g.y, g.z, g.w);                            \
-        if (!have || key_less(k, best)) { best = k; have = true; }             \
-        if (COLOR_SWAP) {                                                       \
-            Key128 k2 = sorted_image(g.z, g.w, g.x, g.y);                       \
-            if (key_less(k2, best)) best = k2;                                  \
-        }                                                                       \
+        Key128 k = sorted_image<PENDING>(g.x, g.y, g.z, g.w);                   \
+        if (!have) { best = k; have = true; } else key_min(best, k);            \
+        if (COLOR_SWAP) key_min(best, sorted_image<PENDING>(g.z, g.w, g.x, g.y)); \
     }
 #define QK_STEP(F) { g.x = F(g.x); g.y = F(g.y); g.z = F(g.z); g.w = F(g.w); }
-    QK_CANDIDATE();                        // id
-    QK_STEP(flip_cols);  QK_CANDIDATE();   // reflV
-    QK_STEP(flip_rows);  QK_CANDIDATE();   // rot180
-    QK_STEP(flip_cols);  QK_CANDIDATE();   // reflH
+    QK_CANDIDATE(false);                              // id
+    QK_STEP(brev);               QK_CANDIDATE(false); // rot180
     g = s;
-    QK_STEP(transpose);  QK_CANDIDATE();   // reflD
-    QK_STEP(flip_cols);  QK_CANDIDATE();   // rot90
-    QK_STEP(flip_rows);  QK_CANDIDATE();   // reflAD
-    QK_STEP(flip_cols);  QK_CANDIDATE();   // rot270
+    QK_STEP(flip_rows_pending);  QK_CANDIDATE(true);  // reflH
+    QK_STEP(brev);               QK_CANDIDATE(true);  // reflV
+    g = s;
+    QK_STEP(transpose);          QK_CANDIDATE(false); // reflD
+    const State4 t = g;
+    QK_STEP(brev);               QK_CANDIDATE(false); // reflAD
+    g = t;
+    QK_STEP(flip_rows_pending);  QK_CANDIDATE(true);  // rot270
+    QK_STEP(brev);               QK_CANDIDATE(true);  // rot90
 #undef QK_STEP
 #undef QK_CANDIDATE
     return key_to_state(best);

@@ -106,8 +106,13 @@ QK_HD uint32_t scope_fill(uint32_t u)
 // (MAX_PIECES_PER_SHAPE = 2, commons.py:20; move.py:247-249).
 QK_HD uint32_t lanes_with_two(uint32_t u)
 {
-    uint32_t lo = u & 0xFFFFu, hi = u >> 16;
-    return ((lo & (lo - 1)) ? 0x0000FFFFu : 0u) | ((hi & (hi - 1)) ? 0xFFFF0000u : 0u);
+    // both lanes at once.  (u | H) - L never borrows across lanes, and u & that is non-zero in a lane exactly when
+    // the lane holds >= 2 bits (bit 15 survives only next to another bit; the low bits lose their lowest one).
+    const uint32_t H = 0x80008000u, L = 0x00010001u;
+    const uint32_t t = u & ((u | H) - L);
+    // non-zero lane -> bit 15 -> 0/1 -> 0xFFFF (the last step is an IMAD)
+    const uint32_t nz = (((t & ~H) + ~H) | t) & H;
+    return (nz >> 15) * 0xFFFFu;
 }
 
 // ---------------------------------------------------------------- win test

@@ -178,7 +178,8 @@ __global__ void __launch_bounds__(kBlock) k_perft_dfs(const uint4 *__restrict__ 
         if (idx >= n_items) break;
         const State4 item = to_state(__ldg(items + idx));
         const u64 m = mult[idx];
-        const int leaf_mover = (piece_balance(item) + rem0 - 1) & 1;   // who moves one ply above the target
+        const int item_parity = piece_balance(item);                   // player to move at the item
+        const int leaf_mover = (item_parity + rem0 - 1) & 1;           // who moves one ply above the target
         u64 leaf_nodes = 0, leaf_wins = 0, leaf_blocked = 0;           // per lane, unweighted
 
         int sp = 0, qn = 0;
@@ -189,7 +190,7 @@ __global__ void __launch_bounds__(kBlock) k_perft_dfs(const uint4 *__restrict__ 
             if (expand) {
                 // ---- interior node (warp-uniform): its moves, its winning moves
                 const int d = depth - node_rem;
-                const int mover = piece_balance(node);
+                const int mover = (item_parity + rem0 - node_rem) & 1;
                 uint32_t lo, hi, wab, wcd;
                 legal_masks(node, mover, lo, hi);
                 const int n_moves = popc(lo) + popc(hi);
@@ -212,7 +213,7 @@ __global__ void __launch_bounds__(kBlock) k_perft_dfs(const uint4 *__restrict__ 
                         while (qn >= 32) {
                             qn -= 32;
                             int nm, nw;
-                            leaf_parent_counts(to_state(ws.queue[qn + lane]), nm, nw);
+                            leaf_parent_counts_for(to_state(ws.queue[qn + lane]), leaf_mover, nm, nw);
                             leaf_nodes += nm; leaf_wins += nw; leaf_blocked += nm == 0;
                             __syncwarp();
                         }
@@ -230,7 +231,7 @@ __global__ void __launch_bounds__(kBlock) k_perft_dfs(const uint4 *__restrict__ 
             if (fm == 0) { --sp; expand = false; continue; }
             if (lane == 0) ws.frame_mask[sp - 1] = fm & (fm - 1);
             const State4 parent = to_state(ws.frame_state[sp - 1]);
-            node = apply_action(parent, piece_balance(parent), __ffsll((long long)fm) - 1);
+            node = apply_action(parent, (item_parity + sp - 1) & 1, __ffsll((long long)fm) - 1);
             node_rem = rem0 - sp;       // frame k sits k plies below the item
             expand = true;
             __syncwarp();
@@ -238,7 +239,7 @@ __global__ void __launch_bounds__(kBlock) k_perft_dfs(const uint4 *__restrict__ 
         // ---- drain the queue, fold this item's leaf tallies into the warp counters
         if ((int)lane < qn) {
             int nm, nw;
-            leaf_parent_counts(to_state(ws.queue[lane]), nm, nw);
+            leaf_parent_counts_for(to_state(ws.queue[lane]), leaf_mover, nm, nw);
             leaf_nodes += nm; leaf_wins += nw; leaf_blocked += nm == 0;
         }
         __syncwarp();

@@ -40,6 +40,16 @@ QK_HD void winning_squares(const State4 &s, uint32_t &win_ab, uint32_t &win_cd)
     win_cd = swap_lanes((r23 & rb01) | (z23 & zb01) | (c23 & cb01));
 }
 
+// same, when the caller already knows who is to move (depth parity): saves the four popcounts of piece_balance
+QK_HD void leaf_parent_counts_for(const State4 &s, int mover, int &n_moves, int &n_wins)
+{
+    uint32_t lo, hi, wab, wcd;
+    legal_masks(s, mover, lo, hi);
+    winning_squares(s, wab, wcd);
+    n_moves = popc(lo) + popc(hi);
+    n_wins = popc(lo & wab) + popc(hi & wcd);
+}
+
 // state must be valid and not already won.  Returns the mover; n_moves / n_wins
 // as described above.
 QK_HD int leaf_parent_counts(const State4 &s, int &n_moves, int &n_wins)

@@ -227,6 +227,26 @@ def main():
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e = per_step * world * args.steps / float(e2e_s.item())
 
+    # ---------------------------------------------------------------- perft nodes/s at N GPUs (config 5, shortened)
+    # the 10 946 canonical depth-4 classes (weighted) enumerated 6 plies deeper, roots dealt round-robin over the
+    # ranks, ONE all-reduce of the 5 x 7 counters (quantik_b200.dist.sharded_perft)
+    from quantik_b200 import dist as D
+    sharded = {}
+    d4_path = os.path.join(ROOT, "tests", "golden", "depth4_canonical.npz")
+    if not args.no_extra and os.path.exists(d4_path):
+        d4 = np.load(d4_path)
+        D.sharded_perft(d4["states"], 3, d4["mult"], device=dev)
+        barrier()
+        t0 = time.perf_counter()
+        p10 = D.sharded_perft(d4["states"], 6, d4["mult"], device=dev)
+        torch.cuda.synchronize()
+        t_perft = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=f"cuda:{dev}")
+        if world > 1:
+            dist.all_reduce(t_perft, op=dist.ReduceOp.MAX)
+        assert int(p10["nodes"][2]) == 6241600512 and int(p10["nodes"][4]) == 2097048766464      # GAME_TREE_ANALYSIS.md:9,11
+        sharded = {"perft_cfg5_depth10_weighted_nodes_per_s": float(p10["nodes"][1:].astype(np.float64).sum()) / float(t_perft.item()),
+                   "perft_cfg5_depth10_s": float(t_perft.item()), "perft_cfg5_n_gpus": world}
+
     if rank != 0:
         if world > 1:
             dist.barrier()
@@ -256,7 +276,7 @@ def main():
                 "pipe_fmaheavy_cycles_pct": 65.7, "pipe_xu_pct": 27.3, "lanes_active_per_inst": 30.1},
     }
 
-    extra = {}
+    extra = dict(sharded)
     if not args.no_extra:
         # config 2: exhaustive perft from the empty board to depth 6 (bit-exact counts asserted)
         e = np.zeros((1, 8), np.uint16)

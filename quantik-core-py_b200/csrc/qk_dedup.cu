@@ -140,56 +140,105 @@ __global__ void __launch_bounds__(kBlock) k_emit(const Slot *keys, const u64 *mu
 }
 
 // ---------------------------------------------------------------------------------------------
-// One BFS level of game_stats.SymmetryTable._process_depth (game_stats.py:359-485), fused:
-// warp per parent; the parent's legal / winning-move masks are warp-uniform, lane l materialises
-// children l and l+32, canonicalises them in registers and inserts them into the table with the
-// parent's multiplicity.  Children are never written to HBM.
+// One BFS level of game_stats.SymmetryTable._process_depth (game_stats.py:359-485), fused: expand the
+// parents, drop line-completing moves, canonicalise the other children in registers and insert them into
+// the table with the parent's multiplicity.  Children are never written to HBM.
 // stats: [0] total_moves  [1] line wins by P0  [2] by P1  [3] parents with P0 blocked  [4] P1 blocked
+// Lanes first play "one parent each" (masks, counts), then the children of the 32 parents are dealt out
+// evenly: every lane canonicalises and inserts one child per round, so the expensive part (330 instructions
+// of canonicalisation, the random table probe) runs with full warps and 32 probes in flight per warp --
+// a warp-per-parent version kept ~8 of 32 lanes busy (late-game parents have few children).
+struct BfsWarpScratch {
+    uint4 state[32];               // the tile's parents
+    u64 mult[32];
+    unsigned short queue[2048];    // (parent lane << 6 | action) of every non-winning child of the tile
+    unsigned char mover[32];
+};
+
+__device__ __forceinline__ void table_insert(Slot *table, u64 *counts, size_t slot_mask, u64 khi_new, u64 klo_new, u64 m,
+                                             u64 *n_unique, u64 *all_ones_count, int *overflow, u64 max_unique)
+{
+    if ((khi_new & klo_new) == ~0ull) { atomicAdd(all_ones_count, m); return; }
+    size_t slot = (size_t)mix(khi_new, klo_new) & slot_mask;
+    for (size_t probe = 0; probe <= slot_mask; ++probe, slot = (slot + 1) & slot_mask) {
+        const ulonglong2 raw = __ldcv(reinterpret_cast<const ulonglong2 *>(table + slot));
+        u64 khi = raw.x, klo = raw.y;
+        if (khi == ~0ull || klo == ~0ull) {
+            cas128(table + slot, ~0ull, ~0ull, khi_new, klo_new, khi, klo);
+            if (khi == ~0ull && klo == ~0ull) {
+                if (atomicAdd(n_unique, 1ull) >= max_unique) *overflow = 1;
+                khi = khi_new; klo = klo_new;
+            }
+        }
+        if (khi == khi_new && klo == klo_new) { atomicAdd(counts + slot, m); return; }   // game_stats.py:487-505
+    }
+}
+
 template <bool COLOR_SWAP>
 __global__ void __launch_bounds__(kBlock) k_bfs_expand_insert(const uint4 *__restrict__ parents, const u64 *__restrict__ mult,
                                                                size_t n, Slot *table, u64 *counts, size_t slot_mask,
                                                                u64 *n_unique, u64 *all_ones_count, int *overflow,
                                                                u64 max_unique, u64 *stats)
 {
+    __shared__ BfsWarpScratch s_scratch[kBlock / 32];
+    BfsWarpScratch &ws = s_scratch[threadIdx.x >> 5];
     const unsigned lane = threadIdx.x & 31u;
     const size_t warp = (blockIdx.x * (size_t)kBlock + threadIdx.x) >> 5, n_warps = ((size_t)gridDim.x * kBlock) >> 5;
-    u64 s_moves = 0, s_w0 = 0, s_w1 = 0, s_b0 = 0, s_b1 = 0;      // warp-uniform running sums
-    for (size_t i = warp; i < n; i += n_warps) {
+    u64 s_moves = 0, s_w0 = 0, s_w1 = 0, s_b0 = 0, s_b1 = 0;      // per lane
+    for (size_t tile = warp * 32; tile < n; tile += n_warps * 32) {
         if (*reinterpret_cast<volatile int *>(overflow)) break;     // table too small: the host retries with a larger one
-        const uint4 v = __ldg(parents + i);
-        const State4 parent = { v.x, v.y, v.z, v.w };
-        const u64 m = mult ? mult[i] : 1ull;
-        const int mover = piece_balance(parent);
-        uint32_t lo, hi, wab, wcd;
-        legal_masks(parent, mover, lo, hi);
-        const int n_moves = popc(lo) + popc(hi);
-        if (n_moves == 0) { if (mover == 0) s_b0 += m; else s_b1 += m; continue; }     // game_stats.py:426-443
-        winning_squares(parent, wab, wcd);
-        s_moves += (u64)n_moves * m;                                                   // :401
-        const u64 wins = (u64)(popc(lo & wab) + popc(hi & wcd)) * m;                   // :411-415
-        if (mover == 0) s_w0 += wins; else s_w1 += wins;
-        const uint32_t nl = lo & ~wab, nh = hi & ~wcd;
+        // ---- one parent per lane: moves, winning moves, the children worth keeping
+        uint32_t nl = 0, nh = 0;
+        const size_t i = tile + lane;
+        if (i < n) {
+            const uint4 v = __ldg(parents + i);
+            const State4 parent = { v.x, v.y, v.z, v.w };
+            const u64 m = mult ? mult[i] : 1ull;
+            const int mover = piece_balance(parent);
+            uint32_t lo, hi, wab, wcd;
+            legal_masks(parent, mover, lo, hi);
+            const int n_moves = popc(lo) + popc(hi);
+            if (n_moves == 0) { if (mover == 0) s_b0 += m; else s_b1 += m; }           // game_stats.py:426-443
+            else {
+                winning_squares(parent, wab, wcd);
+                s_moves += (u64)n_moves * m;                                            // :401
+                const u64 wins = (u64)(popc(lo & wab) + popc(hi & wcd)) * m;            // :411-415
+                if (mover == 0) s_w0 += wins; else s_w1 += wins;
+                nl = lo & ~wab; nh = hi & ~wcd;
+            }
+            ws.state[lane] = v; ws.mult[lane] = m; ws.mover[lane] = (unsigned char)mover;
+        }
+        // ---- deal the children out: exclusive scan of the counts, then every lane lists its own
+        const uint32_t cnt = (uint32_t)(popc(nl) + popc(nh));
+        uint32_t incl = cnt;
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            if (!(((half ? nh : nl) >> lane) & 1u)) continue;
-            const State4 c = canonical<COLOR_SWAP>(apply_action(parent, mover, half * 32 + (int)lane));   // :453,:468
-            const u64 khi_new = ((u64)prmt(c.x, 0, 0x0123) << 32) | prmt(c.y, 0, 0x0123);
-            const u64 klo_new = ((u64)prmt(c.z, 0, 0x0123) << 32) | prmt(c.w, 0, 0x0123);
-            if ((khi_new & klo_new) == ~0ull) { atomicAdd(all_ones_count, m); continue; }
-            size_t slot = (size_t)mix(khi_new, klo_new) & slot_mask;
-            for (size_t probe = 0; probe <= slot_mask; ++probe, slot = (slot + 1) & slot_mask) {
-                const ulonglong2 raw = __ldcv(reinterpret_cast<const ulonglong2 *>(table + slot));
-                u64 khi = raw.x, klo = raw.y;
-                if (khi == ~0ull || klo == ~0ull) {
-                    cas128(table + slot, ~0ull, ~0ull, khi_new, klo_new, khi, klo);
-                    if (khi == ~0ull && klo == ~0ull) {
-                        if (atomicAdd(n_unique, 1ull) >= max_unique) *overflow = 1;
-                        khi = khi_new; klo = klo_new;
-                    }
-                }
-                if (khi == khi_new && klo == klo_new) { atomicAdd(counts + slot, m); break; }   // :487-505
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= (unsigned)o) incl += t; }
+        const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+        uint32_t at = incl - cnt;
+        for (uint32_t w = nl; w; w &= w - 1) ws.queue[at++] = (unsigned short)((lane << 6) | (uint32_t)(__ffs((int)w) - 1));
+        for (uint32_t w = nh; w; w &= w - 1) ws.queue[at++] = (unsigned short)((lane << 6) | (uint32_t)(32 + __ffs((int)w) - 1));
+        __syncwarp();
+        // ---- full warps: one child per lane per round, never written to HBM
+        for (uint32_t base = 0; base < total; base += 32) {
+            const uint32_t idx = base + lane;
+            if (idx < total) {
+                const uint32_t e = ws.queue[idx], pl = e >> 6;
+                const uint4 pv = ws.state[pl];
+                const State4 parent = { pv.x, pv.y, pv.z, pv.w };
+                const State4 c = canonical<COLOR_SWAP>(apply_action(parent, ws.mover[pl], (int)(e & 63u)));   // :453,:468
+                table_insert(table, counts, slot_mask, ((u64)prmt(c.x, 0, 0x0123) << 32) | prmt(c.y, 0, 0x0123),
+                             ((u64)prmt(c.z, 0, 0x0123) << 32) | prmt(c.w, 0, 0x0123), ws.mult[pl], n_unique, all_ones_count,
+                             overflow, max_unique);
             }
         }
+        __syncwarp();
+    }
+    // per-lane sums -> one atomic per warp and counter
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s_moves += __shfl_xor_sync(0xFFFFFFFFu, s_moves, o); s_w0 += __shfl_xor_sync(0xFFFFFFFFu, s_w0, o);
+        s_w1 += __shfl_xor_sync(0xFFFFFFFFu, s_w1, o); s_b0 += __shfl_xor_sync(0xFFFFFFFFu, s_b0, o);
+        s_b1 += __shfl_xor_sync(0xFFFFFFFFu, s_b1, o);
     }
     if (lane == 0) {
         if (s_moves) atomicAdd(stats + 0, s_moves);
@@ -383,8 +432,8 @@ int run_bfs_level(Call &call, const uint4 *parents, const uint64_t *mult, size_t
     DedupTable t;
     int rc = dedup_begin(call, cap, t);
     if (rc != QK_OK) return rc;
-    // one warp per parent, grid-stride; 8 resident CTAs per SM
-    const unsigned grid = grid_for(n * 32, kBlock, c->sms, 8);
+    // one parent per lane (tiles of 32 per warp), grid-stride
+    const unsigned grid = grid_for(n, kBlock, c->sms, 5);
     if (color_swap)
         k_bfs_expand_insert<true><<<grid, kBlock, 0, s>>>(parents, (const u64 *)mult, n, t.table, t.counts, t.slots - 1, t.meta, t.meta + 1,
                                                          (int *)(t.meta + 3), t.max_unique, t.meta + 4);

@@ -113,7 +113,11 @@ QK_API int qk_apply_symmetry(const uint16_t *states, const uint16_t *transform, 
  *                      canonicalise n states, merge equal payloads, sum multiplicities
  *                      (mult == NULL: 1 each).  uniq (capacity `cap` states) receives the
  *                      distinct payloads sorted in byte order, uniq_mult their summed
- *                      multiplicities, *n_uniq the count (host pointer).  Synchronous.   */
+ *                      multiplicities, *n_uniq the count (host pointer).  Synchronous.
+ *                      color_swap is a flag word here: bit 0 = the 384-image mode, bit 1
+ *                      (QK_DEDUP_UNSORTED) = leave the output in table order (skips the sort;
+ *                      uniq must then hold cap + 1 states, uniq_mult cap + 1 counts).      */
+#define QK_DEDUP_UNSORTED 2
 QK_API int qk_canon_dedup(const uint16_t *states, const uint64_t *mult, size_t n, int color_swap,
                    uint16_t *uniq, uint64_t *uniq_mult, size_t cap, size_t *n_uniq,
                    int dev, void *stream);

@@ -129,6 +129,37 @@ __global__ void __launch_bounds__(kBlock) k_bitonic_step(Slot *keys, u64 *mults,
     }
 }
 
+// every compare-exchange step of distance < kTile of the stages k_lo..k_hi, on a tile held in shared memory
+// (one global round trip instead of up to 55)
+static constexpr unsigned kTile = 1024;
+__global__ void __launch_bounds__(kBlock) k_bitonic_tile(Slot *keys, u64 *mults, size_t n, size_t k_lo, size_t k_hi)
+{
+    __shared__ Slot s_key[kTile];
+    __shared__ u64 s_mult[kTile];
+    for (size_t base = blockIdx.x * (size_t)kTile; base < n; base += (size_t)gridDim.x * kTile) {
+        for (unsigned t = threadIdx.x; t < kTile; t += kBlock) { s_key[t] = keys[base + t]; s_mult[t] = mults[base + t]; }
+        __syncthreads();
+        for (size_t k = k_lo; k <= k_hi; k <<= 1) {
+            unsigned j = (k >> 1) < (kTile >> 1) ? (unsigned)(k >> 1) : (kTile >> 1);
+            for (; j > 0; j >>= 1) {
+                for (unsigned t = threadIdx.x; t < kTile / 2; t += kBlock) {
+                    const unsigned i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), p = i | j;
+                    const Slot a = s_key[i], b = s_key[p];
+                    const bool a_gt_b = a.hi > b.hi || (a.hi == b.hi && a.lo > b.lo);
+                    const bool up = ((base + i) & k) == 0;
+                    if (a_gt_b == up) {
+                        s_key[i] = b; s_key[p] = a;
+                        const u64 m = s_mult[i]; s_mult[i] = s_mult[p]; s_mult[p] = m;
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        for (unsigned t = threadIdx.x; t < kTile; t += kBlock) { keys[base + t] = s_key[t]; mults[base + t] = s_mult[t]; }
+        __syncthreads();
+    }
+}
+
 __global__ void __launch_bounds__(kBlock) k_emit(const Slot *keys, const u64 *mults, size_t n, uint4 *uniq, u64 *uniq_mult)
 {
     for (size_t i = blockIdx.x * (size_t)kBlock + threadIdx.x; i < n; i += (size_t)gridDim.x * kBlock) {
@@ -377,16 +408,20 @@ static int dedup_finish(Call &call, DedupTable &t, uint16_t *uniq, uint64_t *uni
         *n_uniq = nu;
         return QK_OK;
     }
-    size_t padded = 1;
+    size_t padded = kTile;
     while (padded < nu) padded <<= 1;
     Slot *keys = (Slot *)call.temp((padded + 1) * sizeof(Slot));
     u64 *mults = (u64 *)call.temp((padded + 1) * sizeof(u64));
     if (!keys || !mults) return call.status();
     k_dedup_compact<<<grid_for(t.slots, kBlock, c->sms, 8), kBlock, 0, s>>>(t.table, t.counts, t.slots, keys, mults, t.meta + 2);
     k_pad<<<grid_for(padded - nu + 1, kBlock, c->sms, 8), kBlock, 0, s>>>(keys, mults, nu, padded);
-    for (size_t k = 2; k <= padded; k <<= 1)
-        for (size_t j = k >> 1; j > 0; j >>= 1)
+    const unsigned tile_grid = grid_for(padded / kTile * kBlock, kBlock, c->sms, 8);
+    k_bitonic_tile<<<tile_grid, kBlock, 0, s>>>(keys, mults, padded, 2, kTile);
+    for (size_t k = 2 * (size_t)kTile; k <= padded; k <<= 1) {
+        for (size_t j = k >> 1; j >= kTile; j >>= 1)
             k_bitonic_step<<<grid_for(padded, kBlock, c->sms, 8), kBlock, 0, s>>>(keys, mults, padded, j, k);
+        k_bitonic_tile<<<tile_grid, kBlock, 0, s>>>(keys, mults, padded, k, k);
+    }
     QK_CUDA(cudaGetLastError());
     if (special) {   // the all-ones payload sorts last by construction
         Slot ones = { ~0ull, ~0ull };
@@ -414,14 +449,15 @@ int run_dedup(Call &call, const uint4 *states, const uint64_t *mult, size_t n, i
     DedupTable t;
     int rc = dedup_begin(call, n < cap ? n : cap, t);
     if (rc != QK_OK) return rc;
-    if (color_swap)
+    const bool unsorted = (color_swap & QK_DEDUP_UNSORTED) != 0;
+    if (color_swap & 1)
         k_dedup_insert<true><<<grid_for(n, kBlock, c->sms, 8), kBlock, 0, s>>>(states, (const u64 *)mult, n, t.table, t.counts, t.slots - 1,
                                                                              t.meta, t.meta + 1, (int *)(t.meta + 3), t.max_unique);
     else
         k_dedup_insert<false><<<grid_for(n, kBlock, c->sms, 8), kBlock, 0, s>>>(states, (const u64 *)mult, n, t.table, t.counts, t.slots - 1,
                                                                               t.meta, t.meta + 1, (int *)(t.meta + 3), t.max_unique);
     QK_CUDA(cudaGetLastError());
-    return dedup_finish(call, t, uniq, uniq_mult, cap, n_uniq, nullptr, "qk_canon_dedup");
+    return dedup_finish(call, t, uniq, uniq_mult, cap, n_uniq, nullptr, "qk_canon_dedup", !unsorted);
 }
 
 int run_bfs_level(Call &call, const uint4 *parents, const uint64_t *mult, size_t n, int color_swap, int sort_output,

@@ -177,18 +177,20 @@ def apply_symmetry(states, transforms, device: Optional[int] = None):
     return out.obj
 
 
-def canon_dedup(states, mult=None, color_swap: bool = False, cap: Optional[int] = None, device: Optional[int] = None):
+def canon_dedup(states, mult=None, color_swap: bool = False, cap: Optional[int] = None, device: Optional[int] = None,
+                sort_output: bool = True):
     """Canonicalise, merge equal payloads, sum multiplicities (game_stats.py:487-505).
-    -> (unique payloads sorted in byte order (U, 8), multiplicities (U,))."""
+    -> (unique payloads (U, 8) -- sorted in byte order unless sort_output=False --, multiplicities (U,))."""
     s, on_dev, d = _states_in(states)
     d = _dev(device, on_dev, d)
     lib = N.init(d)
     m = _aux_in(mult, np.uint64, on_dev, d)
     cap = s.n if cap is None else int(cap)
-    uniq = _out((cap, 8), np.uint16, on_dev, d)
-    um = _out((cap,), np.uint64, on_dev, d)
+    uniq = _out((cap + 1, 8), np.uint16, on_dev, d)
+    um = _out((cap + 1,), np.uint64, on_dev, d)
     nu = ctypes.c_size_t(0)
-    N.check(lib.qk_canon_dedup(s.ptr, m.ptr, s.n, int(bool(color_swap)), uniq.ptr, um.ptr, cap, ctypes.byref(nu),
+    flags = int(bool(color_swap)) | (0 if sort_output else 2)          # QK_DEDUP_UNSORTED
+    N.check(lib.qk_canon_dedup(s.ptr, m.ptr, s.n, flags, uniq.ptr, um.ptr, cap, ctypes.byref(nu),
                                d, _stream(on_dev, d)))
     return uniq.obj[:nu.value], um.obj[:nu.value]
 

@@ -98,3 +98,136 @@ def sharded_perft(roots: np.ndarray, depth: int, mult: Optional[np.ndarray] = No
             local[i] = p[k].astype(np.int64)
     tot = all_reduce_counts(local, device, group)
     return {k: tot[i].astype(np.uint64) for i, k in enumerate(names)}
+
+
+# ----------------------------------------------------------------------------- global dedup: the one exchange step
+# Canonical keys shard by index range, but GLOBAL unique counts need equal payloads to meet on one rank
+# (SURVEY 8e): every payload has an owner rank = hash(payload) mod world; one all-to-all moves each locally
+# merged (payload, multiplicity) pair to its owner, which merges again.  torch is plumbing here: the hash,
+# the bucket sort and the collective; canonicalisation and both merges are the library's kernels.
+def _as_i64_pairs(payloads):
+    """(U, 8) uint16 numpy / int16 torch -> torch int64 (U, 2) on the same device, no copy where possible."""
+    import torch
+    if isinstance(payloads, torch.Tensor):
+        return payloads.contiguous().view(torch.int64).reshape(-1, 2)
+    a = np.ascontiguousarray(payloads, dtype=np.uint16).reshape(-1, 8)
+    return torch.from_numpy(a.view(np.int64).reshape(-1, 2))
+
+
+def owner_rank(payloads, world: int):
+    """Owner of each canonical payload: a 64-bit mix of its two halves, mod world (torch int64 tensor)."""
+    import torch
+    p = _as_i64_pairs(payloads)
+    h = p[:, 0] * -7046029254386353131 + p[:, 1] * -4417276706812531889      # wraps mod 2^64
+    h = h ^ (h >> 29)
+    h = h * -4658895280553007687
+    h = h ^ (h >> 32)
+    return torch.remainder(h & 0x7FFFFFFFFFFFFFFF, world)
+
+
+def exchange_by_owner(payloads, mult, group=None):
+    """Send every (payload, multiplicity) pair to its owner rank with one all-to-all (three
+    all_to_all_single calls: counts, payloads, multiplicities).  -> (received int64 (R, 2), received int64 (R,))
+    on the device the inputs live on.  With one rank it is the identity."""
+    import torch
+    import torch.distributed as dist
+    p = _as_i64_pairs(payloads)
+    m = mult if isinstance(mult, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(mult).astype(np.int64))
+    m = m.to(p.device).reshape(-1)
+    rank, world = _world(group)
+    if world == 1:
+        return p, m
+    if dist.get_backend(group) == "nccl" and not p.is_cuda:
+        p, m = p.cuda(), m.cuda()
+    owner = owner_rank(p, world)
+    order = torch.argsort(owner, stable=True)
+    send_p, send_m = p[order].contiguous(), m[order].contiguous()
+    send_counts = torch.bincount(owner, minlength=world)
+    recv_counts = torch.empty_like(send_counts)
+    dist.all_to_all_single(recv_counts, send_counts, group=group)
+    ins, outs = send_counts.tolist(), recv_counts.tolist()
+    recv_p = torch.empty((sum(outs), 2), dtype=torch.int64, device=p.device)
+    recv_m = torch.empty((sum(outs),), dtype=torch.int64, device=p.device)
+    dist.all_to_all_single(recv_p, send_p, outs, ins, group=group)
+    dist.all_to_all_single(recv_m, send_m, outs, ins, group=group)
+    return recv_p, recv_m
+
+
+def _like_states(p64, host: bool):
+    """int64 (U, 2) tensor -> what the batch API takes: numpy (U, 8) uint16 on the host, the tensor itself on the GPU."""
+    if host or not p64.is_cuda:
+        return p64.cpu().numpy().view(np.uint16).reshape(-1, 8)
+    return p64
+
+
+def sharded_canon_dedup(states, mult=None, color_swap: bool = False, device: Optional[int] = None, group=None,
+                        dedup_fn: Callable[..., Tuple] = B.canon_dedup, sort_output: bool = False):
+    """BASELINE config 3 at N GPUs: every rank passes ITS slice of the states; returns
+    (payloads this rank owns, their global multiplicities, global number of distinct classes).
+    local canonicalise+merge -> all-to-all by owner -> merge at the owner -> all-reduce of the counts."""
+    import torch
+    n = len(states)
+    _, world = _world(group)
+    if n:       # the local merge feeds the exchange: its order is irrelevant unless it is also the result
+        uniq, um = dedup_fn(states, mult, color_swap=color_swap, device=device, sort_output=sort_output and world == 1)
+    else:
+        uniq, um = np.zeros((0, 8), np.uint16), np.zeros(0, np.uint64)
+    host = not (isinstance(uniq, torch.Tensor) and uniq.is_cuda)
+    rp, rm = exchange_by_owner(uniq, um, group)
+    if world > 1 and len(rp):
+        mine, mm = dedup_fn(_like_states(rp, host), rm if not host else rm.cpu().numpy().astype(np.uint64),
+                            color_swap=color_swap, device=device, sort_output=sort_output)
+    elif world > 1:
+        mine, mm = np.zeros((0, 8), np.uint16), np.zeros(0, np.uint64)
+    else:
+        mine, mm = uniq, um
+    total = all_reduce_counts(np.array([len(mine)], np.int64), device, group)
+    return mine, mm, int(total[0])
+
+
+def sharded_symmetry_table(max_depth: int, device: Optional[int] = None, group=None, on_device: bool = True,
+                           bfs_fn: Callable[..., Tuple] = B.bfs_level, dedup_fn: Callable[..., Tuple] = B.canon_dedup):
+    """SymmetryTable.analyze_game_tree (game_stats.py:276-296) with the frontier PARTITIONED over the ranks by
+    owner_rank: per depth every rank expands + canonicalises + merges its share (qk_bfs_level), sends each child
+    class to its owner (exchange_by_owner), the owner merges (qk_canon_dedup), and one all-reduce sums the
+    level's counters.  Same rows as batch.symmetry_table on every rank."""
+    import torch
+    rank, world = _world(group)
+    d = 0 if device is None else int(device)
+    on_device = on_device and torch.cuda.is_available()
+    empty = np.zeros((1, 8), np.uint16)
+    mine = int(owner_rank(empty, world)[0]) == rank
+    frontier = empty[: 1 if mine else 0]
+    mult = np.ones(1 if mine else 0, np.uint64)
+    if on_device:
+        frontier = torch.from_numpy(frontier.view(np.int16)).to(f"cuda:{d}")
+        mult = torch.from_numpy(mult.astype(np.int64)).to(f"cuda:{d}")
+    rows = []
+    growth = 64.0                   # local children per local parent at the previous depth: sizes the merge table
+    for _depth in range(1, max_depth + 1):
+        n = int(frontier.shape[0])
+        stats = np.zeros(7, np.int64)
+        kids, kmult = np.zeros((0, 8), np.uint16), np.zeros(0, np.uint64)
+        if n:
+            cap = int(min(64 * n, max(1 << 12, 1.6 * growth * n)))      # bfs_level doubles it when it was too small
+            kids, kmult, st = bfs_fn(frontier, mult, cap=cap, sort_output=False, device=d)
+            growth = max(0.05, int(kids.shape[0]) / n)
+            stats[:5] = [st["total_moves"], st["line_wins_p0"], st["line_wins_p1"], st["blocked_p0"], st["blocked_p1"]]
+        host = not (isinstance(kids, torch.Tensor) and kids.is_cuda)
+        if host and on_device:      # an empty shard still has to join the collective on the GPU
+            kids = torch.zeros((0, 8), dtype=torch.int16, device=f"cuda:{d}")
+            kmult = torch.zeros(0, dtype=torch.int64, device=f"cuda:{d}")
+            host = False
+        rp, rm = exchange_by_owner(kids, kmult, group)
+        if world > 1 and len(rp):
+            frontier, mult = dedup_fn(_like_states(rp, host), rm if not host else rm.cpu().numpy().astype(np.uint64),
+                                      device=d, sort_output=False)
+        elif world > 1:
+            frontier, mult = kids[:0], kmult[:0]
+        else:
+            frontier, mult = kids, kmult
+        stats[5] = int(frontier.shape[0])
+        stats[6] = int(mult.sum()) if len(mult) else 0
+        tot = all_reduce_counts(stats, d, group)
+        rows.append([int(tot[0]), int(tot[5]), int(tot[1] + tot[4]), int(tot[2] + tot[3]), int(tot[6])])
+    return rows

@@ -40,8 +40,39 @@ def _worker(rank, world, port, q):
     roots = O.make_roots(37)
     per_root = D.sharded_root_tallies(roots, 64, seed=O.SEED_DEFAULT, playouts_fn=playouts_fn)
     pf = D.sharded_perft(roots[:9], 2, mult=np.arange(1, 10, dtype=np.uint64), perft_fn=perft_fn)
+
+    # the exchange step: global dedup and the partitioned BFS (oracle stand-ins for the two kernels)
+    def dedup_fn(states, mult=None, color_swap=False, cap=None, device=None, sort_output=True):
+        s = np.asarray(states, np.uint16).reshape(-1, 8)
+        m = np.ones(len(s), np.uint64) if mult is None else np.asarray(mult, np.uint64)
+        canon = O.canonical(s, color_swap)
+        uniq, inv = np.unique(np.ascontiguousarray(canon).view("V16").ravel(), return_inverse=True)
+        sums = np.zeros(len(uniq), np.uint64)
+        np.add.at(sums, inv, m)
+        return uniq.view(np.uint16).reshape(-1, 8), sums
+
+    def bfs_fn(frontier, mult, cap=0, sort_output=False, device=None):
+        f = np.asarray(frontier, np.uint16).reshape(-1, 8)
+        m = np.asarray(mult, np.uint64)
+        mask, tm, _ = O.movegen_masks(f)
+        idx = [i for i, mk in enumerate(mask) for a in range(64) if (int(mk) >> a) & 1]
+        act = [a for mk in mask for a in range(64) if (int(mk) >> a) & 1]
+        kids = O.apply_moves(f[idx], np.array(act, np.uint8))
+        km = m[idx]
+        win = O.win_status(kids)
+        st = {"total_moves": int(km.sum()), "line_wins_p0": int(km[win == 1].sum()), "line_wins_p1": int(km[win == 2].sum()),
+              "blocked_p0": int(m[(mask == 0) & (tm == 0)].sum()), "blocked_p1": int(m[(mask == 0) & (tm == 1)].sum())}
+        u, um = dedup_fn(kids[win == 0], km[win == 0])
+        return u, um, st
+
+    images = np.load(os.path.join(ROOT, "tests", "golden", "symmetry_images.npz"))
+    pool = np.concatenate([images["image"], images["states"]]).astype(np.uint16)
+    b, e = D.shard_range(len(pool), rank, world)
+    own, own_mult, n_global = D.sharded_canon_dedup(pool[b:e], None, dedup_fn=dedup_fn)
+    rows = D.sharded_symmetry_table(4, on_device=False, bfs_fn=bfs_fn, dedup_fn=dedup_fn)
+    q.put(("shard", rank, np.asarray(own).tolist(), np.asarray(own_mult).tolist(), n_global, rows))
     if rank == 0:
-        q.put((tally.tolist(), per_root.tolist(), {k: v.tolist() for k, v in pf.items()}))
+        q.put(("main", tally.tolist(), per_root.tolist(), {k: v.tolist() for k, v in pf.items()}))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -65,10 +96,12 @@ def test_world2_matches_single_process():
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    tally, per_root, pf = q.get(timeout=180)
+    got = [q.get(timeout=300) for _ in range(3)]
     for p in procs:
         p.join(60)
         assert p.exitcode == 0
+    _, tally, per_root, pf = next(g for g in got if g[0] == "main")
+    shards = sorted((g for g in got if g[0] == "shard"), key=lambda g: g[1])
     one = O.playouts(np.zeros((1, 8), np.uint16), 5001)
     assert tally == [int(one["wins_p0"][0]), int(one["wins_p1"][0]), int(one["draws"][0])]
     roots = O.make_roots(37)
@@ -77,3 +110,23 @@ def test_world2_matches_single_process():
     want = O.perft(roots[:9], 2, np.arange(1, 10, dtype=np.uint64))
     for k in want:
         assert pf[k] == want[k].tolist()
+
+    # global dedup: the owners' shares are disjoint, their union equals the single-process result
+    images = np.load(os.path.join(ROOT, "tests", "golden", "symmetry_images.npz"))
+    pool = np.concatenate([images["image"], images["states"]]).astype(np.uint16)
+    canon = O.canonical(pool)
+    uniq, counts = np.unique(np.ascontiguousarray(canon).view("V16").ravel(), return_counts=True)
+    want = {bytes(u): int(c) for u, c in zip(uniq, counts)}
+    have = {}
+    for _, _, own, own_mult, n_global, _ in shards:
+        assert n_global == len(want)
+        for p_, m_ in zip(own, own_mult):
+            key = np.array(p_, np.uint16).tobytes()
+            assert key not in have
+            have[key] = int(m_)
+    assert have == want
+    assert min(len(s[2]) for s in shards) > 0            # both ranks own something
+    # partitioned BFS: the reference's table rows (GAME_TREE_ANALYSIS.md:4-7), identical on every rank
+    table = O.symmetry_table(4)
+    for s in shards:
+        assert np.array_equal(np.array(s[5], np.uint64), table)

@@ -189,6 +189,15 @@ def test_canon_dedup_vs_oracle_with_multiplicities():
     np.add.at(want_mult, inv.ravel(), mult)
     assert np.array_equal(uniq.astype("<u2").view(np.uint8).reshape(-1, 16), keys)
     assert np.array_equal(um, want_mult)
+    u2, m2 = B.canon_dedup(s, mult, sort_output=False)      # QK_DEDUP_UNSORTED: same set, table order
+    order = np.lexsort(u2.astype("<u2").view(np.uint8).reshape(-1, 16).T[::-1])
+    assert np.array_equal(u2[order], uniq) and np.array_equal(m2[order], um)
+    for n_small in (1, 2, 1023, 1025, 4097):               # sort sizes around the shared-memory tile
+        u3, m3 = B.canon_dedup(s[:n_small], mult[:n_small])
+        k3, inv3 = np.unique(oc[:n_small], axis=0, return_inverse=True)
+        w3 = np.zeros(len(k3), np.uint64)
+        np.add.at(w3, inv3.ravel(), mult[:n_small])
+        assert np.array_equal(u3.astype("<u2").view(np.uint8).reshape(-1, 16), k3) and np.array_equal(m3, w3)
     ones = np.full((5, 8), 0xFFFF, np.uint16)              # the payload that equals the table's empty marker
     uniq, um = B.canon_dedup(np.concatenate([s[:100], ones]))
     assert np.array_equal(uniq[-1], ones[0]) and int(um[-1]) == 5
@@ -576,3 +585,31 @@ def test_engine_plugins():
     o = O.guided_playouts(np.zeros((1, 8), np.uint16), 256, SEED, 0.1, Q.SEEDED_WEIGHTS, root_index_base=2, max_plies=16)
     assert abs(sim(eng, 0) - (float(o["wins_p0"][0]) - float(o["wins_p1"][0])) / 256) < 1e-12
     Cfg.rollout_eval_config = None
+
+
+def test_exchange_step_functions_at_world_size_one_and_two_gpus():
+    """quantik_b200.dist's global dedup and partitioned BFS.  With one process they must equal
+    the plain calls; when the box has >= 2 GPUs the real NCCL all-to-all runs under torchrun (scripts/multi_gpu_bfs.py)."""
+    import subprocess
+    import sys
+    import torch
+    from quantik_b200 import dist as D
+    rows = D.sharded_symmetry_table(7, device=0)
+    assert [list(map(int, r)) for r in B.symmetry_table(7)] == rows
+    pos = _random_positions(4096)
+    pos = pos[O.validate(pos)[1] == 0]
+    own, mult, n_global = D.sharded_canon_dedup(pos, None, device=0, sort_output=True)
+    u, um = B.canon_dedup(pos)
+    assert n_global == len(u) and np.array_equal(np.asarray(own), u) and np.array_equal(np.asarray(mult), um)
+    # owners partition the classes evenly enough to be useful
+    owners = D.owner_rank(u, 8).numpy()
+    assert np.bincount(owners, minlength=8).min() > len(u) // 16
+    if torch.cuda.device_count() >= 2:
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                              "--master-addr", "127.0.0.1", "--master-port", "29533",
+                              os.path.join(root, "scripts", "multi_gpu_bfs.py"), "9", "18"],
+                             capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0, out.stderr[-2000:]
+        rec = json.loads(out.stdout.strip().splitlines()[-1])
+        assert rec["bfs_matches_single_gpu"] and rec["dedup_matches_single_gpu"] and rec["n_gpus"] == 2

@@ -148,6 +148,39 @@ QK_API int qk_book_level(const uint16_t *states, size_t n, int color_swap, uint1
                          uint64_t *uniq_indegree, size_t cap, size_t *n_uniq, uint64_t *stats,
                          int dev, void *stream);
 
+/* ---- the exchange step at N GPUs: merge fused with its all-to-all over peer memory ------------------
+ * The reference merges canonical states in ONE parent process (game_stats.py:487-505,
+ * examples/generate_opening_book.py:458-496).  At N GPUs equal payloads found by different ranks have to
+ * meet: every payload has an owner rank (a hash of the payload), and each rank owns an INBOX that its peers
+ * write into directly over NVLink -- the emit pass of the local merge stores each distinct class into the
+ * owner's inbox, so no separate collective moves the data.
+ *   inbox[r]      device pointer to rank r's inbox, mapped into THIS process (peer access, CUDA IPC, or
+ *                 torch symmetric memory; with world == 1 simply a local buffer) -- host array of `world`
+ *                 pointers.  An inbox is qk_inbox_bytes(world, slots_per_src) bytes: a header of per-source
+ *                 counts and one region of slots_per_src (payload, multiplicity) entries per source rank.
+ *   protocol      every rank: qk_*_scatter (returns after its peer stores are complete)  ->  a barrier among
+ *                 the ranks (the caller's; e.g. an NCCL all-reduce)  ->  qk_inbox_merge on the own inbox.
+ *                 A rank may scatter into an inbox again only after its owner merged it (use two inboxes
+ *                 alternately when levels follow each other without a second barrier).
+ * qk_canon_dedup_scatter : qk_canon_dedup's canonicalise + local merge, then scatter.  flags bit 0 = 384-image
+ *                 mode.  sent (host, `world` values, may be NULL) = entries written per destination.
+ * qk_bfs_level_scatter   : qk_bfs_level's expand + canonicalise + local merge (table sized for local_cap
+ *                 distinct children), then scatter.  stats as qk_bfs_level.
+ * qk_inbox_merge : merge the regions of the own inbox (payloads are canonical already) into uniq / uniq_mult
+ *                 (capacity cap + 1; table order unless sort_output), *n_uniq = count.
+ * QK_E_NOMEM: a region, the local table, or cap was too small (nothing useful was delivered: repeat the level
+ * with larger sizes on EVERY rank).  world <= QK_MAX_WORLD.  All three are synchronous.                      */
+#define QK_MAX_WORLD 16
+QK_API int qk_inbox_bytes(int world, size_t slots_per_src, size_t *bytes);
+QK_API int qk_canon_dedup_scatter(const uint16_t *states, const uint64_t *mult, size_t n, int flags,
+                                  void *const *inbox, int world, int rank, size_t slots_per_src,
+                                  uint64_t *sent, int dev, void *stream);
+QK_API int qk_bfs_level_scatter(const uint16_t *states, const uint64_t *mult, size_t n, int flags, size_t local_cap,
+                                void *const *inbox, int world, int rank, size_t slots_per_src,
+                                uint64_t *stats, uint64_t *sent, int dev, void *stream);
+QK_API int qk_inbox_merge(const void *my_inbox, int world, size_t slots_per_src, int sort_output,
+                          uint16_t *uniq, uint64_t *uniq_mult, size_t cap, size_t *n_uniq, int dev, void *stream);
+
 /* ---- random playouts ---------------------------------------------------------------
  * qk_playouts       <- BeamSearchEngine._rollout/_default_evaluate (beam_search.py:614-645)
  *                      when max_plies < 0 (play to a true terminal; result +-1), and

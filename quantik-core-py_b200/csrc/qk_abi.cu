@@ -336,6 +336,75 @@ int qk_book_level(const uint16_t *states, size_t n, int color_swap, uint16_t *un
     return call.finish();
 }
 
+static int make_peers(void *const *inbox, int world, int rank, size_t slots_per_src, Peers &p)
+{
+    QK_REQUIRE(inbox, "inbox pointer array is NULL");
+    QK_REQUIRE(world >= 1 && world <= QK_MAX_WORLD, "world must be 1..QK_MAX_WORLD");
+    QK_REQUIRE(rank >= 0 && rank < world, "rank out of range");
+    QK_REQUIRE(slots_per_src > 0, "slots_per_src must be positive");
+    for (int r = 0; r < QK_MAX_WORLD; ++r) p.inbox[r] = r < world ? inbox[r] : nullptr;
+    for (int r = 0; r < world; ++r) QK_REQUIRE(inbox[r], "an inbox pointer is NULL");
+    p.world = world; p.rank = rank; p.slots_per_src = slots_per_src;
+    return QK_OK;
+}
+
+int qk_inbox_bytes(int world, size_t slots_per_src, size_t *bytes)
+{
+    QK_REQUIRE(bytes, "qk_inbox_bytes: bytes is NULL");
+    QK_REQUIRE(world >= 1 && world <= QK_MAX_WORLD, "world must be 1..QK_MAX_WORLD");
+    *bytes = inbox_bytes(world, slots_per_src);
+    return QK_OK;
+}
+
+int qk_canon_dedup_scatter(const uint16_t *states, const uint64_t *mult, size_t n, int flags, void *const *inbox, int world,
+                           int rank, size_t slots_per_src, uint64_t *sent, int dev, void *stream)
+{
+    QK_REQUIRE(states || n == 0, "qk_canon_dedup_scatter: states is NULL");
+    Peers peers;
+    int rc = make_peers(inbox, world, rank, slots_per_src, peers);
+    if (rc != QK_OK) return rc;
+    QK_BEGIN(call);
+    const uint4 *d_states = (const uint4 *)call.in(states, n * 16);
+    const uint64_t *d_mult = (const uint64_t *)call.in(mult, n * 8);
+    QK_CHECK(call);
+    rc = run_dedup_scatter(call, d_states, d_mult, n, flags, peers, sent);      // n == 0 still publishes zero counts
+    if (rc != QK_OK) return rc;
+    return call.finish();
+}
+
+int qk_bfs_level_scatter(const uint16_t *states, const uint64_t *mult, size_t n, int flags, size_t local_cap,
+                         void *const *inbox, int world, int rank, size_t slots_per_src, uint64_t *stats, uint64_t *sent,
+                         int dev, void *stream)
+{
+    QK_REQUIRE(stats, "qk_bfs_level_scatter: stats is NULL");
+    QK_REQUIRE(states || n == 0, "qk_bfs_level_scatter: states is NULL");
+    QK_REQUIRE(local_cap > 0, "qk_bfs_level_scatter: local_cap must be positive");
+    for (int i = 0; i < 5; ++i) stats[i] = 0;
+    Peers peers;
+    int rc = make_peers(inbox, world, rank, slots_per_src, peers);
+    if (rc != QK_OK) return rc;
+    QK_BEGIN(call);
+    const uint4 *d_states = (const uint4 *)call.in(states, n * 16);
+    const uint64_t *d_mult = (const uint64_t *)call.in(mult, n * 8);
+    QK_CHECK(call);
+    rc = run_bfs_level_scatter(call, d_states, d_mult, n, flags, local_cap, peers, stats, sent);
+    if (rc != QK_OK) return rc;
+    return call.finish();
+}
+
+int qk_inbox_merge(const void *my_inbox, int world, size_t slots_per_src, int sort_output, uint16_t *uniq, uint64_t *uniq_mult,
+                   size_t cap, size_t *n_uniq, int dev, void *stream)
+{
+    QK_REQUIRE(my_inbox && n_uniq && uniq && uniq_mult, "qk_inbox_merge: NULL argument");
+    QK_REQUIRE(world >= 1 && world <= QK_MAX_WORLD, "world must be 1..QK_MAX_WORLD");
+    QK_REQUIRE(slots_per_src > 0 && cap > 0, "qk_inbox_merge: slots_per_src and cap must be positive");
+    *n_uniq = 0;
+    QK_BEGIN(call);
+    int rc = run_inbox_merge(call, my_inbox, world, slots_per_src, sort_output, uniq, uniq_mult, cap, n_uniq);
+    if (rc != QK_OK) return rc;
+    return call.finish();
+}
+
 int qk_playouts_ex(const uint16_t *roots, size_t n_roots, uint32_t rollouts_per_root, uint64_t seed,
                    uint64_t first_rollout, uint32_t root_index_base, int max_plies, uint32_t *wins_p0,
                    uint32_t *wins_p1, uint32_t *draws, int8_t *per_playout, uint8_t *per_plies, int dev, void *stream)

@@ -85,6 +85,13 @@ int run_bfs_level(Call &call, const uint4 *parents, const uint64_t *mult, size_t
                   uint16_t *uniq, uint64_t *uniq_mult, size_t cap, size_t *n_uniq, uint64_t *h_stats);
 int run_book_level(Call &call, const uint4 *parents, size_t n, int color_swap, uint16_t *uniq, uint64_t *uniq_mult,
                    size_t cap, size_t *n_uniq, uint64_t *h_stats);
+struct Peers { void *inbox[QK_MAX_WORLD]; int world; int rank; size_t slots_per_src; };
+size_t inbox_bytes(int world, size_t slots_per_src);
+int run_dedup_scatter(Call &call, const uint4 *states, const uint64_t *mult, size_t n, int flags, const Peers &peers, uint64_t *h_sent);
+int run_bfs_level_scatter(Call &call, const uint4 *parents, const uint64_t *mult, size_t n, int flags, size_t local_cap,
+                          const Peers &peers, uint64_t *h_stats, uint64_t *h_sent);
+int run_inbox_merge(Call &call, const void *my_inbox, int world, size_t slots_per_src, int sort_output,
+                    uint16_t *uniq, uint64_t *uniq_mult, size_t cap, size_t *n_uniq);
 int launch_eval_features(const uint4 *states, const uint8_t *player, size_t n, double *features, Ctx *c, cudaStream_t s);
 int launch_playouts_guided(const uint4 *roots, size_t n_roots, uint32_t rollouts, uint64_t seed, uint64_t first_rollout,
                            uint32_t root_index_base, int max_plies, double epsilon, const double *weights, uint32_t *wins_p0,

@@ -480,6 +480,220 @@ int run_bfs_level(Call &call, const uint4 *parents, const uint64_t *mult, size_t
     return dedup_finish(call, t, uniq, uniq_mult, cap, n_uniq, h_stats, "qk_bfs_level", sort_output != 0);
 }
 
+// ------------------------------------------------------------------ exchange step over peer memory
+// Inbox of one rank: [0, 128) u64 counts[source] | Slot keys[world][slots_per_src] | u64 mults[world][slots_per_src]
+struct InboxView { u64 *counts; Slot *keys; u64 *mults; };
+static constexpr size_t kInboxHeader = 128;
+
+size_t inbox_bytes(int world, size_t slots_per_src)
+{
+    return kInboxHeader + (size_t)world * slots_per_src * (sizeof(Slot) + sizeof(u64));
+}
+__host__ __device__ __forceinline__ InboxView inbox_view(void *base, int world, size_t slots_per_src)
+{
+    char *b = (char *)base;
+    InboxView v = { (u64 *)b, (Slot *)(b + kInboxHeader), (u64 *)(b + kInboxHeader + (size_t)world * slots_per_src * sizeof(Slot)) };
+    return v;
+}
+// owner rank of a canonical payload: high bits of a second mix, so it is independent of the slot index bits
+__device__ __forceinline__ int owner_of(u64 hi, u64 lo, int world)
+{
+    return (int)__umulhi((uint32_t)(mix(lo, hi) >> 32), (uint32_t)world);
+}
+
+// local table -> the owners' inboxes.  Per 256 slots a block counts its entries per destination in shared
+// memory, reserves one range per destination in the SOURCE-side cursor (regions are per source, so no remote
+// atomics), then every thread stores its (key, multiplicity) straight into the peer's memory.
+__global__ void __launch_bounds__(kBlock) k_dedup_scatter(const Slot *table, const u64 *counts, size_t slots, Peers p,
+                                                           u64 *cursor, int *overflow)
+{
+    __shared__ unsigned s_cnt[QK_MAX_WORLD];
+    __shared__ u64 s_base[QK_MAX_WORLD];
+    const size_t stride = (size_t)gridDim.x * kBlock;
+    const size_t rounds = (slots + stride - 1) / stride;
+    for (size_t round = 0; round < rounds; ++round) {
+        const size_t i = round * stride + blockIdx.x * (size_t)kBlock + threadIdx.x;
+        if (threadIdx.x < QK_MAX_WORLD) s_cnt[threadIdx.x] = 0;
+        __syncthreads();
+        Slot k = { ~0ull, ~0ull };
+        if (i < slots) k = table[i];
+        const bool have = !(k.hi == ~0ull && k.lo == ~0ull);
+        int dst = 0;
+        unsigned r = 0;
+        u64 m = 0;
+        if (have) {
+            m = counts[i];
+            dst = owner_of(k.hi, k.lo, p.world);
+            r = atomicAdd(&s_cnt[dst], 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x < (unsigned)p.world && s_cnt[threadIdx.x])
+            s_base[threadIdx.x] = atomicAdd(cursor + threadIdx.x, (u64)s_cnt[threadIdx.x]);
+        __syncthreads();
+        if (have) {
+            const u64 pos = s_base[dst] + r;
+            if (pos < p.slots_per_src) {
+                const InboxView v = inbox_view(p.inbox[dst], p.world, p.slots_per_src);
+                const size_t at = (size_t)p.rank * p.slots_per_src + pos;
+                v.keys[at] = k;
+                v.mults[at] = m;
+            } else {
+                *overflow = 1;
+            }
+        }
+    }
+}
+
+// after the scatter: the all-ones payload (kept outside the table) joins its owner's region, and every
+// destination learns how many entries this source wrote
+__global__ void k_scatter_publish(Peers p, u64 *cursor, u64 all_ones_mult)
+{
+    const int dst = (int)threadIdx.x;
+    if (dst >= p.world) return;
+    const InboxView v = inbox_view(p.inbox[dst], p.world, p.slots_per_src);
+    u64 n = cursor[dst];
+    if (all_ones_mult && owner_of(~0ull, ~0ull, p.world) == dst) {
+        if (n < p.slots_per_src) {
+            const size_t at = (size_t)p.rank * p.slots_per_src + n;
+            v.keys[at].hi = ~0ull; v.keys[at].lo = ~0ull;
+            v.mults[at] = all_ones_mult;
+        }
+        ++n;
+        cursor[dst] = n;
+    }
+    v.counts[p.rank] = n;
+}
+
+// the owner's side: entries of one inbox region (canonical already) into the merge table
+__global__ void __launch_bounds__(kBlock) k_inbox_insert(const Slot *keys, const u64 *mults, size_t n, Slot *table, u64 *counts,
+                                                          size_t slot_mask, u64 *n_unique, u64 *all_ones_count, int *overflow,
+                                                          u64 max_unique)
+{
+    for (size_t i = blockIdx.x * (size_t)kBlock + threadIdx.x; i < n; i += (size_t)gridDim.x * kBlock) {
+        if (*reinterpret_cast<volatile int *>(overflow)) break;
+        const Slot key = keys[i];
+        const u64 hi = key.hi, lo = key.lo, m = mults[i];
+        if ((hi & lo) == ~0ull) { atomicAdd(all_ones_count, m); continue; }
+        size_t slot = (size_t)mix(hi, lo) & slot_mask;
+        for (size_t probe = 0; probe <= slot_mask; ++probe, slot = (slot + 1) & slot_mask) {
+            const ulonglong2 raw = __ldcv(reinterpret_cast<const ulonglong2 *>(table + slot));
+            u64 khi = raw.x, klo = raw.y;
+            if (khi == ~0ull || klo == ~0ull) {
+                cas128(table + slot, ~0ull, ~0ull, hi, lo, khi, klo);
+                if (khi == ~0ull && klo == ~0ull) {
+                    if (atomicAdd(n_unique, 1ull) >= max_unique) *overflow = 1;
+                    khi = hi; klo = lo;
+                }
+            }
+            if (khi == hi && klo == lo) { atomicAdd(counts + slot, m); break; }
+        }
+    }
+}
+
+// local table -> peers; h_stats (5 x u64, may be null), h_sent (world x u64, may be null)
+static int scatter_finish(Call &call, DedupTable &t, const Peers &peers, uint64_t *h_stats, uint64_t *h_sent, const char *who)
+{
+    cudaStream_t s = call.stream();
+    Ctx *c = call.ctx();
+    u64 h_meta[10];
+    QK_CUDA(cudaMemcpyAsync(h_meta, t.meta, sizeof h_meta, cudaMemcpyDeviceToHost, s));
+    QK_CUDA(cudaStreamSynchronize(s));
+    if (h_stats) for (int i = 0; i < 5; ++i) h_stats[i] = h_meta[4 + i];
+    if ((int)h_meta[3] != 0) {
+        set_error(std::string(who) + ": more distinct canonical states than the local table holds");
+        return QK_E_NOMEM;
+    }
+    u64 *cursor = (u64 *)call.temp((QK_MAX_WORLD + 1) * sizeof(u64), true);     // [QK_MAX_WORLD] = overflow flag
+    if (!cursor) return call.status();
+    int *overflow = (int *)(cursor + QK_MAX_WORLD);
+    k_dedup_scatter<<<grid_for(t.slots, kBlock, c->sms, 8), kBlock, 0, s>>>(t.table, t.counts, t.slots, peers, cursor, overflow);
+    k_scatter_publish<<<1, 32, 0, s>>>(peers, cursor, h_meta[1]);
+    QK_CUDA(cudaGetLastError());
+    u64 h_cursor[QK_MAX_WORLD + 1];
+    QK_CUDA(cudaMemcpyAsync(h_cursor, cursor, sizeof h_cursor, cudaMemcpyDeviceToHost, s));
+    QK_CUDA(cudaStreamSynchronize(s));                                          // peer stores are complete here
+    bool too_small = (int)h_cursor[QK_MAX_WORLD] != 0;
+    for (int r = 0; r < peers.world; ++r) {
+        if (h_sent) h_sent[r] = h_cursor[r];
+        too_small |= h_cursor[r] > peers.slots_per_src;
+    }
+    if (too_small) {
+        set_error(std::string(who) + ": an inbox region (slots_per_src) is too small for this rank's share");
+        return QK_E_NOMEM;
+    }
+    return QK_OK;
+}
+
+int run_dedup_scatter(Call &call, const uint4 *states, const uint64_t *mult, size_t n, int flags, const Peers &peers, uint64_t *h_sent)
+{
+    cudaStream_t s = call.stream();
+    Ctx *c = call.ctx();
+    DedupTable t;
+    int rc = dedup_begin(call, n, t);
+    if (rc != QK_OK) return rc;
+    if (n) {
+        if (flags & 1)
+            k_dedup_insert<true><<<grid_for(n, kBlock, c->sms, 8), kBlock, 0, s>>>(states, (const u64 *)mult, n, t.table, t.counts, t.slots - 1,
+                                                                                 t.meta, t.meta + 1, (int *)(t.meta + 3), t.max_unique);
+        else
+            k_dedup_insert<false><<<grid_for(n, kBlock, c->sms, 8), kBlock, 0, s>>>(states, (const u64 *)mult, n, t.table, t.counts, t.slots - 1,
+                                                                                  t.meta, t.meta + 1, (int *)(t.meta + 3), t.max_unique);
+        QK_CUDA(cudaGetLastError());
+    }
+    return scatter_finish(call, t, peers, nullptr, h_sent, "qk_canon_dedup_scatter");
+}
+
+int run_bfs_level_scatter(Call &call, const uint4 *parents, const uint64_t *mult, size_t n, int flags, size_t local_cap,
+                          const Peers &peers, uint64_t *h_stats, uint64_t *h_sent)
+{
+    cudaStream_t s = call.stream();
+    Ctx *c = call.ctx();
+    DedupTable t;
+    int rc = dedup_begin(call, local_cap, t);
+    if (rc != QK_OK) return rc;
+    if (n) {
+        const unsigned grid = grid_for(n, kBlock, c->sms, 5);
+        if (flags & 1)
+            k_bfs_expand_insert<true><<<grid, kBlock, 0, s>>>(parents, (const u64 *)mult, n, t.table, t.counts, t.slots - 1, t.meta, t.meta + 1,
+                                                             (int *)(t.meta + 3), t.max_unique, t.meta + 4);
+        else
+            k_bfs_expand_insert<false><<<grid, kBlock, 0, s>>>(parents, (const u64 *)mult, n, t.table, t.counts, t.slots - 1, t.meta, t.meta + 1,
+                                                              (int *)(t.meta + 3), t.max_unique, t.meta + 4);
+        QK_CUDA(cudaGetLastError());
+    }
+    return scatter_finish(call, t, peers, h_stats, h_sent, "qk_bfs_level_scatter");
+}
+
+int run_inbox_merge(Call &call, const void *my_inbox, int world, size_t slots_per_src, int sort_output,
+                    uint16_t *uniq, uint64_t *uniq_mult, size_t cap, size_t *n_uniq)
+{
+    cudaStream_t s = call.stream();
+    Ctx *c = call.ctx();
+    const InboxView v = inbox_view(const_cast<void *>(my_inbox), world, slots_per_src);
+    u64 h_counts[QK_MAX_WORLD];
+    QK_CUDA(cudaMemcpyAsync(h_counts, v.counts, world * sizeof(u64), cudaMemcpyDeviceToHost, s));
+    QK_CUDA(cudaStreamSynchronize(s));
+    size_t total = 0;
+    for (int r = 0; r < world; ++r) {
+        if (h_counts[r] > slots_per_src) {
+            set_error("qk_inbox_merge: source rank " + std::to_string(r) + " overflowed its region");
+            return QK_E_NOMEM;
+        }
+        total += (size_t)h_counts[r];
+    }
+    DedupTable t;
+    int rc = dedup_begin(call, total < cap ? total : cap, t);
+    if (rc != QK_OK) return rc;
+    for (int r = 0; r < world; ++r) {
+        if (!h_counts[r]) continue;
+        k_inbox_insert<<<grid_for((size_t)h_counts[r], kBlock, c->sms, 8), kBlock, 0, s>>>(
+            v.keys + (size_t)r * slots_per_src, v.mults + (size_t)r * slots_per_src, (size_t)h_counts[r], t.table, t.counts, t.slots - 1,
+            t.meta, t.meta + 1, (int *)(t.meta + 3), t.max_unique);
+    }
+    QK_CUDA(cudaGetLastError());
+    return dedup_finish(call, t, uniq, uniq_mult, cap, n_uniq, nullptr, "qk_inbox_merge", sort_output != 0);
+}
+
 int run_book_level(Call &call, const uint4 *parents, size_t n, int color_swap, uint16_t *uniq, uint64_t *uniq_mult,
                    size_t cap, size_t *n_uniq, uint64_t *h_stats)
 {

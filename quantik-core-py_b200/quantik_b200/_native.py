@@ -46,6 +46,13 @@ PROTOTYPES = {
                              c_void_p, c_int, c_void_p]),
     "qk_book_level": (c_int, [c_void_p, c_size_t, c_int, c_void_p, c_void_p, c_size_t, POINTER(c_size_t), c_void_p,
                               c_int, c_void_p]),
+    "qk_inbox_bytes": (c_int, [c_int, c_size_t, POINTER(c_size_t)]),
+    "qk_canon_dedup_scatter": (c_int, [c_void_p, c_void_p, c_size_t, c_int, POINTER(c_void_p), c_int, c_int, c_size_t,
+                                       c_void_p, c_int, c_void_p]),
+    "qk_bfs_level_scatter": (c_int, [c_void_p, c_void_p, c_size_t, c_int, c_size_t, POINTER(c_void_p), c_int, c_int,
+                                     c_size_t, c_void_p, c_void_p, c_int, c_void_p]),
+    "qk_inbox_merge": (c_int, [c_void_p, c_int, c_size_t, c_int, c_void_p, c_void_p, c_size_t, POINTER(c_size_t),
+                               c_int, c_void_p]),
     "qk_playouts": (c_int, [c_void_p, c_size_t, c_uint32, c_uint64, c_int, c_void_p, c_void_p, c_void_p,
                             c_void_p, c_int, c_void_p]),
     "qk_playouts_ex": (c_int, [c_void_p, c_size_t, c_uint32, c_uint64, c_uint64, c_uint32, c_int, c_void_p,

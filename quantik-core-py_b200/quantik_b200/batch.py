@@ -253,6 +253,61 @@ def symmetry_table(max_depth: int, device: Optional[int] = None, on_device: bool
     return rows
 
 
+# ----------------------------------------------------------------------------- exchange step over peer memory
+def inbox_bytes(world: int, slots_per_src: int) -> int:
+    """Size of one rank's inbox (qk_inbox_bytes)."""
+    b = ctypes.c_size_t(0)
+    N.check(N.load().qk_inbox_bytes(int(world), int(slots_per_src), ctypes.byref(b)))
+    return int(b.value)
+
+
+def _ptr_array(ptrs):
+    return (ctypes.c_void_p * len(ptrs))(*[int(p) for p in ptrs])
+
+
+def canon_dedup_scatter(states, mult, inbox_ptrs, rank: int, slots_per_src: int, color_swap: bool = False,
+                        device: Optional[int] = None) -> np.ndarray:
+    """Canonicalise + merge locally, then store every distinct class into its owner's inbox over peer memory
+    (qk_canon_dedup_scatter).  -> entries written per destination rank."""
+    s, on_dev, d = _states_in(states)
+    d = _dev(device, on_dev, d)
+    lib = N.init(d)
+    m = _aux_in(mult, np.uint64, on_dev, d)
+    sent = np.zeros(len(inbox_ptrs), np.uint64)
+    N.check(lib.qk_canon_dedup_scatter(s.ptr, m.ptr, s.n, int(bool(color_swap)), _ptr_array(inbox_ptrs), len(inbox_ptrs),
+                                       int(rank), int(slots_per_src), sent.ctypes.data, d, _stream(on_dev, d)))
+    return sent
+
+
+def bfs_level_scatter(states, mult, inbox_ptrs, rank: int, slots_per_src: int, local_cap: int, color_swap: bool = False,
+                      device: Optional[int] = None):
+    """One BFS depth of this rank's share of the frontier, children delivered to their owners' inboxes
+    (qk_bfs_level_scatter).  -> (stats dict, entries written per destination)."""
+    s, on_dev, d = _states_in(states)
+    d = _dev(device, on_dev, d)
+    lib = N.init(d)
+    m = _aux_in(mult, np.uint64, on_dev, d)
+    sent = np.zeros(len(inbox_ptrs), np.uint64)
+    stats = np.zeros(5, np.uint64)
+    N.check(lib.qk_bfs_level_scatter(s.ptr, m.ptr, s.n, int(bool(color_swap)), int(local_cap), _ptr_array(inbox_ptrs),
+                                     len(inbox_ptrs), int(rank), int(slots_per_src), stats.ctypes.data, sent.ctypes.data,
+                                     d, _stream(on_dev, d)))
+    names = ["total_moves", "line_wins_p0", "line_wins_p1", "blocked_p0", "blocked_p1"]
+    return {k: int(v) for k, v in zip(names, stats)}, sent
+
+
+def inbox_merge(inbox_ptr: int, world: int, slots_per_src: int, cap: int, device: int = 0, sort_output: bool = False):
+    """Merge what the peers delivered into this rank's inbox (qk_inbox_merge; call after a barrier).
+    -> (payloads (U, 8) int16 CUDA tensor, multiplicities (U,) int64 CUDA tensor)."""
+    lib = N.init(device)
+    uniq = _out((cap + 1, 8), np.uint16, True, device)
+    um = _out((cap + 1,), np.uint64, True, device)
+    nu = ctypes.c_size_t(0)
+    N.check(lib.qk_inbox_merge(ctypes.c_void_p(int(inbox_ptr)), int(world), int(slots_per_src), int(bool(sort_output)),
+                               uniq.ptr, um.ptr, int(cap), ctypes.byref(nu), device, _stream(True, device)))
+    return uniq.obj[:nu.value], um.obj[:nu.value]
+
+
 def book_level(states, color_swap: bool = False, cap: int = 1 << 20, device: Optional[int] = None):
     """One depth of the opening-book BFS (examples/generate_opening_book.py:185-280): finished classes are
     terminal and not expanded, every other class contributes its distinct canonical children.

@@ -231,3 +231,138 @@ def sharded_symmetry_table(max_depth: int, device: Optional[int] = None, group=N
         tot = all_reduce_counts(stats, d, group)
         rows.append([int(tot[0]), int(tot[5]), int(tot[1] + tot[4]), int(tot[2] + tot[3]), int(tot[6])])
     return rows
+
+
+# ----------------------------------------------------------------------------- the exchange fused into the merge
+# Same two jobs as above, but the all-to-all is not a separate collective: the emit pass of the local merge
+# stores every distinct class straight into its owner's INBOX over NVLink (include/quantik_b200.h,
+# qk_*_scatter / qk_inbox_merge).  torch symmetric memory only provides the peer mapping of the inboxes;
+# one small all-reduce per step is both the barrier of the protocol and the "did every region fit" vote.
+class PeerInboxes:
+    """`copies` inboxes per rank (alternate them between consecutive steps), each mapped into every peer."""
+
+    def __init__(self, slots_per_src: int, device: int, group=None, copies: int = 2):
+        self.device, self.group, self.copies = int(device), group, copies
+        self.rank, self.world = _world(group)
+        self.slots_per_src = 0
+        self.bufs, self.ptrs = [], []
+        self.ensure(slots_per_src)
+
+    def ensure(self, slots_per_src: int) -> None:
+        """Collective: (re)allocate when the regions are smaller than `slots_per_src` (same value on every rank)."""
+        import torch
+        if slots_per_src <= self.slots_per_src:
+            return
+        self.bufs, self.ptrs = [], []
+        self.slots_per_src = int(slots_per_src)
+        nbytes = B.inbox_bytes(self.world, self.slots_per_src)
+        for _ in range(self.copies):
+            if self.world == 1:
+                t = torch.empty(nbytes, dtype=torch.uint8, device=f"cuda:{self.device}")
+                ptrs = [t.data_ptr()]
+            else:
+                import torch.distributed as dist
+                import torch.distributed._symmetric_memory as symm_mem
+                t = symm_mem.empty(nbytes, dtype=torch.uint8, device=f"cuda:{self.device}")
+                h = symm_mem.rendezvous(t, group=self.group if self.group is not None else dist.group.WORLD)
+                ptrs = [int(p) for p in h.buffer_ptrs]
+            self.bufs.append(t)
+            self.ptrs.append(ptrs)
+
+    def received(self, k: int) -> int:
+        """Entries the peers wrote into my inbox k (its header; valid after the barrier)."""
+        import torch
+        return int(self.bufs[k][: 8 * self.world].view(torch.int64).sum().item())
+
+
+def _vote(failed: bool, device: int, group=None) -> bool:
+    """All-reduce(max) of a flag: the barrier between scatter and merge, and the agreement to retry."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return failed
+    t = torch.tensor([int(failed)], dtype=torch.int32, device=f"cuda:{device}")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    return bool(t.item())
+
+
+def _max_over_ranks(value: int, device: int, group=None) -> int:
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return int(value)
+    t = torch.tensor([int(value)], dtype=torch.int64, device=f"cuda:{device}")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    return int(t.item())
+
+
+def fused_canon_dedup(states, mult=None, color_swap: bool = False, device: int = 0, group=None,
+                      inboxes: Optional[PeerInboxes] = None, sort_output: bool = False):
+    """sharded_canon_dedup with the exchange fused into the merge (GPU only).  Same return value."""
+    from ._native import QuantikB200Error
+    rank, world = _world(group)
+    n = len(states)
+    want = _max_over_ranks(int(1.25 * n / world) + 4096, device, group)     # every local state distinct, evenly owned
+    if inboxes is None:
+        inboxes = PeerInboxes(want, device, group, copies=1)
+    inboxes.ensure(want)
+    while True:
+        failed = False
+        try:
+            B.canon_dedup_scatter(states, mult, inboxes.ptrs[0], rank, inboxes.slots_per_src, color_swap=color_swap, device=device)
+        except QuantikB200Error as e:
+            if e.code != -4:
+                raise
+            failed = True
+        if not _vote(failed, device, group):
+            break
+        inboxes.ensure(2 * inboxes.slots_per_src)
+    got = inboxes.received(0)
+    mine, mm = B.inbox_merge(inboxes.ptrs[0][rank], world, inboxes.slots_per_src, max(got, 1), device=device, sort_output=sort_output)
+    total = all_reduce_counts(np.array([int(mine.shape[0])], np.int64), device, group)
+    return mine, mm, int(total[0])
+
+
+def fused_symmetry_table(max_depth: int, device: int = 0, group=None, inboxes: Optional[PeerInboxes] = None):
+    """sharded_symmetry_table with the per-depth exchange fused into the expansion's merge: per depth one
+    qk_bfs_level_scatter, one vote (the barrier), one qk_inbox_merge; the counters are all-reduced once at the end."""
+    import torch
+    from ._native import QuantikB200Error
+    rank, world = _world(group)
+    d = int(device)
+    if inboxes is None:
+        inboxes = PeerInboxes(1 << 14, d, group, copies=2)
+    # the empty board belongs to whoever owns it under the library's hash: let the merge decide -- rank 0 scatters it
+    frontier = torch.zeros((1 if rank == 0 else 0, 8), dtype=torch.int16, device=f"cuda:{d}")
+    mult = torch.ones(1 if rank == 0 else 0, dtype=torch.int64, device=f"cuda:{d}")
+    B.canon_dedup_scatter(frontier, mult, inboxes.ptrs[1], rank, inboxes.slots_per_src, device=d)
+    _vote(False, d, group)
+    frontier, mult = B.inbox_merge(inboxes.ptrs[1][rank], world, inboxes.slots_per_src, 1, device=d)
+    levels = np.zeros((max_depth, 7), np.int64)
+    growth = 64.0
+    for depth in range(1, max_depth + 1):
+        k = depth % 2
+        n = int(frontier.shape[0])
+        local_cap = int(min(64 * max(n, 1), max(1 << 12, 1.6 * growth * n)))
+        want = _max_over_ranks(int(1.25 * local_cap / 1.6 / world) + 4096, d, group)
+        inboxes.ensure(want)
+        while True:
+            failed = False
+            try:
+                st, sent = B.bfs_level_scatter(frontier, mult, inboxes.ptrs[k], rank, inboxes.slots_per_src, local_cap, device=d)
+            except QuantikB200Error as e:
+                if e.code != -4:
+                    raise
+                failed = True
+            if not _vote(failed, d, group):
+                break
+            local_cap *= 2                      # whichever of the two was short, on whichever rank
+            inboxes.ensure(2 * inboxes.slots_per_src)
+        growth = max(0.05, float(sent.sum()) / max(n, 1))
+        got = inboxes.received(k)
+        frontier, mult = B.inbox_merge(inboxes.ptrs[k][rank], world, inboxes.slots_per_src, max(got, 1), device=d)
+        levels[depth - 1, :5] = [st["total_moves"], st["line_wins_p0"], st["line_wins_p1"], st["blocked_p0"], st["blocked_p1"]]
+        levels[depth - 1, 5] = int(frontier.shape[0])
+        levels[depth - 1, 6] = int(mult.sum()) if len(mult) else 0
+    tot = all_reduce_counts(levels, d, group)
+    return [[int(t[0]), int(t[5]), int(t[1] + t[4]), int(t[2] + t[3]), int(t[6])] for t in tot]

@@ -41,6 +41,12 @@ def timed(fn):
 
 D.sharded_symmetry_table(6, device=local)                       # warm-up: context, pool, NCCL channels
 rows, t_bfs = timed(lambda: D.sharded_symmetry_table(depth, device=local))
+# the same with the exchange fused into the merge kernels (peer stores into the owners' inboxes)
+boxes = D.PeerInboxes(1 << 14, local, copies=2)
+D.fused_symmetry_table(6, device=local, inboxes=boxes)
+D.fused_symmetry_table(depth, device=local, inboxes=boxes)      # sizes the inboxes for the deepest level
+fused_rows, t_bfs_fused = timed(lambda: D.fused_symmetry_table(depth, device=local, inboxes=boxes))
+del boxes
 
 # config 3 scaled: every rank draws 2^log2n mid-game positions (its own index range of the root stream), and
 # pushes each through a pseudo-random symmetry so that equal classes are spread over all ranks
@@ -54,6 +60,10 @@ images = Q.apply_symmetry(roots, codes, device=local)
 dev_images = torch.from_numpy(np.ascontiguousarray(images).view(np.int16)).to(f"cuda:{local}")
 (own, own_mult, n_global), t_dedup = timed(lambda: D.sharded_canon_dedup(dev_images, None, device=local))
 mass = D.all_reduce_counts(np.array([int(own_mult.sum())], np.int64), local)
+dbox = D.PeerInboxes(int(1.25 * n / world) + 4096, local, copies=1)
+D.fused_canon_dedup(dev_images, None, device=local, inboxes=dbox)
+(f_own, f_mult, f_global), t_dedup_fused = timed(lambda: D.fused_canon_dedup(dev_images, None, device=local, inboxes=dbox))
+f_mass = D.all_reduce_counts(np.array([int(f_mult.sum())], np.int64), local)
 
 # single-GPU check on rank 0: gather every rank's inputs
 if world > 1:
@@ -70,7 +80,10 @@ if rank == 0:
                       "canonical_states_total": int(sum(r[1] for r in rows)),
                       "dedup_states": int(everything.shape[0]), "dedup_seconds": t_dedup,
                       "dedup_keys_per_s": int(everything.shape[0]) / t_dedup, "dedup_unique_global": n_global,
-                      "dedup_matches_single_gpu": n_global == int(u.shape[0]) and int(mass[0]) == int(everything.shape[0])}))
+                      "dedup_matches_single_gpu": n_global == int(u.shape[0]) and int(mass[0]) == int(everything.shape[0]),
+                      "fused_bfs_seconds": t_bfs_fused, "fused_bfs_matches_single_gpu": fused_rows == [list(map(int, r)) for r in one_rows],
+                      "fused_dedup_seconds": t_dedup_fused, "fused_dedup_keys_per_s": int(everything.shape[0]) / t_dedup_fused,
+                      "fused_dedup_matches_single_gpu": f_global == int(u.shape[0]) and int(f_mass[0]) == int(everything.shape[0])}))
 if world > 1:
     dist.barrier()
     dist.destroy_process_group()

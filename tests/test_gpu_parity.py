@@ -613,3 +613,55 @@ def test_exchange_step_functions_at_world_size_one_and_two_gpus():
         assert out.returncode == 0, out.stderr[-2000:]
         rec = json.loads(out.stdout.strip().splitlines()[-1])
         assert rec["bfs_matches_single_gpu"] and rec["dedup_matches_single_gpu"] and rec["n_gpus"] == 2
+        assert rec["fused_bfs_matches_single_gpu"] and rec["fused_dedup_matches_single_gpu"]      # peer-memory path
+
+
+def test_fused_exchange_with_emulated_ranks_on_one_gpu():
+    """qk_canon_dedup_scatter / qk_bfs_level_scatter / qk_inbox_merge with W ranks played by ONE GPU (every inbox
+    is a local buffer): the owners' shares must be disjoint and add up to the single-table result; a BFS run
+    through the inboxes must give the published table.  The real peer-memory run is scripts/multi_gpu_bfs.py."""
+    import torch
+    W, sps = 3, 40_000
+    nbytes = B.inbox_bytes(W, sps)
+    bufs = [torch.empty(nbytes, dtype=torch.uint8, device="cuda:0") for _ in range(W)]
+    ptrs = [b.data_ptr() for b in bufs]
+    pos = _random_positions(120_000, seed=99)[:60_000]
+    pos = np.concatenate([pos, np.full((5, 8), 0xFFFF, np.uint16)])          # the payload kept outside the tables
+    mult = np.random.default_rng(5).integers(1, 1000, len(pos)).astype(np.uint64)
+    sent = np.zeros((W, W), np.uint64)
+    for r, (s_, m_) in enumerate(zip(np.array_split(pos, W), np.array_split(mult, W))):
+        sent[r] = B.canon_dedup_scatter(s_, m_, ptrs, r, sps)
+    want_u, want_m = B.canon_dedup(pos, mult)
+    got_u, got_m = [], []
+    for r in range(W):
+        received = int(bufs[r][: 8 * W].view(torch.int64).sum().item())
+        assert received == int(sent[:, r].sum())
+        u, m = B.inbox_merge(ptrs[r], W, sps, max(received, 1), sort_output=True)
+        got_u.append(u.cpu().numpy().view(np.uint16)); got_m.append(m.cpu().numpy().view(np.uint64))
+    assert min(len(u) for u in got_u) > len(want_u) // (2 * W)                 # owners share the classes evenly
+    allu, allm = np.concatenate(got_u), np.concatenate(got_m)
+    assert len(allu) == len(want_u)                                            # disjoint shares
+    order = np.lexsort(allu.astype("<u2").view(np.uint8).reshape(-1, 16).T[::-1])
+    assert np.array_equal(allu[order], want_u) and np.array_equal(allm[order], want_m)
+    with pytest.raises(Q.QuantikB200Error):                                     # region too small -> QK_E_NOMEM
+        B.canon_dedup_scatter(pos, mult, ptrs, 0, 100)
+
+    # BFS through the inboxes: depth 1..6 from the empty board with W emulated ranks
+    sps = 400_000
+    bufs = [torch.empty(B.inbox_bytes(W, sps), dtype=torch.uint8, device="cuda:0") for _ in range(W)]
+    ptrs = [b.data_ptr() for b in bufs]
+    shards = [(np.zeros((1 if r == 0 else 0, 8), np.uint16), np.ones(1 if r == 0 else 0, np.uint64)) for r in range(W)]
+    rows = []
+    for depth in range(1, 7):
+        tot = np.zeros(5, np.int64)
+        for r, (f, m) in enumerate(shards):
+            st, _ = B.bfs_level_scatter(f, m, ptrs, r, sps, local_cap=max(4096, 40 * len(f)))
+            tot += np.array(list(st.values()), np.int64)
+        shards = []
+        for r in range(W):
+            received = int(bufs[r][: 8 * W].view(torch.int64).sum().item())
+            u, m = B.inbox_merge(ptrs[r], W, sps, max(received, 1))
+            shards.append((u.cpu().numpy().view(np.uint16), m.cpu().numpy().view(np.uint64)))
+        rows.append([int(tot[0]), sum(len(u) for u, _ in shards), int(tot[1] + tot[4]), int(tot[2] + tot[3]),
+                     int(sum(int(m.sum()) for _, m in shards))])
+    assert rows == [list(map(int, r)) for r in B.symmetry_table(6)]

@@ -18,8 +18,13 @@ static constexpr unsigned kBlock = 256;
 typedef unsigned long long u64;
 
 struct __align__(16) Slot { u64 hi, lo; };     // Key128 (a:b, c:d); all ones = empty
+// One table entry = one 32-byte sector: the key and its multiplicity travel together, so the probe's load,
+// the claim's CAS and the multiplicity's RED all hit the same sector (the table is far larger than L2 and the
+// probes are random: with the counts in a second array every insert cost two DRAM row activations).
+struct __align__(32) TSlot { u64 hi, lo, count, pad; };
+static constexpr size_t kMaxProbe = 8192;      // longer chains mean the table is as good as full
 
-__device__ __forceinline__ void cas128(Slot *addr, u64 cmp_hi, u64 cmp_lo, u64 new_hi, u64 new_lo, u64 &old_hi, u64 &old_lo)
+__device__ __forceinline__ void cas128(void *addr, u64 cmp_hi, u64 cmp_lo, u64 new_hi, u64 new_lo, u64 &old_hi, u64 &old_lo)
 {
     // memory layout of Slot is {hi, lo}; the b128 register packs {low 64 bits, high 64 bits}
     asm volatile(
@@ -42,18 +47,55 @@ __device__ __forceinline__ u64 mix(u64 h, u64 l)
     return x;
 }
 
-__global__ void __launch_bounds__(kBlock) k_dedup_fill(Slot *table, u64 *counts, size_t slots)
+__global__ void __launch_bounds__(kBlock) k_dedup_fill(TSlot *table, size_t slots)
 {
     for (size_t i = blockIdx.x * (size_t)kBlock + threadIdx.x; i < slots; i += (size_t)gridDim.x * kBlock) {
-        table[i].hi = ~0ull; table[i].lo = ~0ull; counts[i] = 0;
+        ulonglong4 e = { ~0ull, ~0ull, 0ull, 0ull };
+        *reinterpret_cast<ulonglong4 *>(table + i) = e;
+    }
+}
+
+// Adds multiplicity m to key (khi_new, klo_new), creating the entry when it is new.  -> true when THIS call
+// created it.  Distinct keys are counted by the callers in registers and added to the global counter once per
+// warp at the end of the kernel (flush_claims): a per-insert atomic on one address serialises in one L2 slice.
+__device__ __forceinline__ bool table_insert(TSlot *table, size_t slot_mask, u64 khi_new, u64 klo_new, u64 m,
+                                             u64 *all_ones_count, int *overflow)
+{
+    if ((khi_new & klo_new) == ~0ull) { atomicAdd(all_ones_count, m); return false; }   // the payload that equals the empty marker
+    size_t slot = (size_t)mix(khi_new, klo_new) & slot_mask;
+    const size_t max_probe = slot_mask < kMaxProbe ? slot_mask : kMaxProbe;
+    for (size_t probe = 0; probe <= max_probe; ++probe, slot = (slot + 1) & slot_mask) {
+        // fast path: one 128-bit load; a slot caught half-way through another thread's
+        // CAS can only look like "some half is all ones", which falls through to the CAS
+        const ulonglong2 raw = __ldcv(reinterpret_cast<const ulonglong2 *>(table + slot));
+        u64 khi = raw.x, klo = raw.y;
+        bool claimed = false;
+        if (khi == ~0ull || klo == ~0ull) {
+            cas128(table + slot, ~0ull, ~0ull, khi_new, klo_new, khi, klo);
+            if (khi == ~0ull && klo == ~0ull) { claimed = true; khi = khi_new; klo = klo_new; }
+        }
+        if (khi == khi_new && klo == klo_new) { atomicAdd(&table[slot].count, m); return claimed; }   // game_stats.py:487-505
+    }
+    *overflow = 1;      // no room within kMaxProbe slots: the host retries with a larger table
+    return false;
+}
+
+// every lane of the warp must call this (after its loops): one atomic per warp and kernel
+__device__ __forceinline__ void flush_claims(unsigned claims, u64 *n_unique, int *overflow, u64 max_unique)
+{
+    const unsigned total = __reduce_add_sync(0xFFFFFFFFu, claims);
+    if ((threadIdx.x & 31u) == 0 && total) {
+        const u64 before = atomicAdd(n_unique, (u64)total);
+        if (before + total > max_unique) *overflow = 1;
     }
 }
 
 template <bool COLOR_SWAP>
 __global__ void __launch_bounds__(kBlock) k_dedup_insert(const uint4 *__restrict__ states, const u64 *__restrict__ mult, size_t n,
-                                                          Slot *table, u64 *counts, size_t slot_mask,
+                                                          TSlot *table, size_t slot_mask,
                                                           u64 *n_unique, u64 *all_ones_count, int *overflow, u64 max_unique)
 {
+    unsigned claims = 0;
     for (size_t i = blockIdx.x * (size_t)kBlock + threadIdx.x; i < n; i += (size_t)gridDim.x * kBlock) {
         if (*reinterpret_cast<volatile int *>(overflow)) break;     // table too small: give up early
         uint4 v = __ldg(states + i);
@@ -62,48 +104,39 @@ __global__ void __launch_bounds__(kBlock) k_dedup_insert(const uint4 *__restrict
         // comparable big-endian limbs of the payload bytes
         u64 hi = ((u64)prmt(c.x, 0, 0x0123) << 32) | prmt(c.y, 0, 0x0123);
         u64 lo = ((u64)prmt(c.z, 0, 0x0123) << 32) | prmt(c.w, 0, 0x0123);
-        u64 m = mult ? mult[i] : 1ull;
-        if ((hi & lo) == ~0ull) { atomicAdd(all_ones_count, m); continue; }   // the one payload that equals the empty marker
-        size_t slot = (size_t)mix(hi, lo) & slot_mask;
-        for (size_t probe = 0; probe <= slot_mask; ++probe, slot = (slot + 1) & slot_mask) {
-            // fast path: one 128-bit load; a slot caught half-way through another thread's
-            // CAS can only look like "some half is all ones", which falls through to the CAS
-            const ulonglong2 raw = __ldcv(reinterpret_cast<const ulonglong2 *>(table + slot));
-            u64 khi = raw.x, klo = raw.y;
-            if (khi == ~0ull || klo == ~0ull) {
-                cas128(table + slot, ~0ull, ~0ull, hi, lo, khi, klo);
-                if (khi == ~0ull && klo == ~0ull) {            // we claimed the slot
-                    if (atomicAdd(n_unique, 1ull) >= max_unique) *overflow = 1;
-                    khi = hi; klo = lo;
-                }
-            }
-            if (khi == hi && klo == lo) { atomicAdd(counts + slot, m); break; }
-        }
+        claims += table_insert(table, slot_mask, hi, lo, mult ? mult[i] : 1ull, all_ones_count, overflow) ? 1u : 0u;
     }
+    flush_claims(claims, n_unique, overflow, max_unique);
 }
 
-__global__ void __launch_bounds__(kBlock) k_dedup_compact(const Slot *table, const u64 *counts, size_t slots,
-                                                           Slot *keys, u64 *mults, u64 *cursor)
+__device__ __forceinline__ TSlot load_entry(const TSlot *table, size_t i)
+{
+    const ulonglong4 e = *reinterpret_cast<const ulonglong4 *>(table + i);
+    TSlot t = { e.x, e.y, e.z, e.w };
+    return t;
+}
+
+__global__ void __launch_bounds__(kBlock) k_dedup_compact(const TSlot *table, size_t slots, Slot *keys, u64 *mults, u64 *cursor)
 {
     for (size_t i = blockIdx.x * (size_t)kBlock + threadIdx.x; i < slots; i += (size_t)gridDim.x * kBlock) {
-        Slot k = table[i];
+        const TSlot k = load_entry(table, i);
         if (k.hi == ~0ull && k.lo == ~0ull) continue;
         u64 o = atomicAdd(cursor, 1ull);
-        keys[o] = k; mults[o] = counts[i];
+        keys[o].hi = k.hi; keys[o].lo = k.lo; mults[o] = k.count;
     }
 }
 
 // unsorted path: table -> caller's payload / multiplicity arrays directly (no intermediate copy)
-__global__ void __launch_bounds__(kBlock) k_dedup_compact_emit(const Slot *table, const u64 *counts, size_t slots,
+__global__ void __launch_bounds__(kBlock) k_dedup_compact_emit(const TSlot *table, size_t slots,
                                                                 uint4 *uniq, u64 *uniq_mult, u64 *cursor)
 {
     for (size_t i = blockIdx.x * (size_t)kBlock + threadIdx.x; i < slots; i += (size_t)gridDim.x * kBlock) {
-        Slot k = table[i];
+        const TSlot k = load_entry(table, i);
         if (k.hi == ~0ull && k.lo == ~0ull) continue;
         u64 o = atomicAdd(cursor, 1ull);
         uniq[o] = make_uint4(prmt((uint32_t)(k.hi >> 32), 0, 0x0123), prmt((uint32_t)k.hi, 0, 0x0123),
                              prmt((uint32_t)(k.lo >> 32), 0, 0x0123), prmt((uint32_t)k.lo, 0, 0x0123));
-        uniq_mult[o] = counts[i];
+        uniq_mult[o] = k.count;
     }
 }
 
@@ -186,28 +219,9 @@ struct BfsWarpScratch {
     unsigned char mover[32];
 };
 
-__device__ __forceinline__ void table_insert(Slot *table, u64 *counts, size_t slot_mask, u64 khi_new, u64 klo_new, u64 m,
-                                             u64 *n_unique, u64 *all_ones_count, int *overflow, u64 max_unique)
-{
-    if ((khi_new & klo_new) == ~0ull) { atomicAdd(all_ones_count, m); return; }
-    size_t slot = (size_t)mix(khi_new, klo_new) & slot_mask;
-    for (size_t probe = 0; probe <= slot_mask; ++probe, slot = (slot + 1) & slot_mask) {
-        const ulonglong2 raw = __ldcv(reinterpret_cast<const ulonglong2 *>(table + slot));
-        u64 khi = raw.x, klo = raw.y;
-        if (khi == ~0ull || klo == ~0ull) {
-            cas128(table + slot, ~0ull, ~0ull, khi_new, klo_new, khi, klo);
-            if (khi == ~0ull && klo == ~0ull) {
-                if (atomicAdd(n_unique, 1ull) >= max_unique) *overflow = 1;
-                khi = khi_new; klo = klo_new;
-            }
-        }
-        if (khi == khi_new && klo == klo_new) { atomicAdd(counts + slot, m); return; }   // game_stats.py:487-505
-    }
-}
-
 template <bool COLOR_SWAP>
 __global__ void __launch_bounds__(kBlock) k_bfs_expand_insert(const uint4 *__restrict__ parents, const u64 *__restrict__ mult,
-                                                               size_t n, Slot *table, u64 *counts, size_t slot_mask,
+                                                               size_t n, TSlot *table, size_t slot_mask,
                                                                u64 *n_unique, u64 *all_ones_count, int *overflow,
                                                                u64 max_unique, u64 *stats)
 {
@@ -216,8 +230,9 @@ __global__ void __launch_bounds__(kBlock) k_bfs_expand_insert(const uint4 *__res
     const unsigned lane = threadIdx.x & 31u;
     const size_t warp = (blockIdx.x * (size_t)kBlock + threadIdx.x) >> 5, n_warps = ((size_t)gridDim.x * kBlock) >> 5;
     u64 s_moves = 0, s_w0 = 0, s_w1 = 0, s_b0 = 0, s_b1 = 0;      // per lane
+    unsigned claims = 0;
     for (size_t tile = warp * 32; tile < n; tile += n_warps * 32) {
-        if (*reinterpret_cast<volatile int *>(overflow)) break;     // table too small: the host retries with a larger one
+        if (__any_sync(0xFFFFFFFFu, *reinterpret_cast<volatile int *>(overflow))) break;   // table too small: the host retries
         // ---- one parent per lane: moves, winning moves, the children worth keeping
         uint32_t nl = 0, nh = 0;
         const size_t i = tile + lane;
@@ -257,13 +272,14 @@ __global__ void __launch_bounds__(kBlock) k_bfs_expand_insert(const uint4 *__res
                 const uint4 pv = ws.state[pl];
                 const State4 parent = { pv.x, pv.y, pv.z, pv.w };
                 const State4 c = canonical<COLOR_SWAP>(apply_action(parent, ws.mover[pl], (int)(e & 63u)));   // :453,:468
-                table_insert(table, counts, slot_mask, ((u64)prmt(c.x, 0, 0x0123) << 32) | prmt(c.y, 0, 0x0123),
-                             ((u64)prmt(c.z, 0, 0x0123) << 32) | prmt(c.w, 0, 0x0123), ws.mult[pl], n_unique, all_ones_count,
-                             overflow, max_unique);
+                claims += table_insert(table, slot_mask, ((u64)prmt(c.x, 0, 0x0123) << 32) | prmt(c.y, 0, 0x0123),
+                                       ((u64)prmt(c.z, 0, 0x0123) << 32) | prmt(c.w, 0, 0x0123), ws.mult[pl], all_ones_count,
+                                       overflow) ? 1u : 0u;
             }
         }
         __syncwarp();
     }
+    flush_claims(claims, n_unique, overflow, max_unique);
     // per-lane sums -> one atomic per warp and counter
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -290,7 +306,7 @@ __global__ void __launch_bounds__(kBlock) k_bfs_expand_insert(const uint4 *__res
 // shared memory).  Only one lane per distinct child inserts, so the stored multiplicity of a class is
 // its in-degree in position_edges.    stats: [0] terminal parents  [1] edges
 template <bool COLOR_SWAP>
-__global__ void __launch_bounds__(kBlock) k_book_expand_insert(const uint4 *__restrict__ parents, size_t n, Slot *table, u64 *counts,
+__global__ void __launch_bounds__(kBlock) k_book_expand_insert(const uint4 *__restrict__ parents, size_t n, TSlot *table,
                                                                 size_t slot_mask, u64 *n_unique, u64 *all_ones_count, int *overflow,
                                                                 u64 max_unique, u64 *stats)
 {
@@ -299,8 +315,9 @@ __global__ void __launch_bounds__(kBlock) k_book_expand_insert(const uint4 *__re
     const unsigned lane = threadIdx.x & 31u;
     const size_t warp = (blockIdx.x * (size_t)kBlock + threadIdx.x) >> 5, n_warps = ((size_t)gridDim.x * kBlock) >> 5;
     u64 s_terminal = 0, s_edges = 0;
+    unsigned claims = 0;
     for (size_t i = warp; i < n; i += n_warps) {
-        if (*reinterpret_cast<volatile int *>(overflow)) break;
+        if (__any_sync(0xFFFFFFFFu, *reinterpret_cast<volatile int *>(overflow))) break;
         const uint4 v = __ldg(parents + i);
         const State4 parent = { v.x, v.y, v.z, v.w };
         if (has_winning_line(parent)) { ++s_terminal; continue; }                       // generate_opening_book.py:205-211
@@ -331,25 +348,11 @@ __global__ void __launch_bounds__(kBlock) k_book_expand_insert(const uint4 *__re
         __syncwarp();
         s_edges += (u64)(__popc(__ballot_sync(0xFFFFFFFFu, leader[0])) + __popc(__ballot_sync(0xFFFFFFFFu, leader[1])));
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            if (!leader[half]) continue;
-            const u64 khi_new = key[half].hi, klo_new = key[half].lo;
-            if ((khi_new & klo_new) == ~0ull) { atomicAdd(all_ones_count, 1ull); continue; }
-            size_t slot = (size_t)mix(khi_new, klo_new) & slot_mask;
-            for (size_t probe = 0; probe <= slot_mask; ++probe, slot = (slot + 1) & slot_mask) {
-                const ulonglong2 raw = __ldcv(reinterpret_cast<const ulonglong2 *>(table + slot));
-                u64 khi = raw.x, klo = raw.y;
-                if (khi == ~0ull || klo == ~0ull) {
-                    cas128(table + slot, ~0ull, ~0ull, khi_new, klo_new, khi, klo);
-                    if (khi == ~0ull && klo == ~0ull) {
-                        if (atomicAdd(n_unique, 1ull) >= max_unique) *overflow = 1;
-                        khi = khi_new; klo = klo_new;
-                    }
-                }
-                if (khi == khi_new && klo == klo_new) { atomicAdd(counts + slot, 1ull); break; }
-            }
-        }
+        for (int half = 0; half < 2; ++half)
+            if (leader[half])
+                claims += table_insert(table, slot_mask, key[half].hi, key[half].lo, 1ull, all_ones_count, overflow) ? 1u : 0u;
     }
+    flush_claims(claims, n_unique, overflow, max_unique);
     if (lane == 0) {
         if (s_terminal) atomicAdd(stats + 0, s_terminal);
         if (s_edges) atomicAdd(stats + 1, s_edges);
@@ -357,19 +360,18 @@ __global__ void __launch_bounds__(kBlock) k_book_expand_insert(const uint4 *__re
 }
 
 // ------------------------------------------------------------------ host side
-struct DedupTable { Slot *table; u64 *counts; u64 *meta; size_t slots; u64 max_unique; };
+struct DedupTable { TSlot *table; u64 *meta; size_t slots; u64 max_unique; };
 
 static int dedup_begin(Call &call, size_t expected_unique, DedupTable &t)
 {
     cudaStream_t s = call.stream();
     t.slots = 1024;
     while (t.slots < 2 * expected_unique + 2) t.slots <<= 1;
-    t.table = (Slot *)call.temp(t.slots * sizeof(Slot));
-    t.counts = (u64 *)call.temp(t.slots * sizeof(u64));
+    t.table = (TSlot *)call.temp(t.slots * sizeof(TSlot));
     t.meta = (u64 *)call.temp(10 * sizeof(u64), true);   // n_unique, all-ones mult, cursor, overflow, stats[5]
-    if (!t.table || !t.counts || !t.meta) return call.status();
+    if (!t.table || !t.meta) return call.status();
     t.max_unique = (u64)(t.slots / 2);
-    k_dedup_fill<<<grid_for(t.slots, kBlock, call.ctx()->sms, 8), kBlock, 0, s>>>(t.table, t.counts, t.slots);
+    k_dedup_fill<<<grid_for(t.slots, kBlock, call.ctx()->sms, 8), kBlock, 0, s>>>(t.table, t.slots);
     QK_CUDA(cudaGetLastError());
     return QK_OK;
 }
@@ -396,7 +398,7 @@ static int dedup_finish(Call &call, DedupTable &t, uint16_t *uniq, uint64_t *uni
         uint4 *d_uniq = (uint4 *)call.out(uniq, (nu + 1) * 16);
         u64 *d_um = (u64 *)call.out(uniq_mult, (nu + 1) * 8);
         if (call.status() != QK_OK) return call.status();
-        k_dedup_compact_emit<<<grid_for(t.slots, kBlock, c->sms, 8), kBlock, 0, s>>>(t.table, t.counts, t.slots, d_uniq, d_um, t.meta + 2);
+        k_dedup_compact_emit<<<grid_for(t.slots, kBlock, c->sms, 8), kBlock, 0, s>>>(t.table, t.slots, d_uniq, d_um, t.meta + 2);
         QK_CUDA(cudaGetLastError());
         if (special) {
             const uint32_t ones[4] = { ~0u, ~0u, ~0u, ~0u };
@@ -413,7 +415,7 @@ static int dedup_finish(Call &call, DedupTable &t, uint16_t *uniq, uint64_t *uni
     Slot *keys = (Slot *)call.temp((padded + 1) * sizeof(Slot));
     u64 *mults = (u64 *)call.temp((padded + 1) * sizeof(u64));
     if (!keys || !mults) return call.status();
-    k_dedup_compact<<<grid_for(t.slots, kBlock, c->sms, 8), kBlock, 0, s>>>(t.table, t.counts, t.slots, keys, mults, t.meta + 2);
+    k_dedup_compact<<<grid_for(t.slots, kBlock, c->sms, 8), kBlock, 0, s>>>(t.table, t.slots, keys, mults, t.meta + 2);
     k_pad<<<grid_for(padded - nu + 1, kBlock, c->sms, 8), kBlock, 0, s>>>(keys, mults, nu, padded);
     const unsigned tile_grid = grid_for(padded / kTile * kBlock, kBlock, c->sms, 8);
     k_bitonic_tile<<<tile_grid, kBlock, 0, s>>>(keys, mults, padded, 2, kTile);
@@ -451,10 +453,10 @@ int run_dedup(Call &call, const uint4 *states, const uint64_t *mult, size_t n, i
     if (rc != QK_OK) return rc;
     const bool unsorted = (color_swap & QK_DEDUP_UNSORTED) != 0;
     if (color_swap & 1)
-        k_dedup_insert<true><<<grid_for(n, kBlock, c->sms, 8), kBlock, 0, s>>>(states, (const u64 *)mult, n, t.table, t.counts, t.slots - 1,
+        k_dedup_insert<true><<<grid_for(n, kBlock, c->sms, 8), kBlock, 0, s>>>(states, (const u64 *)mult, n, t.table, t.slots - 1,
                                                                              t.meta, t.meta + 1, (int *)(t.meta + 3), t.max_unique);
     else
-        k_dedup_insert<false><<<grid_for(n, kBlock, c->sms, 8), kBlock, 0, s>>>(states, (const u64 *)mult, n, t.table, t.counts, t.slots - 1,
+        k_dedup_insert<false><<<grid_for(n, kBlock, c->sms, 8), kBlock, 0, s>>>(states, (const u64 *)mult, n, t.table, t.slots - 1,
                                                                               t.meta, t.meta + 1, (int *)(t.meta + 3), t.max_unique);
     QK_CUDA(cudaGetLastError());
     return dedup_finish(call, t, uniq, uniq_mult, cap, n_uniq, nullptr, "qk_canon_dedup", !unsorted);
@@ -471,10 +473,10 @@ int run_bfs_level(Call &call, const uint4 *parents, const uint64_t *mult, size_t
     // one parent per lane (tiles of 32 per warp), grid-stride
     const unsigned grid = grid_for(n, kBlock, c->sms, 5);
     if (color_swap)
-        k_bfs_expand_insert<true><<<grid, kBlock, 0, s>>>(parents, (const u64 *)mult, n, t.table, t.counts, t.slots - 1, t.meta, t.meta + 1,
+        k_bfs_expand_insert<true><<<grid, kBlock, 0, s>>>(parents, (const u64 *)mult, n, t.table, t.slots - 1, t.meta, t.meta + 1,
                                                          (int *)(t.meta + 3), t.max_unique, t.meta + 4);
     else
-        k_bfs_expand_insert<false><<<grid, kBlock, 0, s>>>(parents, (const u64 *)mult, n, t.table, t.counts, t.slots - 1, t.meta, t.meta + 1,
+        k_bfs_expand_insert<false><<<grid, kBlock, 0, s>>>(parents, (const u64 *)mult, n, t.table, t.slots - 1, t.meta, t.meta + 1,
                                                           (int *)(t.meta + 3), t.max_unique, t.meta + 4);
     QK_CUDA(cudaGetLastError());
     return dedup_finish(call, t, uniq, uniq_mult, cap, n_uniq, h_stats, "qk_bfs_level", sort_output != 0);
@@ -504,7 +506,7 @@ __device__ __forceinline__ int owner_of(u64 hi, u64 lo, int world)
 // local table -> the owners' inboxes.  Per 256 slots a block counts its entries per destination in shared
 // memory, reserves one range per destination in the SOURCE-side cursor (regions are per source, so no remote
 // atomics), then every thread stores its (key, multiplicity) straight into the peer's memory.
-__global__ void __launch_bounds__(kBlock) k_dedup_scatter(const Slot *table, const u64 *counts, size_t slots, Peers p,
+__global__ void __launch_bounds__(kBlock) k_dedup_scatter(const TSlot *table, size_t slots, Peers p,
                                                            u64 *cursor, int *overflow)
 {
     __shared__ unsigned s_cnt[QK_MAX_WORLD];
@@ -515,14 +517,14 @@ __global__ void __launch_bounds__(kBlock) k_dedup_scatter(const Slot *table, con
         const size_t i = round * stride + blockIdx.x * (size_t)kBlock + threadIdx.x;
         if (threadIdx.x < QK_MAX_WORLD) s_cnt[threadIdx.x] = 0;
         __syncthreads();
-        Slot k = { ~0ull, ~0ull };
-        if (i < slots) k = table[i];
+        TSlot e = { ~0ull, ~0ull, 0ull, 0ull };
+        if (i < slots) e = load_entry(table, i);
+        const Slot k = { e.hi, e.lo };
         const bool have = !(k.hi == ~0ull && k.lo == ~0ull);
         int dst = 0;
         unsigned r = 0;
-        u64 m = 0;
+        const u64 m = e.count;
         if (have) {
-            m = counts[i];
             dst = owner_of(k.hi, k.lo, p.world);
             r = atomicAdd(&s_cnt[dst], 1u);
         }
@@ -565,29 +567,17 @@ __global__ void k_scatter_publish(Peers p, u64 *cursor, u64 all_ones_mult)
 }
 
 // the owner's side: entries of one inbox region (canonical already) into the merge table
-__global__ void __launch_bounds__(kBlock) k_inbox_insert(const Slot *keys, const u64 *mults, size_t n, Slot *table, u64 *counts,
+__global__ void __launch_bounds__(kBlock) k_inbox_insert(const Slot *keys, const u64 *mults, size_t n, TSlot *table,
                                                           size_t slot_mask, u64 *n_unique, u64 *all_ones_count, int *overflow,
                                                           u64 max_unique)
 {
+    unsigned claims = 0;
     for (size_t i = blockIdx.x * (size_t)kBlock + threadIdx.x; i < n; i += (size_t)gridDim.x * kBlock) {
         if (*reinterpret_cast<volatile int *>(overflow)) break;
         const Slot key = keys[i];
-        const u64 hi = key.hi, lo = key.lo, m = mults[i];
-        if ((hi & lo) == ~0ull) { atomicAdd(all_ones_count, m); continue; }
-        size_t slot = (size_t)mix(hi, lo) & slot_mask;
-        for (size_t probe = 0; probe <= slot_mask; ++probe, slot = (slot + 1) & slot_mask) {
-            const ulonglong2 raw = __ldcv(reinterpret_cast<const ulonglong2 *>(table + slot));
-            u64 khi = raw.x, klo = raw.y;
-            if (khi == ~0ull || klo == ~0ull) {
-                cas128(table + slot, ~0ull, ~0ull, hi, lo, khi, klo);
-                if (khi == ~0ull && klo == ~0ull) {
-                    if (atomicAdd(n_unique, 1ull) >= max_unique) *overflow = 1;
-                    khi = hi; klo = lo;
-                }
-            }
-            if (khi == hi && klo == lo) { atomicAdd(counts + slot, m); break; }
-        }
+        claims += table_insert(table, slot_mask, key.hi, key.lo, mults[i], all_ones_count, overflow) ? 1u : 0u;
     }
+    flush_claims(claims, n_unique, overflow, max_unique);
 }
 
 // local table -> peers; h_stats (5 x u64, may be null), h_sent (world x u64, may be null)
@@ -606,7 +596,7 @@ static int scatter_finish(Call &call, DedupTable &t, const Peers &peers, uint64_
     u64 *cursor = (u64 *)call.temp((QK_MAX_WORLD + 1) * sizeof(u64), true);     // [QK_MAX_WORLD] = overflow flag
     if (!cursor) return call.status();
     int *overflow = (int *)(cursor + QK_MAX_WORLD);
-    k_dedup_scatter<<<grid_for(t.slots, kBlock, c->sms, 8), kBlock, 0, s>>>(t.table, t.counts, t.slots, peers, cursor, overflow);
+    k_dedup_scatter<<<grid_for(t.slots, kBlock, c->sms, 8), kBlock, 0, s>>>(t.table, t.slots, peers, cursor, overflow);
     k_scatter_publish<<<1, 32, 0, s>>>(peers, cursor, h_meta[1]);
     QK_CUDA(cudaGetLastError());
     u64 h_cursor[QK_MAX_WORLD + 1];
@@ -633,10 +623,10 @@ int run_dedup_scatter(Call &call, const uint4 *states, const uint64_t *mult, siz
     if (rc != QK_OK) return rc;
     if (n) {
         if (flags & 1)
-            k_dedup_insert<true><<<grid_for(n, kBlock, c->sms, 8), kBlock, 0, s>>>(states, (const u64 *)mult, n, t.table, t.counts, t.slots - 1,
+            k_dedup_insert<true><<<grid_for(n, kBlock, c->sms, 8), kBlock, 0, s>>>(states, (const u64 *)mult, n, t.table, t.slots - 1,
                                                                                  t.meta, t.meta + 1, (int *)(t.meta + 3), t.max_unique);
         else
-            k_dedup_insert<false><<<grid_for(n, kBlock, c->sms, 8), kBlock, 0, s>>>(states, (const u64 *)mult, n, t.table, t.counts, t.slots - 1,
+            k_dedup_insert<false><<<grid_for(n, kBlock, c->sms, 8), kBlock, 0, s>>>(states, (const u64 *)mult, n, t.table, t.slots - 1,
                                                                                   t.meta, t.meta + 1, (int *)(t.meta + 3), t.max_unique);
         QK_CUDA(cudaGetLastError());
     }
@@ -654,10 +644,10 @@ int run_bfs_level_scatter(Call &call, const uint4 *parents, const uint64_t *mult
     if (n) {
         const unsigned grid = grid_for(n, kBlock, c->sms, 5);
         if (flags & 1)
-            k_bfs_expand_insert<true><<<grid, kBlock, 0, s>>>(parents, (const u64 *)mult, n, t.table, t.counts, t.slots - 1, t.meta, t.meta + 1,
+            k_bfs_expand_insert<true><<<grid, kBlock, 0, s>>>(parents, (const u64 *)mult, n, t.table, t.slots - 1, t.meta, t.meta + 1,
                                                              (int *)(t.meta + 3), t.max_unique, t.meta + 4);
         else
-            k_bfs_expand_insert<false><<<grid, kBlock, 0, s>>>(parents, (const u64 *)mult, n, t.table, t.counts, t.slots - 1, t.meta, t.meta + 1,
+            k_bfs_expand_insert<false><<<grid, kBlock, 0, s>>>(parents, (const u64 *)mult, n, t.table, t.slots - 1, t.meta, t.meta + 1,
                                                               (int *)(t.meta + 3), t.max_unique, t.meta + 4);
         QK_CUDA(cudaGetLastError());
     }
@@ -687,7 +677,7 @@ int run_inbox_merge(Call &call, const void *my_inbox, int world, size_t slots_pe
     for (int r = 0; r < world; ++r) {
         if (!h_counts[r]) continue;
         k_inbox_insert<<<grid_for((size_t)h_counts[r], kBlock, c->sms, 8), kBlock, 0, s>>>(
-            v.keys + (size_t)r * slots_per_src, v.mults + (size_t)r * slots_per_src, (size_t)h_counts[r], t.table, t.counts, t.slots - 1,
+            v.keys + (size_t)r * slots_per_src, v.mults + (size_t)r * slots_per_src, (size_t)h_counts[r], t.table, t.slots - 1,
             t.meta, t.meta + 1, (int *)(t.meta + 3), t.max_unique);
     }
     QK_CUDA(cudaGetLastError());
@@ -704,10 +694,10 @@ int run_book_level(Call &call, const uint4 *parents, size_t n, int color_swap, u
     if (rc != QK_OK) return rc;
     const unsigned grid = grid_for(n * 32, kBlock, c->sms, 8);
     if (color_swap)
-        k_book_expand_insert<true><<<grid, kBlock, 0, s>>>(parents, n, t.table, t.counts, t.slots - 1, t.meta, t.meta + 1,
+        k_book_expand_insert<true><<<grid, kBlock, 0, s>>>(parents, n, t.table, t.slots - 1, t.meta, t.meta + 1,
                                                           (int *)(t.meta + 3), t.max_unique, t.meta + 4);
     else
-        k_book_expand_insert<false><<<grid, kBlock, 0, s>>>(parents, n, t.table, t.counts, t.slots - 1, t.meta, t.meta + 1,
+        k_book_expand_insert<false><<<grid, kBlock, 0, s>>>(parents, n, t.table, t.slots - 1, t.meta, t.meta + 1,
                                                            (int *)(t.meta + 3), t.max_unique, t.meta + 4);
     QK_CUDA(cudaGetLastError());
     uint64_t st[5] = { 0, 0, 0, 0, 0 };

@@ -58,13 +58,14 @@ __global__ void __launch_bounds__(kBlock) k_dedup_fill(TSlot *table, size_t slot
 // Adds multiplicity m to key (khi_new, klo_new), creating the entry when it is new.  -> true when THIS call
 // created it.  Distinct keys are counted by the callers in registers and added to the global counter once per
 // warp at the end of the kernel (flush_claims): a per-insert atomic on one address serialises in one L2 slice.
-__device__ __forceinline__ bool table_insert(TSlot *table, size_t slot_mask, u64 khi_new, u64 klo_new, u64 m,
+__device__ __forceinline__ bool table_insert(TSlot *table, size_t slots, u64 khi_new, u64 klo_new, u64 m,
                                              u64 *all_ones_count, int *overflow)
 {
     if ((khi_new & klo_new) == ~0ull) { atomicAdd(all_ones_count, m); return false; }   // the payload that equals the empty marker
-    size_t slot = (size_t)mix(khi_new, klo_new) & slot_mask;
-    const size_t max_probe = slot_mask < kMaxProbe ? slot_mask : kMaxProbe;
-    for (size_t probe = 0; probe <= max_probe; ++probe, slot = (slot + 1) & slot_mask) {
+    // any table size (not only powers of two: the table is filled and scanned once per call, so its size is time)
+    size_t slot = (size_t)__umul64hi(mix(khi_new, klo_new), (u64)slots);
+    const size_t max_probe = slots - 1 < kMaxProbe ? slots - 1 : kMaxProbe;
+    for (size_t probe = 0; probe <= max_probe; ++probe, slot = slot + 1 == slots ? 0 : slot + 1) {
         // fast path: one 128-bit load; a slot caught half-way through another thread's
         // CAS can only look like "some half is all ones", which falls through to the CAS
         const ulonglong2 raw = __ldcv(reinterpret_cast<const ulonglong2 *>(table + slot));
@@ -92,7 +93,7 @@ __device__ __forceinline__ void flush_claims(unsigned claims, u64 *n_unique, int
 
 template <bool COLOR_SWAP>
 __global__ void __launch_bounds__(kBlock) k_dedup_insert(const uint4 *__restrict__ states, const u64 *__restrict__ mult, size_t n,
-                                                          TSlot *table, size_t slot_mask,
+                                                          TSlot *table, size_t slots,
                                                           u64 *n_unique, u64 *all_ones_count, int *overflow, u64 max_unique)
 {
     unsigned claims = 0;
@@ -104,7 +105,7 @@ __global__ void __launch_bounds__(kBlock) k_dedup_insert(const uint4 *__restrict
         // comparable big-endian limbs of the payload bytes
         u64 hi = ((u64)prmt(c.x, 0, 0x0123) << 32) | prmt(c.y, 0, 0x0123);
         u64 lo = ((u64)prmt(c.z, 0, 0x0123) << 32) | prmt(c.w, 0, 0x0123);
-        claims += table_insert(table, slot_mask, hi, lo, mult ? mult[i] : 1ull, all_ones_count, overflow) ? 1u : 0u;
+        claims += table_insert(table, slots, hi, lo, mult ? mult[i] : 1ull, all_ones_count, overflow) ? 1u : 0u;
     }
     flush_claims(claims, n_unique, overflow, max_unique);
 }
@@ -116,13 +117,25 @@ __device__ __forceinline__ TSlot load_entry(const TSlot *table, size_t i)
     return t;
 }
 
+// position of this lane's entry in the dense output: one cursor atomic per warp (slots and the grid stride are
+// multiples of 32, so the warp is converged here)
+__device__ __forceinline__ u64 compact_slot(bool have, u64 *cursor)
+{
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned present = __ballot_sync(0xFFFFFFFFu, have);
+    u64 base = 0;
+    if (lane == 0 && present) base = atomicAdd(cursor, (u64)__popc(present));
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    return base + (u64)__popc(present & ((1u << lane) - 1u));
+}
+
 __global__ void __launch_bounds__(kBlock) k_dedup_compact(const TSlot *table, size_t slots, Slot *keys, u64 *mults, u64 *cursor)
 {
     for (size_t i = blockIdx.x * (size_t)kBlock + threadIdx.x; i < slots; i += (size_t)gridDim.x * kBlock) {
         const TSlot k = load_entry(table, i);
-        if (k.hi == ~0ull && k.lo == ~0ull) continue;
-        u64 o = atomicAdd(cursor, 1ull);
-        keys[o].hi = k.hi; keys[o].lo = k.lo; mults[o] = k.count;
+        const bool have = !(k.hi == ~0ull && k.lo == ~0ull);
+        const u64 o = compact_slot(have, cursor);
+        if (have) { keys[o].hi = k.hi; keys[o].lo = k.lo; mults[o] = k.count; }
     }
 }
 
@@ -132,11 +145,13 @@ __global__ void __launch_bounds__(kBlock) k_dedup_compact_emit(const TSlot *tabl
 {
     for (size_t i = blockIdx.x * (size_t)kBlock + threadIdx.x; i < slots; i += (size_t)gridDim.x * kBlock) {
         const TSlot k = load_entry(table, i);
-        if (k.hi == ~0ull && k.lo == ~0ull) continue;
-        u64 o = atomicAdd(cursor, 1ull);
-        uniq[o] = make_uint4(prmt((uint32_t)(k.hi >> 32), 0, 0x0123), prmt((uint32_t)k.hi, 0, 0x0123),
-                             prmt((uint32_t)(k.lo >> 32), 0, 0x0123), prmt((uint32_t)k.lo, 0, 0x0123));
-        uniq_mult[o] = k.count;
+        const bool have = !(k.hi == ~0ull && k.lo == ~0ull);
+        const u64 o = compact_slot(have, cursor);
+        if (have) {
+            uniq[o] = make_uint4(prmt((uint32_t)(k.hi >> 32), 0, 0x0123), prmt((uint32_t)k.hi, 0, 0x0123),
+                                 prmt((uint32_t)(k.lo >> 32), 0, 0x0123), prmt((uint32_t)k.lo, 0, 0x0123));
+            uniq_mult[o] = k.count;
+        }
     }
 }
 
@@ -221,7 +236,7 @@ struct BfsWarpScratch {
 
 template <bool COLOR_SWAP>
 __global__ void __launch_bounds__(kBlock) k_bfs_expand_insert(const uint4 *__restrict__ parents, const u64 *__restrict__ mult,
-                                                               size_t n, TSlot *table, size_t slot_mask,
+                                                               size_t n, TSlot *table, size_t slots,
                                                                u64 *n_unique, u64 *all_ones_count, int *overflow,
                                                                u64 max_unique, u64 *stats)
 {
@@ -272,7 +287,7 @@ __global__ void __launch_bounds__(kBlock) k_bfs_expand_insert(const uint4 *__res
                 const uint4 pv = ws.state[pl];
                 const State4 parent = { pv.x, pv.y, pv.z, pv.w };
                 const State4 c = canonical<COLOR_SWAP>(apply_action(parent, ws.mover[pl], (int)(e & 63u)));   // :453,:468
-                claims += table_insert(table, slot_mask, ((u64)prmt(c.x, 0, 0x0123) << 32) | prmt(c.y, 0, 0x0123),
+                claims += table_insert(table, slots, ((u64)prmt(c.x, 0, 0x0123) << 32) | prmt(c.y, 0, 0x0123),
                                        ((u64)prmt(c.z, 0, 0x0123) << 32) | prmt(c.w, 0, 0x0123), ws.mult[pl], all_ones_count,
                                        overflow) ? 1u : 0u;
             }
@@ -307,7 +322,7 @@ __global__ void __launch_bounds__(kBlock) k_bfs_expand_insert(const uint4 *__res
 // its in-degree in position_edges.    stats: [0] terminal parents  [1] edges
 template <bool COLOR_SWAP>
 __global__ void __launch_bounds__(kBlock) k_book_expand_insert(const uint4 *__restrict__ parents, size_t n, TSlot *table,
-                                                                size_t slot_mask, u64 *n_unique, u64 *all_ones_count, int *overflow,
+                                                                size_t slots, u64 *n_unique, u64 *all_ones_count, int *overflow,
                                                                 u64 max_unique, u64 *stats)
 {
     __shared__ Slot s_first[kBlock / 32][32];
@@ -350,7 +365,7 @@ __global__ void __launch_bounds__(kBlock) k_book_expand_insert(const uint4 *__re
 #pragma unroll
         for (int half = 0; half < 2; ++half)
             if (leader[half])
-                claims += table_insert(table, slot_mask, key[half].hi, key[half].lo, 1ull, all_ones_count, overflow) ? 1u : 0u;
+                claims += table_insert(table, slots, key[half].hi, key[half].lo, 1ull, all_ones_count, overflow) ? 1u : 0u;
     }
     flush_claims(claims, n_unique, overflow, max_unique);
     if (lane == 0) {
@@ -365,12 +380,15 @@ struct DedupTable { TSlot *table; u64 *meta; size_t slots; u64 max_unique; };
 static int dedup_begin(Call &call, size_t expected_unique, DedupTable &t)
 {
     cudaStream_t s = call.stream();
-    t.slots = 1024;
-    while (t.slots < 2 * expected_unique + 2) t.slots <<= 1;
+    // 1.5 slots per expected key (linear probing stays short up to ~2/3 full), a multiple of 256 so that warps
+    // scan it converged
+    t.slots = expected_unique + expected_unique / 2 + 2;
+    if (t.slots < 1024) t.slots = 1024;
+    t.slots = (t.slots + 255) / 256 * 256;
     t.table = (TSlot *)call.temp(t.slots * sizeof(TSlot));
     t.meta = (u64 *)call.temp(10 * sizeof(u64), true);   // n_unique, all-ones mult, cursor, overflow, stats[5]
     if (!t.table || !t.meta) return call.status();
-    t.max_unique = (u64)(t.slots / 2);
+    t.max_unique = (u64)(expected_unique < 512 ? 512 : expected_unique);
     k_dedup_fill<<<grid_for(t.slots, kBlock, call.ctx()->sms, 8), kBlock, 0, s>>>(t.table, t.slots);
     QK_CUDA(cudaGetLastError());
     return QK_OK;
@@ -453,10 +471,10 @@ int run_dedup(Call &call, const uint4 *states, const uint64_t *mult, size_t n, i
     if (rc != QK_OK) return rc;
     const bool unsorted = (color_swap & QK_DEDUP_UNSORTED) != 0;
     if (color_swap & 1)
-        k_dedup_insert<true><<<grid_for(n, kBlock, c->sms, 8), kBlock, 0, s>>>(states, (const u64 *)mult, n, t.table, t.slots - 1,
+        k_dedup_insert<true><<<grid_for(n, kBlock, c->sms, 8), kBlock, 0, s>>>(states, (const u64 *)mult, n, t.table, t.slots,
                                                                              t.meta, t.meta + 1, (int *)(t.meta + 3), t.max_unique);
     else
-        k_dedup_insert<false><<<grid_for(n, kBlock, c->sms, 8), kBlock, 0, s>>>(states, (const u64 *)mult, n, t.table, t.slots - 1,
+        k_dedup_insert<false><<<grid_for(n, kBlock, c->sms, 8), kBlock, 0, s>>>(states, (const u64 *)mult, n, t.table, t.slots,
                                                                               t.meta, t.meta + 1, (int *)(t.meta + 3), t.max_unique);
     QK_CUDA(cudaGetLastError());
     return dedup_finish(call, t, uniq, uniq_mult, cap, n_uniq, nullptr, "qk_canon_dedup", !unsorted);
@@ -473,10 +491,10 @@ int run_bfs_level(Call &call, const uint4 *parents, const uint64_t *mult, size_t
     // one parent per lane (tiles of 32 per warp), grid-stride
     const unsigned grid = grid_for(n, kBlock, c->sms, 5);
     if (color_swap)
-        k_bfs_expand_insert<true><<<grid, kBlock, 0, s>>>(parents, (const u64 *)mult, n, t.table, t.slots - 1, t.meta, t.meta + 1,
+        k_bfs_expand_insert<true><<<grid, kBlock, 0, s>>>(parents, (const u64 *)mult, n, t.table, t.slots, t.meta, t.meta + 1,
                                                          (int *)(t.meta + 3), t.max_unique, t.meta + 4);
     else
-        k_bfs_expand_insert<false><<<grid, kBlock, 0, s>>>(parents, (const u64 *)mult, n, t.table, t.slots - 1, t.meta, t.meta + 1,
+        k_bfs_expand_insert<false><<<grid, kBlock, 0, s>>>(parents, (const u64 *)mult, n, t.table, t.slots, t.meta, t.meta + 1,
                                                           (int *)(t.meta + 3), t.max_unique, t.meta + 4);
     QK_CUDA(cudaGetLastError());
     return dedup_finish(call, t, uniq, uniq_mult, cap, n_uniq, h_stats, "qk_bfs_level", sort_output != 0);
@@ -568,14 +586,14 @@ __global__ void k_scatter_publish(Peers p, u64 *cursor, u64 all_ones_mult)
 
 // the owner's side: entries of one inbox region (canonical already) into the merge table
 __global__ void __launch_bounds__(kBlock) k_inbox_insert(const Slot *keys, const u64 *mults, size_t n, TSlot *table,
-                                                          size_t slot_mask, u64 *n_unique, u64 *all_ones_count, int *overflow,
+                                                          size_t slots, u64 *n_unique, u64 *all_ones_count, int *overflow,
                                                           u64 max_unique)
 {
     unsigned claims = 0;
     for (size_t i = blockIdx.x * (size_t)kBlock + threadIdx.x; i < n; i += (size_t)gridDim.x * kBlock) {
         if (*reinterpret_cast<volatile int *>(overflow)) break;
         const Slot key = keys[i];
-        claims += table_insert(table, slot_mask, key.hi, key.lo, mults[i], all_ones_count, overflow) ? 1u : 0u;
+        claims += table_insert(table, slots, key.hi, key.lo, mults[i], all_ones_count, overflow) ? 1u : 0u;
     }
     flush_claims(claims, n_unique, overflow, max_unique);
 }
@@ -623,10 +641,10 @@ int run_dedup_scatter(Call &call, const uint4 *states, const uint64_t *mult, siz
     if (rc != QK_OK) return rc;
     if (n) {
         if (flags & 1)
-            k_dedup_insert<true><<<grid_for(n, kBlock, c->sms, 8), kBlock, 0, s>>>(states, (const u64 *)mult, n, t.table, t.slots - 1,
+            k_dedup_insert<true><<<grid_for(n, kBlock, c->sms, 8), kBlock, 0, s>>>(states, (const u64 *)mult, n, t.table, t.slots,
                                                                                  t.meta, t.meta + 1, (int *)(t.meta + 3), t.max_unique);
         else
-            k_dedup_insert<false><<<grid_for(n, kBlock, c->sms, 8), kBlock, 0, s>>>(states, (const u64 *)mult, n, t.table, t.slots - 1,
+            k_dedup_insert<false><<<grid_for(n, kBlock, c->sms, 8), kBlock, 0, s>>>(states, (const u64 *)mult, n, t.table, t.slots,
                                                                                   t.meta, t.meta + 1, (int *)(t.meta + 3), t.max_unique);
         QK_CUDA(cudaGetLastError());
     }
@@ -644,10 +662,10 @@ int run_bfs_level_scatter(Call &call, const uint4 *parents, const uint64_t *mult
     if (n) {
         const unsigned grid = grid_for(n, kBlock, c->sms, 5);
         if (flags & 1)
-            k_bfs_expand_insert<true><<<grid, kBlock, 0, s>>>(parents, (const u64 *)mult, n, t.table, t.slots - 1, t.meta, t.meta + 1,
+            k_bfs_expand_insert<true><<<grid, kBlock, 0, s>>>(parents, (const u64 *)mult, n, t.table, t.slots, t.meta, t.meta + 1,
                                                              (int *)(t.meta + 3), t.max_unique, t.meta + 4);
         else
-            k_bfs_expand_insert<false><<<grid, kBlock, 0, s>>>(parents, (const u64 *)mult, n, t.table, t.slots - 1, t.meta, t.meta + 1,
+            k_bfs_expand_insert<false><<<grid, kBlock, 0, s>>>(parents, (const u64 *)mult, n, t.table, t.slots, t.meta, t.meta + 1,
                                                               (int *)(t.meta + 3), t.max_unique, t.meta + 4);
         QK_CUDA(cudaGetLastError());
     }
@@ -677,7 +695,7 @@ int run_inbox_merge(Call &call, const void *my_inbox, int world, size_t slots_pe
     for (int r = 0; r < world; ++r) {
         if (!h_counts[r]) continue;
         k_inbox_insert<<<grid_for((size_t)h_counts[r], kBlock, c->sms, 8), kBlock, 0, s>>>(
-            v.keys + (size_t)r * slots_per_src, v.mults + (size_t)r * slots_per_src, (size_t)h_counts[r], t.table, t.slots - 1,
+            v.keys + (size_t)r * slots_per_src, v.mults + (size_t)r * slots_per_src, (size_t)h_counts[r], t.table, t.slots,
             t.meta, t.meta + 1, (int *)(t.meta + 3), t.max_unique);
     }
     QK_CUDA(cudaGetLastError());
@@ -694,10 +712,10 @@ int run_book_level(Call &call, const uint4 *parents, size_t n, int color_swap, u
     if (rc != QK_OK) return rc;
     const unsigned grid = grid_for(n * 32, kBlock, c->sms, 8);
     if (color_swap)
-        k_book_expand_insert<true><<<grid, kBlock, 0, s>>>(parents, n, t.table, t.slots - 1, t.meta, t.meta + 1,
+        k_book_expand_insert<true><<<grid, kBlock, 0, s>>>(parents, n, t.table, t.slots, t.meta, t.meta + 1,
                                                           (int *)(t.meta + 3), t.max_unique, t.meta + 4);
     else
-        k_book_expand_insert<false><<<grid, kBlock, 0, s>>>(parents, n, t.table, t.slots - 1, t.meta, t.meta + 1,
+        k_book_expand_insert<false><<<grid, kBlock, 0, s>>>(parents, n, t.table, t.slots, t.meta, t.meta + 1,
                                                            (int *)(t.meta + 3), t.max_unique, t.meta + 4);
     QK_CUDA(cudaGetLastError());
     uint64_t st[5] = { 0, 0, 0, 0, 0 };

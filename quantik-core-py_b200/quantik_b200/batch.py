@@ -195,6 +195,13 @@ def canon_dedup(states, mult=None, color_swap: bool = False, cap: Optional[int] 
     return uniq.obj[:nu.value], um.obj[:nu.value]
 
 
+def level_margin(n_parents: int) -> float:
+    """Head-room of the next frontier's size estimate (children per parent of the previous depth x parents): the
+    ratio only falls as the board fills up, so big late levels need little; a level that still overflows is
+    repeated with a doubled table (QK_E_NOMEM)."""
+    return 1.6 if n_parents < (1 << 20) else 1.25
+
+
 def bfs_level(states, mult=None, color_swap: bool = False, cap: int = 1 << 20, sort_output: bool = True,
               device: Optional[int] = None):
     """One depth of the reference's SymmetryTable / opening-book BFS (game_stats.py:359-485), fused on the
@@ -240,7 +247,7 @@ def symmetry_table(max_depth: int, device: Optional[int] = None, on_device: bool
             rows.append([0, 0, 0, 0, 0])
             continue
         t0 = _time.perf_counter()
-        cap = int(min(64 * n, max(1 << 12, 1.6 * growth * n)))
+        cap = int(min(64 * n, max(1 << 12, level_margin(n) * growth * n)))
         nxt, nmult, st = bfs_level(frontier, mult, cap=cap, sort_output=sort_output, device=d)
         del frontier, mult
         frontier, mult = nxt, nmult
@@ -345,7 +352,7 @@ def opening_book_summary(depth: int, device: Optional[int] = None) -> dict:
     growth = 64.0
     for cur in range(depth + 1):
         n = int(frontier.shape[0])
-        cap = int(min(64 * max(n, 1), max(1 << 12, 1.6 * growth * n)))
+        cap = int(min(64 * max(n, 1), max(1 << 12, level_margin(n) * growth * n)))
         nxt, _deg, st = book_level(frontier, cap=cap, device=d) if n else (frontier, None, {"terminal": 0, "edges": 0})
         per_depth.append({"depth": cur, "positions": n, "terminal": st["terminal"], "edges": st["edges"]})
         growth = max(0.05, int(nxt.shape[0]) / max(n, 1))

@@ -209,7 +209,7 @@ def sharded_symmetry_table(max_depth: int, device: Optional[int] = None, group=N
         stats = np.zeros(7, np.int64)
         kids, kmult = np.zeros((0, 8), np.uint16), np.zeros(0, np.uint64)
         if n:
-            cap = int(min(64 * n, max(1 << 12, 1.6 * growth * n)))      # bfs_level doubles it when it was too small
+            cap = int(min(64 * n, max(1 << 12, B.level_margin(n) * growth * n)))      # bfs_level doubles it when it was too small
             kids, kmult, st = bfs_fn(frontier, mult, cap=cap, sort_output=False, device=d)
             growth = max(0.05, int(kids.shape[0]) / n)
             stats[:5] = [st["total_moves"], st["line_wins_p0"], st["line_wins_p1"], st["blocked_p0"], st["blocked_p1"]]
@@ -343,8 +343,8 @@ def fused_symmetry_table(max_depth: int, device: int = 0, group=None, inboxes: O
     for depth in range(1, max_depth + 1):
         k = depth % 2
         n = int(frontier.shape[0])
-        local_cap = int(min(64 * max(n, 1), max(1 << 12, 1.6 * growth * n)))
-        want = _max_over_ranks(int(1.25 * local_cap / 1.6 / world) + 4096, d, group)
+        local_cap = int(min(64 * max(n, 1), max(1 << 12, B.level_margin(n) * growth * n)))
+        want = _max_over_ranks(int(1.25 * local_cap / B.level_margin(n) / world) + 4096, d, group)
         inboxes.ensure(want)
         while True:
             failed = False

@@ -39,7 +39,7 @@ def timed(fn):
     return out, float(dt.item())
 
 
-D.sharded_symmetry_table(6, device=local)                       # warm-up: context, pool, NCCL channels
+D.sharded_symmetry_table(depth, device=local)                   # warm-up: context, memory pool, NCCL channels
 rows, t_bfs = timed(lambda: D.sharded_symmetry_table(depth, device=local))
 # the same with the exchange fused into the merge kernels (peer stores into the owners' inboxes)
 boxes = D.PeerInboxes(1 << 14, local, copies=2)

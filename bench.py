@@ -299,7 +299,8 @@ def main():
         extra["perft_depth7_nodes_per_s"] = float(p7["nodes"][1:].sum()) / dt7
         extra["perft_depth7_ms"] = dt7 * 1e3
         # config 5 / SURVEY 8f-1: the complete canonical game tree (depth 1..16) with the fused BFS
-        B.symmetry_table(6, device=dev)
+        B.symmetry_table(16, device=dev)               # warm-up: grows the stream-ordered memory pool once
+        torch.cuda.synchronize()
         t0 = time.perf_counter()
         rows = B.symmetry_table(16, device=dev)
         dt = time.perf_counter() - t0
@@ -324,6 +325,17 @@ def main():
         extra["canonical_frac_int_issue"] = kps * OPS_PER_KEY / nominal_peak
         extra["canonical_hbm_gbs"] = kps * 32 / 1e9
         del states, out
+        # config 3, merge part: canonicalise + merge equal classes + sum multiplicities over 2^24 mid-game positions
+        pos = B.random_roots(1 << 24, seed=SEED, min_plies=3, span=6, device=dev, as_torch=True)
+        B.canon_dedup(pos, None, sort_output=False)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(5):
+            u, _m = B.canon_dedup(pos, None, sort_output=False)
+        torch.cuda.synchronize()
+        extra["canon_dedup_keys_per_s"] = 5 * (1 << 24) / (time.perf_counter() - t0)
+        extra["canon_dedup_distinct"] = int(u.shape[0])
+        del pos, u, _m
         # config 4: 65 536 mid-game roots x 1024 rollouts
         roots = B.random_roots(65536, seed=SEED, device=dev, as_torch=True)
         B.playouts(roots, 1024, SEED)

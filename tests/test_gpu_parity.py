@@ -442,6 +442,27 @@ def test_abi_error_paths_and_degenerate_sizes():
         B.apply_moves(s, np.zeros(3, np.uint8))
     with pytest.raises(ValueError):
         B.movegen_masks(np.zeros(7, np.uint16))
+    # the exchange entry points: argument checks, and an empty share still publishes its (zero) counts
+    import ctypes
+    import torch
+    box = torch.full((B.inbox_bytes(2, 64),), 0xFF, dtype=torch.uint8, device="cuda:0")
+    ptrs = (ctypes.c_void_p * 2)(box.data_ptr(), box.data_ptr())
+    sent = np.full(2, 7, np.uint64)
+    assert lib.qk_canon_dedup_scatter(s.ctypes.data, None, 4, 0, ptrs, 17, 0, 64, sent.ctypes.data, 0, None) == -1   # world > 16
+    assert lib.qk_canon_dedup_scatter(s.ctypes.data, None, 4, 0, ptrs, 2, 2, 64, sent.ctypes.data, 0, None) == -1    # rank >= world
+    assert lib.qk_canon_dedup_scatter(s.ctypes.data, None, 4, 0, None, 2, 0, 64, sent.ctypes.data, 0, None) == -1    # no inboxes
+    assert lib.qk_canon_dedup_scatter(s.ctypes.data, None, 4, 0, ptrs, 2, 0, 0, sent.ctypes.data, 0, None) == -1     # empty regions
+    nb = ctypes.c_size_t(0)
+    assert lib.qk_inbox_bytes(0, 64, ctypes.byref(nb)) == -1 and lib.qk_inbox_bytes(2, 64, None) == -1
+    one = (ctypes.c_void_p * 1)(box.data_ptr())
+    assert B.canon_dedup_scatter(np.zeros((0, 8), np.uint16), None, [box.data_ptr()], 0, 64).tolist() == [0]
+    assert int(box[:8].view(torch.int64).item()) == 0
+    u_, m_ = B.inbox_merge(box.data_ptr(), 1, 64, 1)
+    assert len(u_) == 0 and len(m_) == 0
+    assert B.canon_dedup_scatter(s, None, [box.data_ptr()], 0, 64).tolist() == [1]          # four empty boards: one class
+    u_, m_ = B.inbox_merge(box.data_ptr(), 1, 64, 1)
+    assert u_.cpu().numpy().view(np.uint16).tolist() == [[0] * 8] and m_.tolist() == [4]
+    del one
     # zero-sized work is fine everywhere
     e = np.zeros((0, 8), np.uint16)
     r = B.playouts(e, 16)

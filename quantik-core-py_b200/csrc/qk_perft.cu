@@ -17,6 +17,7 @@
 // parent come from popcounts (qk_perft_core.cuh).
 #include "qk_common.cuh"
 #include "qk_perft_core.cuh"
+#include "qk_playout_core.cuh"     // SquareLut: scope / square masks of one square
 
 #include <stdlib.h>
 
@@ -153,8 +154,28 @@ __global__ void __launch_bounds__(kBlock) k_perft_leaf(const uint4 *__restrict__
 }
 
 // ------------------------------------------------------------------ warp-cooperative DFS
+// move / winning-move counts of a leaf parent from its PARENT's data: `legal` = the squares its mover could have
+// played one ply earlier (legal_masks of the parent for the player NOT to move there), `action` = the move that
+// was made.  The new piece takes its square away from every shape and its row / column / zone away from its own
+// shape (move.py:169-196); nothing else changes for the other player.
+__device__ __forceinline__ void leaf_counts_delta(const State4 &child, uint2 legal, int action, const SquareLut *lut,
+                                                  int &n_moves, int &n_wins)
+{
+    const SquareLut e = lut[action & 15];
+    const uint32_t lane = (action & 16) ? 0xFFFF0000u : 0x0000FFFFu;
+    const uint32_t own = e.scope2 & lane;                                  // the square itself is inside its scope
+    const uint32_t lo = legal.x & ~(e.bit2 | ((action & 32) ? 0u : own));
+    const uint32_t hi = legal.y & ~(e.bit2 | ((action & 32) ? own : 0u));
+    uint32_t wab, wcd;
+    winning_squares(child, wab, wcd);
+    n_moves = popc(lo) + popc(hi);
+    n_wins = popc(lo & wab) + popc(hi & wcd);
+}
+
 struct WarpScratch {
     uint4 queue[96];              // leaf parents waiting for a full warp (<= 31 + 64)
+    uint2 queue_legal[96];        // ... the legal squares of THEIR mover at their parent (before the parent's move)
+    unsigned char queue_action[96];   // ... and the move that made them
     uint4 frame_state[QK_MAX_DEPTH];
     u64 frame_mask[QK_MAX_DEPTH]; // non-winning children of frame_state still to visit
     u64 cnt[5 * kRows];           // this warp's share of the counters, weighted by multiplicity
@@ -164,6 +185,9 @@ __global__ void __launch_bounds__(kBlock) k_perft_dfs(const uint4 *__restrict__ 
                                                        int d0, int depth, u64 *__restrict__ next_item, u64 *__restrict__ counters)
 {
     __shared__ WarpScratch s_scratch[kWarps];
+    __shared__ __align__(16) SquareLut s_lut[16];
+    if (threadIdx.x < 16) s_lut[threadIdx.x] = square_lut((int)threadIdx.x);
+    __syncthreads();
     WarpScratch &ws = s_scratch[threadIdx.x >> 5];
     const unsigned lane = threadIdx.x & 31u;
     const uint32_t lt = (1u << lane) - 1u;
@@ -204,16 +228,30 @@ __global__ void __launch_bounds__(kBlock) k_perft_dfs(const uint4 *__restrict__ 
                         ws.cnt[(1 + mover) * kRows + d + 1] += (u64)(popc(lo & wab) + popc(hi & wcd)) * m;   // :411-415
                     }
                     if (node_rem == 2) {
-                        // children are leaf parents: lane l writes children l and l+32 into the queue
+                        // children are leaf parents: lane l writes children l and l+32 into the queue, together
+                        // with what the OTHER player could play here -- a child's legal moves are those minus
+                        // the new piece's square and scope (leaf_counts_delta), 8 operations instead of 46
+                        uint32_t ylo, yhi;
+                        legal_masks(node, mover ^ 1, ylo, yhi);
+                        const uint2 ylegal = make_uint2(ylo, yhi);
                         const int c_lo = popc(nl);
-                        if ((nl >> lane) & 1u) ws.queue[qn + popc(nl & lt)] = to_u4(apply_action(node, mover, (int)lane));
-                        if ((nh >> lane) & 1u) ws.queue[qn + c_lo + popc(nh & lt)] = to_u4(apply_action(node, mover, 32 + (int)lane));
+                        if ((nl >> lane) & 1u) {
+                            const int at = qn + popc(nl & lt);
+                            ws.queue[at] = to_u4(apply_action(node, mover, (int)lane));
+                            ws.queue_legal[at] = ylegal; ws.queue_action[at] = (unsigned char)lane;
+                        }
+                        if ((nh >> lane) & 1u) {
+                            const int at = qn + c_lo + popc(nh & lt);
+                            ws.queue[at] = to_u4(apply_action(node, mover, 32 + (int)lane));
+                            ws.queue_legal[at] = ylegal; ws.queue_action[at] = (unsigned char)(32 + lane);
+                        }
                         qn += c_lo + popc(nh);
                         __syncwarp();
                         while (qn >= 32) {
                             qn -= 32;
                             int nm, nw;
-                            leaf_parent_counts_for(to_state(ws.queue[qn + lane]), leaf_mover, nm, nw);
+                            leaf_counts_delta(to_state(ws.queue[qn + lane]), ws.queue_legal[qn + lane], ws.queue_action[qn + lane],
+                                              s_lut, nm, nw);
                             leaf_nodes += nm; leaf_wins += nw; leaf_blocked += nm == 0;
                             __syncwarp();
                         }
@@ -239,7 +277,7 @@ __global__ void __launch_bounds__(kBlock) k_perft_dfs(const uint4 *__restrict__ 
         // ---- drain the queue, fold this item's leaf tallies into the warp counters
         if ((int)lane < qn) {
             int nm, nw;
-            leaf_parent_counts_for(to_state(ws.queue[lane]), leaf_mover, nm, nw);
+            leaf_counts_delta(to_state(ws.queue[lane]), ws.queue_legal[lane], ws.queue_action[lane], s_lut, nm, nw);
             leaf_nodes += nm; leaf_wins += nw; leaf_blocked += nm == 0;
         }
         __syncwarp();
@@ -381,6 +419,244 @@ __global__ void __launch_bounds__(kLaneWarps * 32) k_perft_lane(const uint4 *__r
         if (ws.acc[k]) atomicAdd(counters + k, ws.acc[k]);
 }
 
+// ------------------------------------------------------------------ lane-parallel DFS with a dealt last level
+// k_perft_lane's walk (one item per lane, frames = masks of unvisited children), except that the LAST interior
+// level is not walked: when a lane evaluates a node two plies above the target, its non-winning children -- the
+// leaf parents, 96 % of all nodes that are ever evaluated in a wide tree -- are listed in a warp-shared queue
+// together with those of the other lanes and dealt out 32 per round.  So the dominant work runs with full warps
+// whatever the fan-out of the individual nodes, and each leaf parent is evaluated from its parent's data
+// (leaf_counts_delta) instead of from scratch.  Interior nodes count unweighted into one packed word per
+// (level, lane); the words are folded into the warp's weighted counters by warp-wide sums when a lane finishes
+// its item (no shared-memory atomics: 64-bit ones are CAS loops and every lane would hit the same row).
+// The target depth accumulates weighted in registers.
+static constexpr int kTileWarps = 4;                  // 128 threads per CTA
+static constexpr int kTileMaxRem = kLaneFrames + 2;   // frames exist for nodes >= 3 plies above the target
+static constexpr unsigned kTileQueue = 1024;          // ring of dealt entries: < 32 left over + what one pass adds
+static constexpr unsigned kTileParents = 64;          // ring of parent records: <= 31 still referenced + 32 new
+static constexpr unsigned kTileFlushEvery = 4000;     // evaluations per lane before its packed counters could overflow
+
+// per-warp shared memory; the two per-level arrays are sized for the job (dynamic shared memory), so shallow
+// remainders -- the wide, early part of the game -- run at a higher occupancy
+struct TileScratch {
+    unsigned short queue[kTileQueue];                 // ring: (mover << 12 | parent record << 6 | action) of a dealt leaf parent
+    uint4 pstate[kTileParents];                       // ring of parent records: the node two plies above the target ...
+    uint2 plegal[kTileParents];                       // ... what the player NOT to move there could play
+    u64 pmult[kTileParents];                          // ... and its item's multiplicity
+    u64 acc[5 * kRows];                               // this warp's weighted share of the counters
+    u64 levels[1][32];                                // frame[rem0 - 1][32]: masks of unvisited children per level and lane,
+                                                      // then cnt[rem0 - 1][32]: moves (bits 0-25) | winning moves (26-51) | blocked (52-63)
+};
+static size_t tile_warp_bytes(int rem0) { return (sizeof(TileScratch) - 256 + (size_t)(2 * rem0 - 2) * 256 + 15) / 16 * 16; }
+
+__global__ void __launch_bounds__(kTileWarps * 32) k_perft_tile(const uint4 *__restrict__ items, const u64 *__restrict__ mult,
+                                                                 u64 n_items, int d0, int depth, u64 *__restrict__ next_item,
+                                                                 u64 *__restrict__ counters)
+{
+    extern __shared__ __align__(16) unsigned char s_dyn[];
+    __shared__ __align__(16) SquareLut s_lut[16];
+    if (threadIdx.x < 16) s_lut[threadIdx.x] = square_lut((int)threadIdx.x);
+    const int rem0 = depth - d0;          // 2 <= rem0 <= kTileMaxRem
+    const size_t warp_bytes = (sizeof(TileScratch) - 256 + (size_t)(2 * rem0 - 2) * 256 + 15) / 16 * 16;
+    TileScratch &ws = *reinterpret_cast<TileScratch *>(s_dyn + (threadIdx.x >> 5) * warp_bytes);
+    u64 (*const frame)[32] = ws.levels;                 // [rem0 - 1][32]
+    u64 (*const cnt_packed)[32] = ws.levels + (rem0 - 1); // [rem0 - 1][32]
+    const unsigned lane = threadIdx.x & 31u;
+    for (int k = lane; k < 5 * kRows; k += 32) ws.acc[k] = 0;
+    for (int r = 0; r <= rem0 - 2; ++r) cnt_packed[r][lane] = 0;
+    __syncthreads();
+
+    State4 cur = { 0, 0, 0, 0 };          // position of the top frame
+    int sp = -1;                          // top frame (= plies below the item); -1: no item
+    int parity = 0;                       // player to move at the item
+    u64 m = 0;                            // multiplicity of the item
+    bool more = true;                     // the global queue may still have items
+    unsigned since_flush = 0;
+    uint32_t q_head = 0, q_tail = 0, q_parents = 0;                       // rings (warp-uniform running counters)
+    // Dealing costs the whole warp a fixed amount per iteration in which some lane gives (the other player's legal
+    // squares, the scan, the list) and saves per leaf parent; late in the game nodes two plies above the target have
+    // fewer than one child on average, and then the lanes walk the last level themselves (as k_perft_lane does).
+    // Decided per warp every 32 iterations: deal while the busy lanes saw at least one such child per iteration each
+    // (measured on the 10 946 depth-4 classes: to depth 12 dealing 11.5 s vs walking 15.6 s, to depth 16 165 s vs 128 s).
+    bool deal = true;
+    uint32_t seen_kids = 0, seen_busy = 0, seen_iters = 0;
+    u64 acc_nodes = 0, acc_w0 = 0, acc_w1 = 0, acc_b0 = 0, acc_b1 = 0;    // the target depth, weighted, per lane
+
+    for (;;) {
+        // ---- idle lanes take the next items
+        State4 node = cur;
+        int level = sp + 1;
+        bool have = sp >= 0;
+        const unsigned idle = __ballot_sync(kFull, sp < 0);
+        if (idle && more) {
+            u64 base = 0;
+            if (lane == (unsigned)(__ffs((int)idle) - 1)) base = atomicAdd(next_item, (u64)__popc(idle));
+            base = __shfl_sync(kFull, base, __ffs((int)idle) - 1);
+            if (sp < 0) {
+                const u64 idx = base + __popc(idle & ((1u << lane) - 1u));
+                if (idx < n_items) {
+                    node = to_state(__ldg(items + idx));
+                    m = mult[idx];
+                    parity = piece_balance(node);
+                    level = 0;
+                    have = true;
+                }
+            }
+            more = base + __popc(idle) < n_items;
+        }
+        if (!__any_sync(kFull, have)) break;
+
+        uint32_t give_lo = 0, give_hi = 0;       // this lane's leaf parents for the dealt stage
+        uint32_t give_ylo = 0, give_yhi = 0;
+        int give_mover = 0;
+        uint32_t kids = 0;                       // children of a node two plies above the target (either mode)
+        bool flush = false;
+        if (have) {
+            if (level > 0) {   // descend: the in-flight child is the lowest set bit of the parent's mask
+                const u64 fm = frame[sp][lane];
+                node = apply_action(cur, (parity + sp) & 1, __ffsll((long long)fm) - 1);
+            }
+            // ---- evaluate the node: its moves, its winning moves (game_stats.py:384-424)
+            const int mover = (parity + level) & 1;
+            uint32_t lo, hi, wab, wcd;
+            legal_masks(node, mover, lo, hi);
+            winning_squares(node, wab, wcd);
+            const int n_moves = popc(lo) + popc(hi);
+            const int n_wins = popc(lo & wab) + popc(hi & wcd);
+            const uint32_t nl = lo & ~wab, nh = hi & ~wcd;
+            const int rem = rem0 - level;
+            bool ret = true;                                     // nothing (more) to walk below this node
+            if (rem == 1) {
+                // a leaf parent walked by its own lane (narrow trees): the target depth, weighted, in registers
+                acc_nodes += (u64)n_moves * m;
+                const u64 w = (u64)n_wins * m, b = n_moves ? 0ull : m;
+                if (mover) { acc_w1 += w; acc_b1 += b; } else { acc_w0 += w; acc_b0 += b; }
+            } else {
+                cnt_packed[level][lane] += (u64)n_moves | ((u64)n_wins << 26) | ((u64)(n_moves == 0) << 52);
+                ++since_flush;
+                if (rem == 2) kids = (uint32_t)(popc(nl) + popc(nh));
+                if (nl | nh) {
+                    if (rem >= 3 || !deal) {
+                        cur = node; sp = level; ret = false;     // push
+                        frame[level][lane] = ((u64)nh << 32) | nl;
+                    } else {
+                        // two plies above the target: hand the children to the dealt stage
+                        legal_masks(node, mover ^ 1, give_ylo, give_yhi);
+                        give_lo = nl; give_hi = nh; give_mover = mover;
+                    }
+                }
+            }
+            if (ret) {
+                if (level == 0) {
+                    sp = -1;                                     // item finished
+                } else {
+                    // return from the child, then from every frame it exhausts
+                    u64 fm = frame[sp][lane];
+                    fm &= fm - 1;
+                    frame[sp][lane] = fm;
+                    while (fm == 0) {
+                        if (--sp < 0) break;
+                        fm = frame[sp][lane];
+                        cur = clear_square(cur, __ffsll((long long)fm) - 1);
+                        fm &= fm - 1;
+                        frame[sp][lane] = fm;
+                    }
+                }
+            }
+            flush = sp < 0 || since_flush >= kTileFlushEvery;
+        }
+        seen_kids += (uint32_t)__reduce_add_sync(kFull, kids);
+        seen_busy += (uint32_t)__popc(__ballot_sync(kFull, have));
+        if (++seen_iters == 32) { deal = seen_kids >= seen_busy; seen_kids = 0; seen_busy = 0; seen_iters = 0; }
+        // ---- the dealt stage: the givers' leaf parents join a ring shared by the warp; full rounds of 32 are
+        //      evaluated at once, fewer than 32 stay for the next iteration.  Entries name a parent RECORD (not a
+        //      lane), so they survive their lane moving on.
+        const uint32_t cnt_all = (uint32_t)(popc(give_lo) + popc(give_hi));
+        const unsigned givers = __ballot_sync(kFull, cnt_all != 0);
+        if (givers) {
+            const uint32_t rec = (q_parents + (uint32_t)__popc(givers & ((1u << lane) - 1u))) & (kTileParents - 1);
+            if (cnt_all) {
+                ws.pstate[rec] = to_u4(node);
+                ws.plegal[rec] = make_uint2(give_ylo, give_yhi);
+                ws.pmult[rec] = m;
+            }
+            q_parents += (uint32_t)__popc(givers);
+            const uint32_t n_all = (uint32_t)__reduce_add_sync(kFull, cnt_all);
+            const int n_pass = n_all + (q_tail - q_head) <= kTileQueue ? 1 : 4;     // 8 lanes x 64 children always fit
+            for (int pass = 0; pass < n_pass; ++pass) {
+                const uint32_t cnt = (n_pass == 1 || (int)(lane >> 3) == pass) ? cnt_all : 0u;
+                uint32_t incl = cnt;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(kFull, incl, o); if (lane >= (unsigned)o) incl += t; }
+                if (cnt) {
+                    uint32_t at = q_tail + incl - cnt;
+                    const uint32_t tag = ((uint32_t)give_mover << 12) | (rec << 6);
+                    for (uint32_t w = give_lo; w; w &= w - 1) ws.queue[at++ & (kTileQueue - 1)] = (unsigned short)(tag | (uint32_t)(__ffs((int)w) - 1));
+                    for (uint32_t w = give_hi; w; w &= w - 1) ws.queue[at++ & (kTileQueue - 1)] = (unsigned short)(tag | (uint32_t)(32 + __ffs((int)w) - 1));
+                }
+                q_tail += __shfl_sync(kFull, incl, 31);
+                __syncwarp();
+                while (q_tail - q_head >= 32) {
+                    const uint32_t e = ws.queue[(q_head + lane) & (kTileQueue - 1)], pr = (e >> 6) & (kTileParents - 1), xm = e >> 12;
+                    const int action = (int)(e & 63u);
+                    const State4 child = apply_action(to_state(ws.pstate[pr]), (int)xm, action);
+                    const u64 pm = ws.pmult[pr];
+                    int nm, nw;
+                    leaf_counts_delta(child, ws.plegal[pr], action, s_lut, nm, nw);
+                    acc_nodes += (u64)nm * pm;
+                    const u64 w = (u64)nw * pm, b = nm ? 0ull : pm;   // the leaf parent's mover is the OTHER player
+                    if (xm) { acc_w0 += w; acc_b0 += b; } else { acc_w1 += w; acc_b1 += b; }
+                    q_head += 32;
+                }
+                __syncwarp();
+            }
+        }
+        // ---- fold finished lanes' packed counters into the warp's weighted counters (warp-wide sums)
+        if (__any_sync(kFull, flush)) {
+            for (int r = 0; r <= rem0 - 2; ++r) {
+                const u64 packed = flush ? cnt_packed[r][lane] : 0ull;
+                if (!__any_sync(kFull, packed != 0)) continue;
+                if (flush) cnt_packed[r][lane] = 0;
+                const u64 c_nodes = (packed & 0x3FFFFFFull) * m, c_wins = ((packed >> 26) & 0x3FFFFFFull) * m, c_blk = (packed >> 52) * m;
+                const bool p1 = ((parity + r) & 1) != 0;         // the player to move at this level
+                const u64 s_nodes = warp_sum(c_nodes);
+                const u64 s_w0 = warp_sum(p1 ? 0ull : c_wins), s_w1 = warp_sum(p1 ? c_wins : 0ull);
+                const u64 s_b0 = warp_sum(p1 ? 0ull : c_blk), s_b1 = warp_sum(p1 ? c_blk : 0ull);
+                if (lane == 0) {
+                    const int d = d0 + r;
+                    ws.acc[0 * kRows + d + 1] += s_nodes;                                      // :401
+                    ws.acc[1 * kRows + d + 1] += s_w0; ws.acc[2 * kRows + d + 1] += s_w1;      // :411-415
+                    ws.acc[3 * kRows + d] += s_b0; ws.acc[4 * kRows + d] += s_b1;              // :426-443
+                }
+            }
+            if (flush) since_flush = 0;
+        }
+    }
+    // ---- what is left in the ring (< 32 entries)
+    if (lane < q_tail - q_head) {
+        const uint32_t e = ws.queue[(q_head + lane) & (kTileQueue - 1)], pr = (e >> 6) & (kTileParents - 1), xm = e >> 12;
+        const int action = (int)(e & 63u);
+        const State4 child = apply_action(to_state(ws.pstate[pr]), (int)xm, action);
+        const u64 pm = ws.pmult[pr];
+        int nm, nw;
+        leaf_counts_delta(child, ws.plegal[pr], action, s_lut, nm, nw);
+        acc_nodes += (u64)nm * pm;
+        const u64 w = (u64)nw * pm, b = nm ? 0ull : pm;
+        if (xm) { acc_w0 += w; acc_b0 += b; } else { acc_w1 += w; acc_b1 += b; }
+    }
+    acc_nodes = warp_sum(acc_nodes); acc_w0 = warp_sum(acc_w0); acc_w1 = warp_sum(acc_w1);
+    acc_b0 = warp_sum(acc_b0); acc_b1 = warp_sum(acc_b1);
+    if (lane == 0) {
+        ws.acc[0 * kRows + depth] += acc_nodes;
+        ws.acc[1 * kRows + depth] += acc_w0;
+        ws.acc[2 * kRows + depth] += acc_w1;
+        ws.acc[3 * kRows + depth - 1] += acc_b0;
+        ws.acc[4 * kRows + depth - 1] += acc_b1;
+    }
+    __syncwarp();
+    for (int k = lane; k < 5 * kRows; k += 32)
+        if (ws.acc[k]) atomicAdd(counters + k, ws.acc[k]);
+}
+
 // ------------------------------------------------------------------ host driver
 int run_perft(Call &call, const uint4 *roots, const uint64_t *mult, size_t n_roots, int depth, uint64_t *host_out)
 {
@@ -401,12 +677,14 @@ int run_perft(Call &call, const uint4 *roots, const uint64_t *mult, size_t n_roo
     QK_CUDA(cudaMemcpyAsync(&n_cur, d_count, sizeof(u64), cudaMemcpyDeviceToHost, s));
     QK_CUDA(cudaStreamSynchronize(s));
 
-    // Widen level by level until there is enough independent work, then walk depth-first:
-    //  * shallow, wide remainders (<= 3 plies from early positions): one item per WARP (k_perft_dfs)
-    //  * anything deeper: one item per LANE (k_perft_lane), which needs many more items
-    const u64 want_warp_items = (u64)c->sms * 4 * kWarps * 8;
-    const u64 want_lane_items = (u64)c->sms * 2048 * 8;
-    const char *force = getenv("QK_PERFT_KERNEL");              // "warp" / "lane": benchmarking aid
+    // Widen level by level until every lane can have its own items, then walk depth-first with k_perft_tile
+    // (one item per lane, last level dealt out to full warps).  Measured from the empty board, in ms, for
+    // tile / warp-per-item / plain lane-per-item: depth 6 1.7 / 3.5 / 4.0, depth 7 38 / 105 / 62, depth 8 835 / 2688 / 1290.
+    u64 want_warp_items = (u64)c->sms * 4 * kWarps * 8;
+    u64 want_lane_items = (u64)c->sms * 2048 * 8;
+    const char *force = getenv("QK_PERFT_KERNEL");              // "tile" / "warp" / "lane": benchmarking aid
+    if (const char *mi = getenv("QK_PERFT_MIN_ITEMS"))          // testing aid: start the depth-first kernels on small frontiers
+        want_warp_items = want_lane_items = strtoull(mi, nullptr, 10);
     int d = 0;
     while (n_cur > 0 && d < depth) {
         const int rem = depth - d;
@@ -415,21 +693,38 @@ int run_perft(Call &call, const uint4 *roots, const uint64_t *mult, size_t n_roo
             QK_CUDA(cudaGetLastError());
             break;
         }
-        // lane kernel as soon as there are enough items for every lane; the warp kernel only for the last
-        // <= 3 plies of a frontier that is still too small for that (measured: perft 6 from the empty board
-        // 3.7 ms warp vs 4.1 ms lane, perft 7 111 ms vs 65 ms, perft 8 2.68 s vs 1.36 s)
         const bool can_lane = rem <= kLaneFrames + 1;
+        const bool can_tile = rem >= 2 && rem <= kTileMaxRem;
         const bool too_big = n_cur * 64 > (1ull << 28);        // next frontier would not be worth materialising
-        bool use_lane = can_lane && (n_cur >= want_lane_items || too_big);
-        bool use_warp = !use_lane && ((rem <= 3 && n_cur >= want_warp_items) || too_big);
-        if (force) {
-            use_lane = force[0] == 'l' && can_lane && (n_cur >= want_lane_items || too_big);
-            use_warp = force[0] != 'l' && (n_cur >= want_warp_items || too_big);
+        // As soon as every lane can have an item: the lane walk with the dealt last level (k_perft_tile) while the
+        // target lies in the wide part of the game, the plain lane walk for the narrow end (measured below the
+        // 10 946 depth-4 classes, tile / lane: to depth 12 11.7 / 15.6 s, to depth 14 108 / 91 s, to depth 16 147 / 128 s)
+        const bool go = n_cur >= want_lane_items || too_big;
+        bool use_tile = false, use_lane = false;
+        if (go && !force) {
+            uint4 first;
+            QK_CUDA(cudaMemcpyAsync(&first, cur_s, sizeof first, cudaMemcpyDeviceToHost, s));
+            QK_CUDA(cudaStreamSynchronize(s));
+            const int target_pieces = __builtin_popcount(first.x) + __builtin_popcount(first.y) + __builtin_popcount(first.z) +
+                                      __builtin_popcount(first.w) + rem;
+            use_tile = can_tile && target_pieces <= 12;
+            use_lane = !use_tile && can_lane;
+            use_tile = use_tile || (!use_lane && can_tile);
         }
-        const bool lane_mode = use_lane;
-        if (use_lane || use_warp) {
+        bool use_warp = go && !use_tile && !use_lane;           // (cannot happen for depth <= 16; the warp kernel is kept for A/B runs)
+        if (force) {                                            // benchmarking aid: the two older kernels
+            use_tile = force[0] == 't' && can_tile && (n_cur >= want_lane_items || too_big);
+            use_lane = force[0] == 'l' && can_lane && (n_cur >= want_lane_items || too_big);
+            use_warp = force[0] == 'w' && (n_cur >= want_warp_items || too_big);
+        }
+        if (use_tile || use_lane || use_warp) {
             QK_CUDA(cudaMemsetAsync(d_next, 0, sizeof(u64), s));
-            if (lane_mode) {
+            if (use_tile) {
+                int per_sm = 0;
+                const size_t smem = kTileWarps * tile_warp_bytes(rem);
+                QK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_perft_tile, kTileWarps * 32, smem));
+                k_perft_tile<<<c->sms * (per_sm > 0 ? per_sm : 1), kTileWarps * 32, smem, s>>>(cur_s, cur_m, n_cur, d, depth, d_next, d_ctr);
+            } else if (use_lane) {
                 int per_sm = 0;
                 QK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_perft_lane, kLaneWarps * 32, 0));
                 k_perft_lane<<<c->sms * (per_sm > 0 ? per_sm : 1), kLaneWarps * 32, 0, s>>>(cur_s, cur_m, n_cur, d, depth, d_next, d_ctr);

@@ -13,7 +13,7 @@ import quantik_b200 as Q  # noqa: E402
 e = np.zeros((1, 8), np.uint16)
 Q.perft(e, 4)
 for depth in (6, 7, 8):
-    for mode in ("warp", "lane", "auto"):
+    for mode in ("tile", "warp", "lane", "auto"):
         if mode == "auto":
             os.environ.pop("QK_PERFT_KERNEL", None)
         else:

@@ -329,8 +329,10 @@ def test_perft_lane_kernel_matches_warp_kernel_and_oracle(monkeypatch):
     mult = np.arange(1, 65, dtype=np.uint64)
     mid = O.make_roots(3000, seed=17, min_plies=4, span=5)
     ref6 = None
-    for mode in ("warp", "lane"):
-        monkeypatch.setenv("QK_PERFT_KERNEL", mode)
+    for mode in ("tile", "warp", "lane", "tile-small"):
+        monkeypatch.setenv("QK_PERFT_KERNEL", mode[:4])
+        if mode == "tile-small":        # the depth-first kernel straight on the 64 mixed-parity roots: every frame depth
+            monkeypatch.setenv("QK_PERFT_MIN_ITEMS", "1")
         p = B.perft(e, 6)
         assert B.symmetry_table_rows(p) == PUBLISHED, mode
         for depth in (2, 3, 5, 7):
@@ -342,6 +344,7 @@ def test_perft_lane_kernel_matches_warp_kernel_and_oracle(monkeypatch):
         for k in g:
             assert np.array_equal(g[k], ref6[k]), (mode, k)
     monkeypatch.delenv("QK_PERFT_KERNEL")
+    monkeypatch.delenv("QK_PERFT_MIN_ITEMS")
     # the automatic choice (lane kernel below wide frontiers) on a deep job: depth-4 classes + 6 = depth 10
     d = _npz("depth4_canonical.npz")
     p = B.perft(d["states"], 6, d["mult"])

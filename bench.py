@@ -40,7 +40,7 @@ SEED = 0x5155414E54494B31
 # incremental formulation existed): 60 lane-ops per ply, of which 36 issue to the 64-lane ALU pipe
 # and 24 to the FMA-heavy pipe (IMAD; IMAD.WIDE counts double); 11.08 plies per empty-board playout;
 # 118 per visited perft leaf parent = 4.4 per counted node at depth 6; 304 per canonical key.
-OPS_PER_PLY, ALU_OPS_PER_PLY, PLIES_PER_PLAYOUT, OPS_PER_NODE, OPS_PER_KEY = 60.0, 36.0, 11.08, 3.4, 304.0
+OPS_PER_PLY, ALU_OPS_PER_PLY, PLIES_PER_PLAYOUT, OPS_PER_NODE, OPS_PER_KEY = 60.0, 36.0, 11.08, 2.5, 304.0
 OPS_PER_PLAYOUT = OPS_PER_PLY * PLIES_PER_PLAYOUT
 
 

@@ -420,6 +420,35 @@ __global__ void __launch_bounds__(kLaneWarps * 32) k_perft_lane(const uint4 *__r
 }
 
 // ------------------------------------------------------------------ lane-parallel DFS with a dealt last level
+// per-square masks for the evaluation of a leaf parent from its parent's data, replicated in both 16-bit lanes
+struct __attribute__((aligned(16))) TileLut { uint32_t scope2, bit2, row2, zone2, col2, pad0, pad1, pad2; };
+__device__ __forceinline__ TileLut tile_lut(int p)
+{
+    const SquareLut e = square_lut(p);
+    TileLut t = { e.scope2, e.bit2, 0x00010001u << (p & 12), 0x00010001u << (p & 10), 0x00010001u << (p & 3), 0u, 0u, 0u };
+    return t;
+}
+// move / winning-move counts of a leaf parent from its PARENT: `legal` = what its mover could have played one ply
+// earlier, `pres` = the parent's line presence, `action` = the move that was made.  The new piece takes its square
+// away from every shape and its scope away from its own shape (move.py:169-196), and adds its shape to its row,
+// zone and column; the child itself is never materialised.
+__device__ __forceinline__ void leaf_counts_from_parent(uint2 legal, Presence pres, int action, const TileLut *lut,
+                                                        int &n_moves, int &n_wins)
+{
+    const uint4 e = *reinterpret_cast<const uint4 *>(lut + (action & 15));                  // scope2, bit2, row2, zone2
+    const uint32_t col2 = lut[action & 15].col2;
+    const uint32_t lane = (action & 16) ? 0xFFFF0000u : 0x0000FFFFu;
+    const uint32_t in_lo = (action & 32) ? 0u : lane, in_hi = lane ^ in_lo;                 // lane of the new piece's shape
+    const uint32_t lo = legal.x & ~(e.y | (e.x & in_lo)), hi = legal.y & ~(e.y | (e.x & in_hi));
+    pres.r01 |= e.z & in_lo; pres.r23 |= e.z & in_hi;
+    pres.z01 |= e.w & in_lo; pres.z23 |= e.w & in_hi;
+    pres.c01 |= col2 & in_lo; pres.c23 |= col2 & in_hi;
+    uint32_t wab, wcd;
+    winning_from_presence(pres, wab, wcd);
+    n_moves = popc(lo) + popc(hi);
+    n_wins = popc(lo & wab) + popc(hi & wcd);
+}
+
 // k_perft_lane's walk (one item per lane, frames = masks of unvisited children), except that the LAST interior
 // level is not walked: when a lane evaluates a node two plies above the target, its non-winning children -- the
 // leaf parents, 96 % of all nodes that are ever evaluated in a wide tree -- are listed in a warp-shared queue
@@ -430,7 +459,7 @@ __global__ void __launch_bounds__(kLaneWarps * 32) k_perft_lane(const uint4 *__r
 // its item (no shared-memory atomics: 64-bit ones are CAS loops and every lane would hit the same row).
 // The target depth accumulates weighted in registers.
 static constexpr int kTileWarps = 4;                  // 128 threads per CTA
-static constexpr int kTileMaxRem = kLaneFrames + 2;   // frames exist for nodes >= 3 plies above the target
+static constexpr int kTileMaxRem = kLaneFrames + 1;   // 4 warps x (fixed part + 2 x (rem - 1) x 256 B) must stay below 48 KB
 static constexpr unsigned kTileQueue = 1024;          // ring of dealt entries: < 32 left over + what one pass adds
 static constexpr unsigned kTileParents = 64;          // ring of parent records: <= 31 still referenced + 32 new
 static constexpr unsigned kTileFlushEvery = 4000;     // evaluations per lane before its packed counters could overflow
@@ -439,8 +468,9 @@ static constexpr unsigned kTileFlushEvery = 4000;     // evaluations per lane be
 // remainders -- the wide, early part of the game -- run at a higher occupancy
 struct TileScratch {
     unsigned short queue[kTileQueue];                 // ring: (mover << 12 | parent record << 6 | action) of a dealt leaf parent
-    uint4 pstate[kTileParents];                       // ring of parent records: the node two plies above the target ...
-    uint2 plegal[kTileParents];                       // ... what the player NOT to move there could play
+    uint4 ppres_rz[kTileParents];                     // ring of parent records (a node two plies above the target): its
+    uint2 ppres_c[kTileParents];                      // ... line presence (rows, zones | columns),
+    uint2 plegal[kTileParents];                       // ... what the player NOT to move there could play,
     u64 pmult[kTileParents];                          // ... and its item's multiplicity
     u64 acc[5 * kRows];                               // this warp's weighted share of the counters
     u64 levels[1][32];                                // frame[rem0 - 1][32]: masks of unvisited children per level and lane,
@@ -453,8 +483,8 @@ __global__ void __launch_bounds__(kTileWarps * 32) k_perft_tile(const uint4 *__r
                                                                  u64 *__restrict__ counters)
 {
     extern __shared__ __align__(16) unsigned char s_dyn[];
-    __shared__ __align__(16) SquareLut s_lut[16];
-    if (threadIdx.x < 16) s_lut[threadIdx.x] = square_lut((int)threadIdx.x);
+    __shared__ __align__(16) TileLut s_lut[16];
+    if (threadIdx.x < 16) s_lut[threadIdx.x] = tile_lut((int)threadIdx.x);
     const int rem0 = depth - d0;          // 2 <= rem0 <= kTileMaxRem
     const size_t warp_bytes = (sizeof(TileScratch) - 256 + (size_t)(2 * rem0 - 2) * 256 + 15) / 16 * 16;
     TileScratch &ws = *reinterpret_cast<TileScratch *>(s_dyn + (threadIdx.x >> 5) * warp_bytes);
@@ -507,6 +537,7 @@ __global__ void __launch_bounds__(kTileWarps * 32) k_perft_tile(const uint4 *__r
 
         uint32_t give_lo = 0, give_hi = 0;       // this lane's leaf parents for the dealt stage
         uint32_t give_ylo = 0, give_yhi = 0;
+        Presence give_pres = { 0, 0, 0, 0, 0, 0 };
         int give_mover = 0;
         uint32_t kids = 0;                       // children of a node two plies above the target (either mode)
         bool flush = false;
@@ -519,7 +550,8 @@ __global__ void __launch_bounds__(kTileWarps * 32) k_perft_tile(const uint4 *__r
             const int mover = (parity + level) & 1;
             uint32_t lo, hi, wab, wcd;
             legal_masks(node, mover, lo, hi);
-            winning_squares(node, wab, wcd);
+            give_pres = line_presence(node);
+            winning_from_presence(give_pres, wab, wcd);
             const int n_moves = popc(lo) + popc(hi);
             const int n_wins = popc(lo & wab) + popc(hi & wcd);
             const uint32_t nl = lo & ~wab, nh = hi & ~wcd;
@@ -575,7 +607,8 @@ __global__ void __launch_bounds__(kTileWarps * 32) k_perft_tile(const uint4 *__r
         if (givers) {
             const uint32_t rec = (q_parents + (uint32_t)__popc(givers & ((1u << lane) - 1u))) & (kTileParents - 1);
             if (cnt_all) {
-                ws.pstate[rec] = to_u4(node);
+                ws.ppres_rz[rec] = make_uint4(give_pres.r01, give_pres.r23, give_pres.z01, give_pres.z23);
+                ws.ppres_c[rec] = make_uint2(give_pres.c01, give_pres.c23);
                 ws.plegal[rec] = make_uint2(give_ylo, give_yhi);
                 ws.pmult[rec] = m;
             }
@@ -598,10 +631,12 @@ __global__ void __launch_bounds__(kTileWarps * 32) k_perft_tile(const uint4 *__r
                 while (q_tail - q_head >= 32) {
                     const uint32_t e = ws.queue[(q_head + lane) & (kTileQueue - 1)], pr = (e >> 6) & (kTileParents - 1), xm = e >> 12;
                     const int action = (int)(e & 63u);
-                    const State4 child = apply_action(to_state(ws.pstate[pr]), (int)xm, action);
+                    const uint4 rz = ws.ppres_rz[pr];
+                    const uint2 cc = ws.ppres_c[pr];
+                    const Presence pres = { rz.x, rz.y, rz.z, rz.w, cc.x, cc.y };
                     const u64 pm = ws.pmult[pr];
                     int nm, nw;
-                    leaf_counts_delta(child, ws.plegal[pr], action, s_lut, nm, nw);
+                    leaf_counts_from_parent(ws.plegal[pr], pres, action, s_lut, nm, nw);
                     acc_nodes += (u64)nm * pm;
                     const u64 w = (u64)nw * pm, b = nm ? 0ull : pm;   // the leaf parent's mover is the OTHER player
                     if (xm) { acc_w0 += w; acc_b0 += b; } else { acc_w1 += w; acc_b1 += b; }
@@ -635,10 +670,12 @@ __global__ void __launch_bounds__(kTileWarps * 32) k_perft_tile(const uint4 *__r
     if (lane < q_tail - q_head) {
         const uint32_t e = ws.queue[(q_head + lane) & (kTileQueue - 1)], pr = (e >> 6) & (kTileParents - 1), xm = e >> 12;
         const int action = (int)(e & 63u);
-        const State4 child = apply_action(to_state(ws.pstate[pr]), (int)xm, action);
+        const uint4 rz = ws.ppres_rz[pr];
+        const uint2 cc = ws.ppres_c[pr];
+        const Presence pres = { rz.x, rz.y, rz.z, rz.w, cc.x, cc.y };
         const u64 pm = ws.pmult[pr];
         int nm, nw;
-        leaf_counts_delta(child, ws.plegal[pr], action, s_lut, nm, nw);
+        leaf_counts_from_parent(ws.plegal[pr], pres, action, s_lut, nm, nw);
         acc_nodes += (u64)nm * pm;
         const u64 w = (u64)nw * pm, b = nm ? 0ull : pm;
         if (xm) { acc_w0 += w; acc_b0 += b; } else { acc_w1 += w; acc_b1 += b; }

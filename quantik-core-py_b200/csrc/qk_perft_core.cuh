@@ -21,15 +21,27 @@ QK_HD uint32_t swap_lanes(uint32_t v) { return prmt(v, 0, 0x1032); }
 // IMAD (FMA pipe) instead of a PRMT (ALU pipe, the bottleneck of the enumeration kernels)
 QK_HD uint32_t dup_low(uint32_t v) { return v * 0x10001u; }
 
-// squares where dropping shape s would complete a line; lanes (A|B<<16, C|D<<16)
-QK_HD void winning_squares(const State4 &s, uint32_t &win_ab, uint32_t &win_cd)
+// which rows / zones / columns hold each shape, colours merged: one bit per line in each 16-bit lane
+// (rows at bit 4r, zones at bits 0, 2, 8, 10, columns at bits 0..3); lanes (A|B<<16, C|D<<16).
+// A new piece of shape s on square p adds bit (p & 12) / (p & 10) / (p & 3) to lane s of the r / z / c word.
+struct Presence { uint32_t r01, r23, z01, z23, c01, c23; };
+
+QK_HD Presence line_presence(const State4 &s)
 {
-    uint32_t u01 = s.x | s.z, u23 = s.y | s.w;
-    uint32_t t01 = pair_or1(u01), t23 = pair_or1(u23);
+    const uint32_t u01 = s.x | s.z, u23 = s.y | s.w;
+    const uint32_t t01 = pair_or1(u01), t23 = pair_or1(u23);
+    Presence p = { row_presence(t01), row_presence(t23), zone_presence(t01), zone_presence(t23),
+                   col_presence(u01), col_presence(u23) };
+    return p;
+}
+
+// squares where dropping shape s would complete a line; lanes (A|B<<16, C|D<<16)
+QK_HD void winning_from_presence(const Presence &p, uint32_t &win_ab, uint32_t &win_cd)
+{
     // "some piece of shape t shares this row / zone / column" as square masks
-    uint32_t r01 = row_presence(t01) * 0xFu, r23 = row_presence(t23) * 0xFu;
-    uint32_t z01 = zone_presence(t01) * 0x33u, z23 = zone_presence(t23) * 0x33u;
-    uint32_t c01 = col_presence(u01) * 0x1111u, c23 = col_presence(u23) * 0x1111u;
+    uint32_t r01 = p.r01 * 0xFu, r23 = p.r23 * 0xFu;
+    uint32_t z01 = p.z01 * 0x33u, z23 = p.z23 * 0x33u;
+    uint32_t c01 = p.c01 * 0x1111u, c23 = p.c23 * 0x1111u;
     // x01 & dup(x23 & x23>>16) has, in lane A, has(A) & has(C) & has(D) -- the squares where the missing shape B
     // wins -- and in lane B the squares where A wins: the masks come out with their lanes swapped, so ONE swap of
     // the combined mask replaces a swap of each of the three ingredients.
@@ -38,6 +50,11 @@ QK_HD void winning_squares(const State4 &s, uint32_t &win_ab, uint32_t &win_cd)
     uint32_t cb01 = dup_low(c01 & (c01 >> 16)), cb23 = dup_low(c23 & (c23 >> 16));
     win_ab = swap_lanes((r01 & rb23) | (z01 & zb23) | (c01 & cb23));
     win_cd = swap_lanes((r23 & rb01) | (z23 & zb01) | (c23 & cb01));
+}
+
+QK_HD void winning_squares(const State4 &s, uint32_t &win_ab, uint32_t &win_cd)
+{
+    winning_from_presence(line_presence(s), win_ab, win_cd);
 }
 
 // same, when the caller already knows who is to move (depth parity): saves the four popcounts of piece_balance

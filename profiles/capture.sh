@@ -12,8 +12,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 # the dominant kernel, full set
 ncu --set full --clock-control none --import-source on -k regex:k_playout -s 3 -c 1 -o gpurun_out/prof_playout_$TAG $CMD > gpurun_out/ncu_playout_$TAG.log 2>&1
 # the two other kernel families
-ncu --set full --clock-control none --import-source on -k regex:k_perft_dfs -s 1 -c 1 -o gpurun_out/prof_perft_$TAG $CMD > gpurun_out/ncu_perft_$TAG.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_perft_lane -s 1 -c 1 -o gpurun_out/prof_perft_lane_$TAG $CMD > gpurun_out/ncu_perft_lane_$TAG.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_bfs_expand_insert -s 15 -c 1 -o gpurun_out/prof_bfs_$TAG $CMD > gpurun_out/ncu_bfs_$TAG.log 2>&1
+# perft: launch 0 = the sharded depth-10 job, 1.. = depth 6 (x4), then depth 7 -- take a depth-7 launch
+ncu --set full --clock-control none --import-source on -k regex:k_perft_tile -s 5 -c 1 -o gpurun_out/prof_perft_tile_$TAG $CMD > gpurun_out/ncu_perft_tile_$TAG.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:k_canonical -s 1 -c 1 -o gpurun_out/prof_canon_$TAG $CMD > gpurun_out/ncu_canon_$TAG.log 2>&1
 ls -la gpurun_out

@@ -261,7 +261,7 @@ def main():
     roofline = {
         "bound": "int_issue", "kernel": "k_playout<false,false>",
         "achieved": achieved / 1e12, "peak": nominal_peak / 1e12, "unit": "Tlane-op/s", "frac": achieved / nominal_peak,
-        "traffic": 57088,   # dram__bytes_read+write of one k_playout launch (ncu --set full, profiles/r01h_playout_ncu.txt)
+        "traffic": 18176,   # dram__bytes_read+write of one k_playout launch (ncu --set full, profiles/r01h_playout_ncu.txt)
         "model": f"{OPS_PER_PLY:.0f} int ops/ply x {PLIES_PER_PLAYOUT} plies/playout (DESIGN.md section 5); peak = SMs x 4 "
                  f"schedulers x 32 lanes x SM clock under load ({sm_mhz:.0f} MHz)",
         "peak_measured_lop3": peak_issue["alu"] / 1e12, "peak_measured_lop3_imad_mix": peak_issue["mixed"] / 1e12,
@@ -273,7 +273,7 @@ def main():
                              "(ncu: profiles/)"},
         "hbm": {"algorithmic_bytes_per_step": 16 + 12, "note": "one 16-byte root in, three u32 tallies out: not memory-bound"},
         "ncu": {"source": "profiles/r01h_playout_ncu.txt", "issue_active_pct": 70.2, "pipe_alu_pct": 63.1,
-                "pipe_fmaheavy_cycles_pct": 65.7, "pipe_xu_pct": 27.3, "lanes_active_per_inst": 30.1},
+                "pipe_fmaheavy_cycles_pct": 65.7, "pipe_xu_pct": 27.3, "lanes_active_per_inst": 30.2},
     }
 
     extra = dict(sharded)

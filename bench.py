@@ -259,7 +259,7 @@ def main():
     nominal_peak = info["sm_count"] * 128 * sm_mhz * 1e6          # 4 schedulers x 32 lanes per SM-clock
     achieved = value / world * OPS_PER_PLAYOUT                    # per GPU
     roofline = {
-        "bound": "int_issue", "kernel": "k_playout<false,false>",
+        "bound": "int_issue", "kernel": "k_playout_single<true> (config 1: one root, tallies only; k_playout<false,false> for many roots)",
         "achieved": achieved / 1e12, "peak": nominal_peak / 1e12, "unit": "Tlane-op/s", "frac": achieved / nominal_peak,
         "traffic": 18176,   # dram__bytes_read+write of one k_playout launch (ncu --set full, profiles/r01h_playout_ncu.txt)
         "model": f"{OPS_PER_PLY:.0f} int ops/ply x {PLIES_PER_PLAYOUT} plies/playout (DESIGN.md section 5); peak = SMs x 4 "

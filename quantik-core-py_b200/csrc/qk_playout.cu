@@ -16,6 +16,8 @@
 #include "qk_common.cuh"
 #include "qk_playout_core.cuh"
 
+#include <stdlib.h>
+
 namespace qk {
 
 static constexpr unsigned kBlock = 256;
@@ -170,6 +172,83 @@ __global__ void QK_PLAYOUT_BOUNDS k_playout(const PlayoutArgs a)
     flush_tallies(a, acc_root, acc_n, acc_p0, acc_dr);
 }
 
+// BASELINE config 1 -- every playout from ONE root, to the end, tallies only -- is the headline workload, and there
+// the refill path above (root / rollout bookkeeping, root-change flush, three global loads with address arithmetic)
+// is 10 of the ~95 instructions a ply costs.  Same loop with the root record in shared memory and a plain counter.
+// a shared-memory load the compiler may not hoist out of the loop (keeping the 11-word root record in registers
+// would cost a CTA of occupancy)
+__device__ __forceinline__ uint4 lds128_fresh(const uint4 *p)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "r"((uint32_t)__cvta_generic_to_shared(p)));
+    return v;
+}
+
+template <bool FRESH>
+__global__ void QK_PLAYOUT_BOUNDS k_playout_single(const PlayoutArgs a)
+{
+    __shared__ __align__(16) SquareLut s_lut[16];
+    __shared__ __align__(16) uint8_t s_sel8[2048];
+    __shared__ uint4 s_root[3];
+    if (threadIdx.x < 3) s_root[threadIdx.x] = __ldg(reinterpret_cast<const uint4 *>(a.roots) + threadIdx.x);
+    fill_tables(s_lut, s_sel8);
+
+    const uint64_t tid = blockIdx.x * (uint64_t)kBlock + threadIdx.x;
+    const uint64_t begin = tid * a.chunk;
+    uint32_t remaining = 0, next_j = 0;    // playouts this thread still has to START, and the next one's index
+    if (begin < a.total) {
+        const uint64_t end = begin + a.chunk < a.total ? begin + a.chunk : a.total;
+        remaining = (uint32_t)(end - begin);
+        next_j = (uint32_t)begin;
+    }
+    const uint32_t flags = s_root[2].w;
+    const bool a_is_p0 = (flags & 1u) == 0;
+    const uint32_t immediate = (flags >> QK_ROOT_IMMEDIATE_SHIFT) & 3u;
+    uint32_t acc_n = 0, acc_p0 = 0;
+    if (immediate) {                       // the root is decided: every playout is that result (mcts.py:412 order)
+        acc_n = remaining; acc_p0 = immediate == 1 ? remaining : 0u;
+        remaining = 0;
+    }
+
+    PlayState st = {};
+    bool active = false;
+    uint32_t block = 0, cur_j = 0;
+    for (;;) {
+        // ---- 4-ply boundary: threads without a game in flight start their next one
+        if (!active && remaining) {
+            const uint4 r0 = FRESH ? lds128_fresh(s_root) : s_root[0], r1 = FRESH ? lds128_fresh(s_root + 1) : s_root[1],
+                        r2 = FRESH ? lds128_fresh(s_root + 2) : s_root[2];
+            st.free2 = ~r0.x; st.ra_lo = r0.y; st.ra_hi = r0.z; st.rb_lo = r0.w;
+            st.rb_hi = r1.x; st.ta_lo = r1.y; st.ta_hi = r1.z; st.tb_lo = r1.w;
+            st.tb_hi = r2.x; st.lp_lo = r2.y; st.lp_hi = r2.z;
+            cur_j = next_j++;
+            block = 0;
+            --remaining;
+            ++acc_n;
+            active = true;
+        }
+        if (!__any_sync(kFull, active)) break;      // nobody plays and (checked above) nobody could start: done
+
+        // ---- one Philox block = four plies, roles alternate A B A B
+        const uint64_t rollout = a.first_rollout + cur_j;
+        const Philox4 rnd = stream_block(a.seed, rollout, a.root_index_base, block);
+        ++block;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            bool blocked, win;
+            if (q & 1) ply_step_fma<1>(st, rnd.v[q], s_lut, s_sel8, a.two, blocked, win);
+            else       ply_step_fma<0>(st, rnd.v[q], s_lut, s_sel8, a.two, blocked, win);
+            // a blocked mover loses (beam_search.py:641-642), a completed line wins (:633-635)
+            const bool mover_is_p0 = (q & 1) ? !a_is_p0 : a_is_p0;
+            const bool fin = active && (blocked || win);
+            acc_p0 += (fin && (mover_is_p0 != blocked)) ? 1u : 0u;
+            active = active && !fin;
+        }
+    }
+    flush_tallies(a, 0u, acc_n, acc_p0, 0u);
+}
+
 size_t playout_scratch_bytes(size_t n_roots) { return n_roots * sizeof(RootRec); }
 
 int launch_playouts(const uint4 *roots, size_t n_roots, uint32_t rollouts, uint64_t seed, uint64_t first_rollout,
@@ -191,6 +270,11 @@ int launch_playouts(const uint4 *roots, size_t n_roots, uint32_t rollouts, uint6
     const bool cutoff = max_plies >= 0, pp = per_playout || per_plies;
     void (*kernel)(const PlayoutArgs) = cutoff ? (pp ? k_playout<true, true> : k_playout<true, false>)
                                                : (pp ? k_playout<false, true> : k_playout<false, false>);
+    if (n_roots == 1 && !cutoff && !pp) {
+        const char *v = getenv("QK_PLAYOUT_VARIANT");           // benchmarking aid: general / hoist / (default) fresh
+        if (!v || v[0] == 'f') kernel = k_playout_single<true>;
+        else if (v[0] == 'h') kernel = k_playout_single<false>;
+    }
     // persistent grid: exactly as many CTAs as are resident at once (no second wave), fewer only
     // when there are not enough playouts to give each thread one
     int per_sm = 0;

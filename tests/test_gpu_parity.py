@@ -689,3 +689,22 @@ def test_fused_exchange_with_emulated_ranks_on_one_gpu():
         rows.append([int(tot[0]), sum(len(u) for u, _ in shards), int(tot[1] + tot[4]), int(tot[2] + tot[3]),
                      int(sum(int(m.sum()) for _, m in shards))])
     assert rows == [list(map(int, r)) for r in B.symmetry_table(6)]
+
+
+def test_single_root_kernel_matches_general_kernel_and_oracle(monkeypatch):
+    """Config 1 (one root, tallies only) runs a specialised kernel; it must give the general kernel's and the oracle's tallies."""
+    roots = [np.zeros((1, 8), np.uint16), O.make_roots(3, seed=5, min_plies=6, span=3)[1:2],
+             np.array([[1, 2, 4, 8, 0, 0, 0, 0]], np.uint16)]           # the last one is already won (row of A B C D)
+    for root in roots:
+        for n, first in ((1, 0), (1000, 0), (300_001, 12345), (1 << 22, 1 << 40)):
+            tallies = {}
+            for variant in ("fresh", "hoist", "general"):
+                monkeypatch.setenv("QK_PLAYOUT_VARIANT", variant)
+                r = B.playouts(root, n, SEED, first_rollout=first)
+                tallies[variant] = (int(r["wins_p0"][0]), int(r["wins_p1"][0]), int(r["draws"][0]))
+                assert sum(tallies[variant]) == n
+            assert tallies["fresh"] == tallies["hoist"] == tallies["general"], (n, first, tallies)
+            if n <= 300_001:
+                o = O.playouts(root, n, SEED, first)
+                assert tallies["fresh"] == (int(o["wins_p0"][0]), int(o["wins_p1"][0]), int(o["draws"][0]))
+    monkeypatch.delenv("QK_PLAYOUT_VARIANT")

@@ -261,7 +261,7 @@ def main():
     roofline = {
         "bound": "int_issue", "kernel": "k_playout_single<true> (config 1: one root, tallies only; k_playout<false,false> for many roots)",
         "achieved": achieved / 1e12, "peak": nominal_peak / 1e12, "unit": "Tlane-op/s", "frac": achieved / nominal_peak,
-        "traffic": 18176,   # dram__bytes_read+write of one k_playout launch (ncu --set full, profiles/r01h_playout_ncu.txt)
+        "traffic": 14592,   # dram__bytes_read+write of one k_playout launch (ncu --set full, profiles/r01i_playout_ncu.txt)
         "model": f"{OPS_PER_PLY:.0f} int ops/ply x {PLIES_PER_PLAYOUT} plies/playout (DESIGN.md section 5); peak = SMs x 4 "
                  f"schedulers x 32 lanes x SM clock under load ({sm_mhz:.0f} MHz)",
         "peak_measured_lop3": peak_issue["alu"] / 1e12, "peak_measured_lop3_imad_mix": peak_issue["mixed"] / 1e12,
@@ -272,8 +272,8 @@ def main():
                      "note": "LOP3/SEL/ISETP/SHF/IADD3 share one 64-lane/clk/SM pipe on sm_100: the binding sub-roofline "
                              "(ncu: profiles/)"},
         "hbm": {"algorithmic_bytes_per_step": 16 + 12, "note": "one 16-byte root in, three u32 tallies out: not memory-bound"},
-        "ncu": {"source": "profiles/r01h_playout_ncu.txt", "issue_active_pct": 70.2, "pipe_alu_pct": 63.1,
-                "pipe_fmaheavy_cycles_pct": 65.7, "pipe_xu_pct": 27.3, "lanes_active_per_inst": 30.2},
+        "ncu": {"source": "profiles/r01i_playout_ncu.txt", "issue_active_pct": 70.5, "pipe_alu_pct": 62.8,
+                "pipe_fmaheavy_cycles_pct": 68.0, "pipe_xu_pct": 29.3, "lanes_active_per_inst": 31.0},
     }
 
     extra = dict(sharded)

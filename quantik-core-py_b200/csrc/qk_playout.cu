@@ -32,7 +32,6 @@ struct PlayoutArgs {
     uint32_t rollouts;
     uint32_t root_index_base;
     int max_plies;
-    uint32_t two;            // the constant 2, opaque to the compiler (see ply_step_fma)
     uint32_t *wins_p0, *wins_p1, *draws;
     int8_t *per_playout;
     uint8_t *per_plies;
@@ -147,8 +146,8 @@ __global__ void QK_PLAYOUT_BOUNDS k_playout(const PlayoutArgs a)
             if (q & 1) ply_step<1>(st, rnd.v[q], s_lut, s_sel8, blocked, win);
             else       ply_step<0>(st, rnd.v[q], s_lut, s_sel8, blocked, win);
 #else
-            if (q & 1) ply_step_fma<1>(st, rnd.v[q], s_lut, s_sel8, a.two, blocked, win);
-            else       ply_step_fma<0>(st, rnd.v[q], s_lut, s_sel8, a.two, blocked, win);
+            if (q & 1) ply_step_fma<1>(st, rnd.v[q], s_lut, s_sel8, blocked, win);
+            else       ply_step_fma<0>(st, rnd.v[q], s_lut, s_sel8, blocked, win);
 #endif
             // outcome bookkeeping without branches: a blocked mover loses (beam_search.py:641-642),
             // otherwise the move is made and may hit the cut-off (mcts.py:412,436-437) or complete a
@@ -237,8 +236,8 @@ __global__ void QK_PLAYOUT_BOUNDS k_playout_single(const PlayoutArgs a)
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             bool blocked, win;
-            if (q & 1) ply_step_fma<1>(st, rnd.v[q], s_lut, s_sel8, a.two, blocked, win);
-            else       ply_step_fma<0>(st, rnd.v[q], s_lut, s_sel8, a.two, blocked, win);
+            if (q & 1) ply_step_fma<1>(st, rnd.v[q], s_lut, s_sel8, blocked, win);
+            else       ply_step_fma<0>(st, rnd.v[q], s_lut, s_sel8, blocked, win);
             // a blocked mover loses (beam_search.py:641-642), a completed line wins (:633-635)
             const bool mover_is_p0 = (q & 1) ? !a_is_p0 : a_is_p0;
             const bool fin = active && (blocked || win);
@@ -264,7 +263,6 @@ int launch_playouts(const uint4 *roots, size_t n_roots, uint32_t rollouts, uint6
     a.total = (uint64_t)n_roots * rollouts;
     a.seed = seed; a.first_rollout = first_rollout; a.rollouts = rollouts; a.root_index_base = root_index_base;
     a.max_plies = max_plies;
-    a.two = 2u;
     a.wins_p0 = wins_p0; a.wins_p1 = wins_p1; a.draws = draws; a.per_playout = per_playout; a.per_plies = per_plies;
 
     const bool cutoff = max_plies >= 0, pp = per_playout || per_plies;

@@ -215,7 +215,7 @@ __device__ __forceinline__ uint32_t qk_madhi(uint32_t a, uint32_t b, uint32_t c)
 
 template <int ROLE>
 __device__ __forceinline__ void ply_step_fma(PlayState &st, uint32_t rnd, const SquareLut *lut, const uint8_t *sel8,
-                                             uint32_t two, bool &blocked, bool &win)
+                                             bool &blocked, bool &win)
 {
     uint32_t &rm_lo = ROLE ? st.rb_lo : st.ra_lo, &rm_hi = ROLE ? st.rb_hi : st.ra_hi;   // mover
     uint32_t &ro_lo = ROLE ? st.ra_lo : st.rb_lo, &ro_hi = ROLE ? st.ra_hi : st.rb_hi;   // other

@@ -420,35 +420,6 @@ __global__ void __launch_bounds__(kLaneWarps * 32) k_perft_lane(const uint4 *__r
 }
 
 // ------------------------------------------------------------------ lane-parallel DFS with a dealt last level
-// per-square masks for the evaluation of a leaf parent from its parent's data, replicated in both 16-bit lanes
-struct __attribute__((aligned(16))) TileLut { uint32_t scope2, bit2, row2, zone2, col2, pad0, pad1, pad2; };
-__device__ __forceinline__ TileLut tile_lut(int p)
-{
-    const SquareLut e = square_lut(p);
-    TileLut t = { e.scope2, e.bit2, 0x00010001u << (p & 12), 0x00010001u << (p & 10), 0x00010001u << (p & 3), 0u, 0u, 0u };
-    return t;
-}
-// move / winning-move counts of a leaf parent from its PARENT: `legal` = what its mover could have played one ply
-// earlier, `pres` = the parent's line presence, `action` = the move that was made.  The new piece takes its square
-// away from every shape and its scope away from its own shape (move.py:169-196), and adds its shape to its row,
-// zone and column; the child itself is never materialised.
-__device__ __forceinline__ void leaf_counts_from_parent(uint2 legal, Presence pres, int action, const TileLut *lut,
-                                                        int &n_moves, int &n_wins)
-{
-    const uint4 e = *reinterpret_cast<const uint4 *>(lut + (action & 15));                  // scope2, bit2, row2, zone2
-    const uint32_t col2 = lut[action & 15].col2;
-    const uint32_t lane = (action & 16) ? 0xFFFF0000u : 0x0000FFFFu;
-    const uint32_t in_lo = (action & 32) ? 0u : lane, in_hi = lane ^ in_lo;                 // lane of the new piece's shape
-    const uint32_t lo = legal.x & ~(e.y | (e.x & in_lo)), hi = legal.y & ~(e.y | (e.x & in_hi));
-    pres.r01 |= e.z & in_lo; pres.r23 |= e.z & in_hi;
-    pres.z01 |= e.w & in_lo; pres.z23 |= e.w & in_hi;
-    pres.c01 |= col2 & in_lo; pres.c23 |= col2 & in_hi;
-    uint32_t wab, wcd;
-    winning_from_presence(pres, wab, wcd);
-    n_moves = popc(lo) + popc(hi);
-    n_wins = popc(lo & wab) + popc(hi & wcd);
-}
-
 // k_perft_lane's walk (one item per lane, frames = masks of unvisited children), except that the LAST interior
 // level is not walked: when a lane evaluates a node two plies above the target, its non-winning children -- the
 // leaf parents, 96 % of all nodes that are ever evaluated in a wide tree -- are listed in a warp-shared queue
@@ -636,7 +607,7 @@ __global__ void __launch_bounds__(kTileWarps * 32) k_perft_tile(const uint4 *__r
                     const Presence pres = { rz.x, rz.y, rz.z, rz.w, cc.x, cc.y };
                     const u64 pm = ws.pmult[pr];
                     int nm, nw;
-                    leaf_counts_from_parent(ws.plegal[pr], pres, action, s_lut, nm, nw);
+                    { const uint2 yl = ws.plegal[pr]; leaf_counts_from_parent(yl.x, yl.y, pres, action, s_lut, nm, nw); }
                     acc_nodes += (u64)nm * pm;
                     const u64 w = (u64)nw * pm, b = nm ? 0ull : pm;   // the leaf parent's mover is the OTHER player
                     if (xm) { acc_w0 += w; acc_b0 += b; } else { acc_w1 += w; acc_b1 += b; }
@@ -675,7 +646,7 @@ __global__ void __launch_bounds__(kTileWarps * 32) k_perft_tile(const uint4 *__r
         const Presence pres = { rz.x, rz.y, rz.z, rz.w, cc.x, cc.y };
         const u64 pm = ws.pmult[pr];
         int nm, nw;
-        leaf_counts_from_parent(ws.plegal[pr], pres, action, s_lut, nm, nw);
+        { const uint2 yl = ws.plegal[pr]; leaf_counts_from_parent(yl.x, yl.y, pres, action, s_lut, nm, nw); }
         acc_nodes += (u64)nm * pm;
         const u64 w = (u64)nw * pm, b = nm ? 0ull : pm;
         if (xm) { acc_w0 += w; acc_b0 += b; } else { acc_w1 += w; acc_b1 += b; }

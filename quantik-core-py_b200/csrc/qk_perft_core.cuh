@@ -57,6 +57,36 @@ QK_HD void winning_squares(const State4 &s, uint32_t &win_ab, uint32_t &win_cd)
     winning_from_presence(line_presence(s), win_ab, win_cd);
 }
 
+// per-square masks for the evaluation of a leaf parent from its parent's data, replicated in both 16-bit lanes
+struct __attribute__((aligned(16))) TileLut { uint32_t scope2, bit2, row2, zone2, col2, pad0, pad1, pad2; };
+QK_HD TileLut tile_lut(int p)
+{
+    const uint32_t scope = ((0xFu << (p & 12)) | (0x1111u << (p & 3)) | (0x33u << (p & 10))) & 0xFFFFu;
+    TileLut t = { scope * 0x10001u, 0x00010001u << p, 0x00010001u << (p & 12), 0x00010001u << (p & 10),
+                  0x00010001u << (p & 3), 0u, 0u, 0u };
+    return t;
+}
+// move / winning-move counts of a leaf parent from its PARENT: (legal_lo, legal_hi) = what its mover could have
+// played one ply earlier (legal_masks of the parent for the player NOT to move there), `pres` = the parent's line
+// presence, `action` = the move that was made.  The new piece takes its square away from every shape and its scope
+// away from its own shape (move.py:169-196), and adds its shape to its row, zone and column; the child itself is
+// never materialised.
+QK_HD void leaf_counts_from_parent(uint32_t legal_lo, uint32_t legal_hi, Presence pres, int action, const TileLut *lut,
+                                   int &n_moves, int &n_wins)
+{
+    const TileLut e = lut[action & 15];
+    const uint32_t lane = (action & 16) ? 0xFFFF0000u : 0x0000FFFFu;
+    const uint32_t in_lo = (action & 32) ? 0u : lane, in_hi = lane ^ in_lo;                 // lane of the new piece's shape
+    const uint32_t lo = legal_lo & ~(e.bit2 | (e.scope2 & in_lo)), hi = legal_hi & ~(e.bit2 | (e.scope2 & in_hi));
+    pres.r01 |= e.row2 & in_lo; pres.r23 |= e.row2 & in_hi;
+    pres.z01 |= e.zone2 & in_lo; pres.z23 |= e.zone2 & in_hi;
+    pres.c01 |= e.col2 & in_lo; pres.c23 |= e.col2 & in_hi;
+    uint32_t wab, wcd;
+    winning_from_presence(pres, wab, wcd);
+    n_moves = popc(lo) + popc(hi);
+    n_wins = popc(lo & wab) + popc(hi & wcd);
+}
+
 // same, when the caller already knows who is to move (depth parity): saves the four popcounts of piece_balance
 QK_HD void leaf_parent_counts_for(const State4 &s, int mover, int &n_moves, int &n_wins)
 {

@@ -34,6 +34,32 @@ void hs_apply(const uint16_t *s, const uint8_t *a, size_t n, uint16_t *out)
 { for (size_t i = 0; i < n; ++i) { State4 x = ld(s + 8 * i); int p = 0; if (validate(x, &p) != 0) p = 0; st(out + 8 * i, apply_action(x, p, a[i])); } }
 void hs_leaf_parent(const uint16_t *s, size_t n, uint8_t *mover, uint8_t *moves, uint8_t *wins)
 { for (size_t i = 0; i < n; ++i) { int m, w; mover[i] = leaf_parent_counts(ld(s + 8 * i), m, w); moves[i] = m; wins[i] = w; } }
+// every non-winning child of every position, evaluated from the parent's data (the perft tile kernel's way) and
+// directly; -> children checked, mismatches
+void hs_leaf_from_parent(const uint16_t *s, size_t n, uint64_t *checked, uint64_t *mismatch)
+{
+    TileLut lut[16];
+    for (int p = 0; p < 16; ++p) lut[p] = tile_lut(p);
+    *checked = 0; *mismatch = 0;
+    for (size_t i = 0; i < n; ++i) {
+        const State4 node = ld(s + 8 * i);
+        const int mover = piece_balance(node);
+        uint32_t lo, hi, wab, wcd, ylo, yhi;
+        legal_masks(node, mover, lo, hi);
+        const Presence pres = line_presence(node);
+        winning_from_presence(pres, wab, wcd);
+        legal_masks(node, mover ^ 1, ylo, yhi);
+        const uint64_t kids = ((uint64_t)(hi & ~wcd) << 32) | (lo & ~wab);
+        for (int a = 0; a < 64; ++a) {
+            if (!((kids >> a) & 1)) continue;
+            int m0, w0, m1, w1;
+            leaf_parent_counts_for(apply_action(node, mover, a), mover ^ 1, m0, w0);
+            leaf_counts_from_parent(ylo, yhi, pres, a, lut, m1, w1);
+            ++*checked;
+            if (m0 != m1 || w0 != w1) ++*mismatch;
+        }
+    }
+}
 void hs_features(const uint16_t *s, const uint8_t *pl, size_t n, double *out)
 { for (size_t i = 0; i < n; ++i) { int f[6]; eval_features(ld(s + 8 * i), pl[i], f); for (int k = 0; k < 6; ++k) out[6 * i + k] = f[k]; } }
 void hs_guided(const uint16_t *roots, size_t n_roots, uint32_t rollouts, uint64_t seed, uint64_t first, uint32_t root_base,

@@ -112,6 +112,18 @@ def test_leaf_parent_bulk_counts(hs):
         assert (int(r["wins_p0"][1]) > 0) <= (mv[i] == 0) and (int(r["wins_p1"][1]) > 0) <= (mv[i] == 1)
 
 
+def test_leaf_parent_from_parent_data(hs):
+    """The perft tile kernel never materialises a leaf parent: its legal squares and line presence are derived from
+    its parent's.  Same counts as the direct evaluation, for every non-winning child of reachable positions."""
+    d = np.load(os.path.join(G, "states_reference.npz"))
+    nv = int(d["n_valid"])
+    s = np.concatenate([d["states"][:nv][d["win"][:nv] == 0], O.make_roots(4000, seed=99, min_plies=0, span=14)])
+    s = np.ascontiguousarray(s[(O.win_status(s) == 0) & (O.validate(s)[1] == 0)])
+    checked, bad = ctypes.c_uint64(0), ctypes.c_uint64(0)
+    hs.hs_leaf_from_parent(P(s), ctypes.c_size_t(len(s)), ctypes.byref(checked), ctypes.byref(bad))
+    assert checked.value > 20_000 and bad.value == 0
+
+
 def test_eval_features_and_guided_policy(hs):
     g = np.load(os.path.join(G, "guided_rollouts.npz"))
     st = np.ascontiguousarray(g["states"])

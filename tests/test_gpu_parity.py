@@ -630,8 +630,12 @@ def test_exchange_step_functions_at_world_size_one_and_two_gpus():
     assert np.bincount(owners, minlength=8).min() > len(u) // 16
     if torch.cuda.device_count() >= 2:
         root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        import socket
+        with socket.socket() as sock:                     # a free rendezvous port
+            sock.bind(("127.0.0.1", 0))
+            port = sock.getsockname()[1]
         out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
-                              "--master-addr", "127.0.0.1", "--master-port", "29533",
+                              "--master-addr", "127.0.0.1", "--master-port", str(port),
                               os.path.join(root, "scripts", "multi_gpu_bfs.py"), "9", "18"],
                              capture_output=True, text=True, timeout=600)
         assert out.returncode == 0, out.stderr[-2000:]

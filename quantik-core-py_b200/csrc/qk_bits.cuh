@@ -307,7 +307,24 @@ QK_HD void key_min(Key128 &best, const Key128 &k)
 }
 QK_HD bool key_equal(const Key128 &p, const Key128 &q) { return p.a == q.a && p.b == q.b && p.c == q.c && p.d == q.d; }
 
-QK_HD void cswap(uint32_t &p, uint32_t &q) { uint32_t lo = p < q ? p : q, hi = p < q ? q : p; p = lo; q = hi; }
+// compare-exchange.  On the device the maximum is  p + q - min  computed with two integer multiply-adds whose
+// multipliers (1 and -1) come from constant memory, so that ptxas cannot fold them back into one IADD3: the
+// canonicalisation kernels are bound by the ALU pipe (min/max, PRMT, LOP3, shifts and IADD3 all issue there: ncu
+// 89 % busy with the FMA-heavy pipe at 33 %), and this moves one of the two VIMNMX of every comparator across.
+#ifdef __CUDACC__
+static __constant__ uint32_t qk_c_one = 1u, qk_c_minus_one = 0xFFFFFFFFu;
+#endif
+QK_HD void cswap(uint32_t &p, uint32_t &q)
+{
+#if defined(__CUDA_ARCH__) && !defined(QK_CSWAP_ALU)
+    const uint32_t lo = p < q ? p : q;
+    const uint32_t sum = p * qk_c_one + q;
+    q = lo * qk_c_minus_one + sum;
+    p = lo;
+#else
+    uint32_t lo = p < q ? p : q, hi = p < q ? q : p; p = lo; q = hi;
+#endif
+}
 
 // sorted-shape arrangement of one board image (c0 = first colour's two registers).  PENDING = the registers
 // still owe a byte swap inside each lane (flip_rows_pending): only the PRMT selectors change.

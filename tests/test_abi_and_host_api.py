@@ -37,6 +37,21 @@ def test_library_exports_every_declared_symbol():
     assert N.load().qk_abi_version() == 1
 
 
+def test_inbox_layout_is_host_arithmetic():
+    """qk_inbox_bytes needs no device: header of per-source counts + one (16 B payload + 8 B multiplicity) region per source."""
+    from quantik_b200 import batch as B
+    assert B.inbox_bytes(1, 1) == 128 + 24
+    assert B.inbox_bytes(8, 1000) == 128 + 8 * 1000 * 24
+    lib = N.load()
+    nb = ctypes.c_size_t(0)
+    assert lib.qk_inbox_bytes(17, 10, ctypes.byref(nb)) == -1 and b"world" in lib.qk_last_error()     # QK_MAX_WORLD = 16
+    # without an initialised device the scatter entry points refuse like every other compute call
+    s = np.zeros((1, 8), np.uint16)
+    ptrs = (ctypes.c_void_p * 1)(ctypes.c_void_p(s.ctypes.data))
+    if _no_gpu():
+        assert lib.qk_canon_dedup_scatter(s.ctypes.data, None, 1, 0, ptrs, 1, 0, 16, None, 0, None) == -3
+
+
 def test_header_cites_reference_for_every_entry_point():
     text = open(os.path.join(ROOT, "include", "quantik_b200.h")).read()
     for ref in ("move.py:199", "move.py:135", "game_utils.py:123", "symmetry.py:289", "symmetry.py:356",

@@ -17,9 +17,6 @@ namespace qk {
 __device__ __forceinline__ State4 to_state4(const uint4 &v) { State4 s = { v.x, v.y, v.z, v.w }; return s; }
 #endif
 QK_HD uint32_t swap_lanes(uint32_t v) { return prmt(v, 0, 0x1032); }
-// low lane replicated into both lanes; callers pass values whose high lane is already zero, so this is one
-// IMAD (FMA pipe) instead of a PRMT (ALU pipe, the bottleneck of the enumeration kernels)
-QK_HD uint32_t dup_low(uint32_t v) { return v * 0x10001u; }
 
 // which rows / zones / columns hold each shape, colours merged: one bit per line in each 16-bit lane
 // (rows at bit 4r, zones at bits 0, 2, 8, 10, columns at bits 0..3); lanes (A|B<<16, C|D<<16).
@@ -42,12 +39,13 @@ QK_HD void winning_from_presence(const Presence &p, uint32_t &win_ab, uint32_t &
     uint32_t r01 = p.r01 * 0xFu, r23 = p.r23 * 0xFu;
     uint32_t z01 = p.z01 * 0x33u, z23 = p.z23 * 0x33u;
     uint32_t c01 = p.c01 * 0x1111u, c23 = p.c23 * 0x1111u;
-    // x01 & dup(x23 & x23>>16) has, in lane A, has(A) & has(C) & has(D) -- the squares where the missing shape B
-    // wins -- and in lane B the squares where A wins: the masks come out with their lanes swapped, so ONE swap of
-    // the combined mask replaces a swap of each of the three ingredients.
-    uint32_t rb01 = dup_low(r01 & (r01 >> 16)), rb23 = dup_low(r23 & (r23 >> 16));
-    uint32_t zb01 = dup_low(z01 & (z01 >> 16)), zb23 = dup_low(z23 & (z23 >> 16));
-    uint32_t cb01 = dup_low(c01 & (c01 >> 16)), cb23 = dup_low(c23 & (c23 >> 16));
+    // x01 & both(x23) has, in lane A, has(A) & has(C) & has(D) -- the squares where the missing shape B wins -- and
+    // in lane B the squares where A wins: the masks come out with their lanes swapped, so ONE swap of the combined
+    // mask replaces a swap of each of the three ingredients.
+    // both lanes of x & swap(x) hold lane0 & lane1: the AND of the word's two shapes, already replicated
+    uint32_t rb01 = r01 & swap_lanes(r01), rb23 = r23 & swap_lanes(r23);
+    uint32_t zb01 = z01 & swap_lanes(z01), zb23 = z23 & swap_lanes(z23);
+    uint32_t cb01 = c01 & swap_lanes(c01), cb23 = c23 & swap_lanes(c23);
     win_ab = swap_lanes((r01 & rb23) | (z01 & zb23) | (c01 & cb23));
     win_cd = swap_lanes((r23 & rb01) | (z23 & zb01) | (c23 & cb01));
 }

@@ -42,12 +42,13 @@ __device__ __forceinline__ uint4 to_u4(const State4 &s) { return make_uint4(s.x,
 __global__ void __launch_bounds__(kBlock) k_perft_filter_roots(const uint4 *__restrict__ roots, const u64 *__restrict__ mult,
                                                                 size_t n, int depth, uint4 *__restrict__ out_states,
                                                                 u64 *__restrict__ out_mult, u64 *__restrict__ out_count,
-                                                                u64 *__restrict__ counters)
+                                                                u64 *__restrict__ counters, unsigned *__restrict__ flags)
 {
     size_t i = blockIdx.x * (size_t)kBlock + threadIdx.x;
     const unsigned lane = threadIdx.x & 31u;
     u64 m = 0, blocked = 0;
     bool keep = false;
+    unsigned seen = 0;
     State4 s = { 0, 0, 0, 0 };
     if (i < n) {
         s = to_state(__ldg(roots + i));
@@ -55,9 +56,12 @@ __global__ void __launch_bounds__(kBlock) k_perft_filter_roots(const uint4 *__re
         int player;
         if (win_status(s) == 0) {                       // a finished root has nothing below it
             if (validate(s, &player) != 0) blocked = m; // generate_legal_moves -> (0, {})  (move.py:223-225)
-            else keep = true;
+            else { keep = true; seen = (1u << player) | ((m >> 32) ? 4u : 0u); }
         }
     }
+    // what the frontier looks like (k_perft_tile has a faster form for one side to move + 32-bit multiplicities)
+    seen = __reduce_or_sync(kFull, seen);
+    if (lane == 0 && seen) atomicOr(flags, seen);
     u64 tot = warp_sum(m), blk = warp_sum(blocked);
     unsigned kmask = __ballot_sync(kFull, keep);
     u64 base = 0;
@@ -449,9 +453,39 @@ struct TileScratch {
 };
 static size_t tile_warp_bytes(int rem0) { return (sizeof(TileScratch) - 256 + (size_t)(2 * rem0 - 2) * 256 + 15) / 16 * 16; }
 
+// weighted tallies of the target depth, per lane.  FAST = every item has the same player to move and every
+// multiplicity fits 32 bits (true for any frontier grown from one root, and for the depth-4 classes): one
+// accumulator per counter and one IMAD.WIDE per addition instead of predicated 64 x 64-bit arithmetic.
+template <bool FAST> struct LeafAcc;
+template <> struct LeafAcc<false> {
+    u64 nodes = 0, w0 = 0, w1 = 0, b0 = 0, b1 = 0;
+    __device__ __forceinline__ void add(int nm, int nw, u64 pm, bool leaf_mover_p1)
+    {
+        nodes += (u64)nm * pm;
+        const u64 w = (u64)nw * pm, b = nm ? 0ull : pm;
+        if (leaf_mover_p1) { w1 += w; b1 += b; } else { w0 += w; b0 += b; }
+    }
+    __device__ __forceinline__ void finish(bool) {}
+};
+template <> struct LeafAcc<true> {
+    u64 nodes = 0, w0 = 0, w1 = 0, b0 = 0, b1 = 0;         // w1 / b1 are filled by finish()
+    __device__ __forceinline__ void add(int nm, int nw, u64 pm, bool)
+    {
+        const uint32_t m32 = (uint32_t)pm;
+        nodes += (u64)((uint32_t)nm) * m32;
+        w0 += (u64)((uint32_t)nw) * m32;
+        b0 += nm ? 0u : m32;
+    }
+    __device__ __forceinline__ void finish(bool leaf_mover_p1)
+    {
+        if (leaf_mover_p1) { w1 = w0; b1 = b0; w0 = 0; b0 = 0; }
+    }
+};
+
+template <bool FAST>
 __global__ void __launch_bounds__(kTileWarps * 32) k_perft_tile(const uint4 *__restrict__ items, const u64 *__restrict__ mult,
-                                                                 u64 n_items, int d0, int depth, u64 *__restrict__ next_item,
-                                                                 u64 *__restrict__ counters)
+                                                                 u64 n_items, int d0, int depth, int uniform_parity,
+                                                                 u64 *__restrict__ next_item, u64 *__restrict__ counters)
 {
     extern __shared__ __align__(16) unsigned char s_dyn[];
     __shared__ __align__(16) TileLut s_lut[16];
@@ -480,7 +514,7 @@ __global__ void __launch_bounds__(kTileWarps * 32) k_perft_tile(const uint4 *__r
     // (measured on the 10 946 depth-4 classes: to depth 12 dealing 11.5 s vs walking 15.6 s, to depth 16 165 s vs 128 s).
     bool deal = true;
     uint32_t seen_kids = 0, seen_busy = 0, seen_iters = 0;
-    u64 acc_nodes = 0, acc_w0 = 0, acc_w1 = 0, acc_b0 = 0, acc_b1 = 0;    // the target depth, weighted, per lane
+    LeafAcc<FAST> acc;                                                    // the target depth, weighted, per lane
 
     for (;;) {
         // ---- idle lanes take the next items
@@ -530,9 +564,7 @@ __global__ void __launch_bounds__(kTileWarps * 32) k_perft_tile(const uint4 *__r
             bool ret = true;                                     // nothing (more) to walk below this node
             if (rem == 1) {
                 // a leaf parent walked by its own lane (narrow trees): the target depth, weighted, in registers
-                acc_nodes += (u64)n_moves * m;
-                const u64 w = (u64)n_wins * m, b = n_moves ? 0ull : m;
-                if (mover) { acc_w1 += w; acc_b1 += b; } else { acc_w0 += w; acc_b0 += b; }
+                acc.add(n_moves, n_wins, m, mover != 0);
             } else {
                 cnt_packed[level][lane] += (u64)n_moves | ((u64)n_wins << 26) | ((u64)(n_moves == 0) << 52);
                 ++since_flush;
@@ -608,9 +640,7 @@ __global__ void __launch_bounds__(kTileWarps * 32) k_perft_tile(const uint4 *__r
                     const u64 pm = ws.pmult[pr];
                     int nm, nw;
                     { const uint2 yl = ws.plegal[pr]; leaf_counts_from_parent(yl.x, yl.y, pres, action, s_lut, nm, nw); }
-                    acc_nodes += (u64)nm * pm;
-                    const u64 w = (u64)nw * pm, b = nm ? 0ull : pm;   // the leaf parent's mover is the OTHER player
-                    if (xm) { acc_w0 += w; acc_b0 += b; } else { acc_w1 += w; acc_b1 += b; }
+                    acc.add(nm, nw, pm, xm == 0);                     // the leaf parent's mover is the OTHER player
                     q_head += 32;
                 }
                 __syncwarp();
@@ -647,18 +677,17 @@ __global__ void __launch_bounds__(kTileWarps * 32) k_perft_tile(const uint4 *__r
         const u64 pm = ws.pmult[pr];
         int nm, nw;
         { const uint2 yl = ws.plegal[pr]; leaf_counts_from_parent(yl.x, yl.y, pres, action, s_lut, nm, nw); }
-        acc_nodes += (u64)nm * pm;
-        const u64 w = (u64)nw * pm, b = nm ? 0ull : pm;
-        if (xm) { acc_w0 += w; acc_b0 += b; } else { acc_w1 += w; acc_b1 += b; }
+        acc.add(nm, nw, pm, xm == 0);
     }
-    acc_nodes = warp_sum(acc_nodes); acc_w0 = warp_sum(acc_w0); acc_w1 = warp_sum(acc_w1);
-    acc_b0 = warp_sum(acc_b0); acc_b1 = warp_sum(acc_b1);
+    acc.finish(((uniform_parity + rem0 - 1) & 1) != 0);     // who moves one ply above the target
+    const u64 t_nodes = warp_sum(acc.nodes), t_w0 = warp_sum(acc.w0), t_w1 = warp_sum(acc.w1);
+    const u64 t_b0 = warp_sum(acc.b0), t_b1 = warp_sum(acc.b1);
     if (lane == 0) {
-        ws.acc[0 * kRows + depth] += acc_nodes;
-        ws.acc[1 * kRows + depth] += acc_w0;
-        ws.acc[2 * kRows + depth] += acc_w1;
-        ws.acc[3 * kRows + depth - 1] += acc_b0;
-        ws.acc[4 * kRows + depth - 1] += acc_b1;
+        ws.acc[0 * kRows + depth] += t_nodes;
+        ws.acc[1 * kRows + depth] += t_w0;
+        ws.acc[2 * kRows + depth] += t_w1;
+        ws.acc[3 * kRows + depth - 1] += t_b0;
+        ws.acc[4 * kRows + depth - 1] += t_b1;
     }
     __syncwarp();
     for (int k = lane; k < 5 * kRows; k += 32)
@@ -671,19 +700,24 @@ int run_perft(Call &call, const uint4 *roots, const uint64_t *mult, size_t n_roo
     cudaStream_t s = call.stream();
     Ctx *c = call.ctx();
     // device block: counters[5][17], frontier size, dfs work counter
-    u64 *d_ctr = (u64 *)call.temp((5 * kRows + 2) * sizeof(u64), true);
+    u64 *d_ctr = (u64 *)call.temp((5 * kRows + 3) * sizeof(u64), true);
     if (!d_ctr) return call.status();
     u64 *d_count = d_ctr + 5 * kRows, *d_next = d_count + 1;
+    unsigned *d_flags = (unsigned *)(d_next + 1);
 
     uint4 *cur_s = (uint4 *)call.temp(n_roots * 16);
     u64 *cur_m = (u64 *)call.temp(n_roots * 8);
     if (!cur_s || !cur_m) return call.status();
     k_perft_filter_roots<<<(unsigned)((n_roots + kBlock - 1) / kBlock), kBlock, 0, s>>>(
-        roots, (const u64 *)mult, n_roots, depth, cur_s, cur_m, d_count, d_ctr);
+        roots, (const u64 *)mult, n_roots, depth, cur_s, cur_m, d_count, d_ctr, d_flags);
     QK_CUDA(cudaGetLastError());
     u64 n_cur = 0;
+    unsigned root_flags = 0;
     QK_CUDA(cudaMemcpyAsync(&n_cur, d_count, sizeof(u64), cudaMemcpyDeviceToHost, s));
+    QK_CUDA(cudaMemcpyAsync(&root_flags, d_flags, sizeof(unsigned), cudaMemcpyDeviceToHost, s));
     QK_CUDA(cudaStreamSynchronize(s));
+    const bool one_side = (root_flags & 3u) == 1u || (root_flags & 3u) == 2u, small_mult = (root_flags & 4u) == 0;
+    const int root_parity = (root_flags & 2u) ? 1 : 0;
 
     // Widen level by level until every lane can have its own items, then walk depth-first with k_perft_tile
     // (one item per lane, last level dealt out to full warps).  Measured from the empty board, in ms, for
@@ -730,8 +764,11 @@ int run_perft(Call &call, const uint4 *roots, const uint64_t *mult, size_t n_roo
             if (use_tile) {
                 int per_sm = 0;
                 const size_t smem = kTileWarps * tile_warp_bytes(rem);
-                QK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_perft_tile, kTileWarps * 32, smem));
-                k_perft_tile<<<c->sms * (per_sm > 0 ? per_sm : 1), kTileWarps * 32, smem, s>>>(cur_s, cur_m, n_cur, d, depth, d_next, d_ctr);
+                const bool fast = one_side && small_mult && !getenv("QK_PERFT_TILE_GENERIC");
+                void (*tile)(const uint4 *, const u64 *, u64, int, int, int, u64 *, u64 *) = fast ? k_perft_tile<true> : k_perft_tile<false>;
+                QK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tile, kTileWarps * 32, smem));
+                tile<<<c->sms * (per_sm > 0 ? per_sm : 1), kTileWarps * 32, smem, s>>>(cur_s, cur_m, n_cur, d, depth,
+                                                                                     (root_parity + d) & 1, d_next, d_ctr);
             } else if (use_lane) {
                 int per_sm = 0;
                 QK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_perft_lane, kLaneWarps * 32, 0));

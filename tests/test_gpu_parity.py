@@ -329,8 +329,12 @@ def test_perft_lane_kernel_matches_warp_kernel_and_oracle(monkeypatch):
     mult = np.arange(1, 65, dtype=np.uint64)
     mid = O.make_roots(3000, seed=17, min_plies=4, span=5)
     ref6 = None
-    for mode in ("tile", "warp", "lane", "tile-small"):
+    for mode in ("tile", "tile-generic", "warp", "lane", "tile-small"):
         monkeypatch.setenv("QK_PERFT_KERNEL", mode[:4])
+        if mode == "tile-generic":      # 64-bit multiplicities / mixed sides-to-move form, on inputs that allow the fast one
+            monkeypatch.setenv("QK_PERFT_TILE_GENERIC", "1")
+        else:
+            monkeypatch.delenv("QK_PERFT_TILE_GENERIC", raising=False)
         if mode == "tile-small":        # the depth-first kernel straight on the 64 mixed-parity roots: every frame depth
             monkeypatch.setenv("QK_PERFT_MIN_ITEMS", "1")
         p = B.perft(e, 6)
@@ -340,6 +344,12 @@ def test_perft_lane_kernel_matches_warp_kernel_and_oracle(monkeypatch):
             for k in o:
                 assert np.array_equal(g[k], o[k]), (mode, depth, k)
         g = B.perft(mid, 4)
+        if mode == "tile-small":        # same-side roots with multiplicities beyond 32 bits: generic form, exact sums
+            same = roots[O.validate(roots)[0] == 0][:8]
+            big = (np.arange(1, len(same) + 1, dtype=np.uint64) << np.uint64(33)) + np.uint64(7)
+            gb, ob = B.perft(same, 3, big), O.perft(same, 3, big)
+            for k in ob:
+                assert np.array_equal(gb[k], ob[k]), (mode, "big multiplicities", k)
         ref6 = ref6 or g
         for k in g:
             assert np.array_equal(g[k], ref6[k]), (mode, k)

@@ -434,19 +434,23 @@ __global__ void __launch_bounds__(kLaneWarps * 32) k_perft_lane(const uint4 *__r
 // its item (no shared-memory atomics: 64-bit ones are CAS loops and every lane would hit the same row).
 // The target depth accumulates weighted in registers.
 static constexpr int kTileWarps = 4;                  // 128 threads per CTA
-static constexpr int kTileMaxRem = kLaneFrames + 1;   // 4 warps x (fixed part + 2 x (rem - 1) x 256 B) must stay below 48 KB
+static constexpr int kTileMaxRem = kLaneFrames;       // 4 warps x (fixed part + 2 x (rem - 1) x 256 B) must stay below 48 KB
 static constexpr unsigned kTileQueue = 1024;          // ring of dealt entries: < 32 left over + what one pass adds
 static constexpr unsigned kTileParents = 64;          // ring of parent records: <= 31 still referenced + 32 new
 static constexpr unsigned kTileFlushEvery = 4000;     // evaluations per lane before its packed counters could overflow
 
+// what a dealt leaf parent needs from its parent: one 48-byte record = three vector loads from one base address
+struct __attribute__((aligned(16))) ParentRec {
+    uint4 rz;                 // line presence: rows (A|B, C|D), zones (A|B, C|D)
+    uint4 cl;                 // line presence: columns (A|B, C|D); what the player NOT to move at the parent could play (lo, hi)
+    u64 mult;                 // the item's multiplicity
+    u64 pad;
+};
 // per-warp shared memory; the two per-level arrays are sized for the job (dynamic shared memory), so shallow
 // remainders -- the wide, early part of the game -- run at a higher occupancy
 struct TileScratch {
     unsigned short queue[kTileQueue];                 // ring: (mover << 12 | parent record << 6 | action) of a dealt leaf parent
-    uint4 ppres_rz[kTileParents];                     // ring of parent records (a node two plies above the target): its
-    uint2 ppres_c[kTileParents];                      // ... line presence (rows, zones | columns),
-    uint2 plegal[kTileParents];                       // ... what the player NOT to move there could play,
-    u64 pmult[kTileParents];                          // ... and its item's multiplicity
+    ParentRec parent[kTileParents];                   // ring of parent records (nodes two plies above the target)
     u64 acc[5 * kRows];                               // this warp's weighted share of the counters
     u64 levels[1][32];                                // frame[rem0 - 1][32]: masks of unvisited children per level and lane,
                                                       // then cnt[rem0 - 1][32]: moves (bits 0-25) | winning moves (26-51) | blocked (52-63)
@@ -610,10 +614,9 @@ __global__ void __launch_bounds__(kTileWarps * 32) k_perft_tile(const uint4 *__r
         if (givers) {
             const uint32_t rec = (q_parents + (uint32_t)__popc(givers & ((1u << lane) - 1u))) & (kTileParents - 1);
             if (cnt_all) {
-                ws.ppres_rz[rec] = make_uint4(give_pres.r01, give_pres.r23, give_pres.z01, give_pres.z23);
-                ws.ppres_c[rec] = make_uint2(give_pres.c01, give_pres.c23);
-                ws.plegal[rec] = make_uint2(give_ylo, give_yhi);
-                ws.pmult[rec] = m;
+                ws.parent[rec].rz = make_uint4(give_pres.r01, give_pres.r23, give_pres.z01, give_pres.z23);
+                ws.parent[rec].cl = make_uint4(give_pres.c01, give_pres.c23, give_ylo, give_yhi);
+                ws.parent[rec].mult = m;
             }
             q_parents += (uint32_t)__popc(givers);
             const uint32_t n_all = (uint32_t)__reduce_add_sync(kFull, cnt_all);
@@ -634,12 +637,11 @@ __global__ void __launch_bounds__(kTileWarps * 32) k_perft_tile(const uint4 *__r
                 while (q_tail - q_head >= 32) {
                     const uint32_t e = ws.queue[(q_head + lane) & (kTileQueue - 1)], pr = (e >> 6) & (kTileParents - 1), xm = e >> 12;
                     const int action = (int)(e & 63u);
-                    const uint4 rz = ws.ppres_rz[pr];
-                    const uint2 cc = ws.ppres_c[pr];
-                    const Presence pres = { rz.x, rz.y, rz.z, rz.w, cc.x, cc.y };
-                    const u64 pm = ws.pmult[pr];
+                    const uint4 rz = ws.parent[pr].rz, cl = ws.parent[pr].cl;
+                    const Presence pres = { rz.x, rz.y, rz.z, rz.w, cl.x, cl.y };
+                    const u64 pm = FAST ? (u64)*reinterpret_cast<const uint32_t *>(&ws.parent[pr].mult) : ws.parent[pr].mult;
                     int nm, nw;
-                    { const uint2 yl = ws.plegal[pr]; leaf_counts_from_parent(yl.x, yl.y, pres, action, s_lut, nm, nw); }
+                    leaf_counts_from_parent(cl.z, cl.w, pres, action, s_lut, nm, nw);
                     acc.add(nm, nw, pm, xm == 0);                     // the leaf parent's mover is the OTHER player
                     q_head += 32;
                 }
@@ -671,12 +673,11 @@ __global__ void __launch_bounds__(kTileWarps * 32) k_perft_tile(const uint4 *__r
     if (lane < q_tail - q_head) {
         const uint32_t e = ws.queue[(q_head + lane) & (kTileQueue - 1)], pr = (e >> 6) & (kTileParents - 1), xm = e >> 12;
         const int action = (int)(e & 63u);
-        const uint4 rz = ws.ppres_rz[pr];
-        const uint2 cc = ws.ppres_c[pr];
-        const Presence pres = { rz.x, rz.y, rz.z, rz.w, cc.x, cc.y };
-        const u64 pm = ws.pmult[pr];
+        const uint4 rz = ws.parent[pr].rz, cl = ws.parent[pr].cl;
+        const Presence pres = { rz.x, rz.y, rz.z, rz.w, cl.x, cl.y };
+        const u64 pm = ws.parent[pr].mult;
         int nm, nw;
-        { const uint2 yl = ws.plegal[pr]; leaf_counts_from_parent(yl.x, yl.y, pres, action, s_lut, nm, nw); }
+        leaf_counts_from_parent(cl.z, cl.w, pres, action, s_lut, nm, nw);
         acc.add(nm, nw, pm, xm == 0);
     }
     acc.finish(((uniform_parity + rem0 - 1) & 1) != 0);     // who moves one ply above the target

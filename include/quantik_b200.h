@@ -72,6 +72,15 @@ QK_API int qk_abi_version(void);
 QK_API int qk_init(int dev);
 QK_API int qk_shutdown(int dev);
 QK_API const char *qk_last_error(void);
+/* Tuning / testing switches, process-wide; every option defaults to 0 = the library's own choice, and
+ * the library never reads the environment.  They select between kernels that compute the same result
+ * (tests/ uses them to put every variant through the parity checks, scripts/ for A/B timing):
+ *   "perft_kernel"        0 auto | 1 k_perft_tile | 2 k_perft_lane | 3 k_perft_dfs (warp per item)
+ *   "perft_min_items"     > 0: start the depth-first kernel as soon as the frontier has this many items
+ *   "perft_tile_generic"  1: k_perft_tile without the one-side / 32-bit-multiplicity fast form
+ *   "playout_variant"     0 auto | 1 single-root kernel, root record hoisted | 2 general kernel for one root
+ *   "dedup_mode"          0 auto | 1 one-level table insert | 2 partitioned (two-level) insert            */
+QK_API int qk_set_option(const char *name, long long value);
 /* SM count and clock (kHz) of an initialised device; either pointer may be NULL. */
 QK_API int qk_device_info(int dev, int *sm_count, int *sm_clock_khz);
 
@@ -172,6 +181,10 @@ QK_API int qk_book_level(const uint16_t *states, size_t n, int color_swap, uint1
  * with larger sizes on EVERY rank).  world <= QK_MAX_WORLD.  All three are synchronous.                      */
 #define QK_MAX_WORLD 16
 QK_API int qk_inbox_bytes(int world, size_t slots_per_src, size_t *bytes);
+/* qk_payload_owner : the owner rank (0..world-1) of each canonical payload -- the partition function of the
+ *                 scatter kernels, for callers that route classes themselves (quantik_b200.dist's NCCL
+ *                 all-to-all path uses the same function, so both exchanges agree rank by rank).            */
+QK_API int qk_payload_owner(const uint16_t *payloads, size_t n, int world, uint8_t *owner, int dev, void *stream);
 QK_API int qk_canon_dedup_scatter(const uint16_t *states, const uint64_t *mult, size_t n, int flags,
                                   void *const *inbox, int world, int rank, size_t slots_per_src,
                                   uint64_t *sent, int dev, void *stream);
@@ -251,6 +264,13 @@ QK_API int qk_random_roots(uint64_t seed, uint64_t first, size_t n, int min_plie
 QK_API int qk_perft(const uint16_t *roots, const uint64_t *mult, size_t n_roots, int depth,
              uint64_t *nodes, uint64_t *wins_p0, uint64_t *wins_p1,
              uint64_t *blocked_p0_loses, uint64_t *blocked_p1_loses, int dev, void *stream);
+
+/* qk_perft_probe    <- the cost probe behind the static partitioning of the enumeration
+ *                      ("LPT/greedy by probe cost"; the reference chunks its frontier by
+ *                      count, examples/generate_opening_book.py:294-332): cost[i] = number of move
+ *                      sequences of length 2 below root i (0 for finished / invalid roots), one
+ *                      thread per root.  quantik_b200.dist deals roots to ranks by it.             */
+QK_API int qk_perft_probe(const uint16_t *roots, size_t n_roots, uint32_t *cost, int dev, void *stream);
 
 /* ---- measurement aid ------------------------------------------------------------------
  * Runs a dependency-free integer micro-kernel and reports warp-instructions x 32 per

@@ -2,7 +2,9 @@
 // argument checks, per-device context, host<->device staging.  No rules live here.
 #include "qk_common.cuh"
 
+#include <atomic>
 #include <mutex>
+#include <string.h>
 #include <stdio.h>
 
 namespace qk {
@@ -10,6 +12,9 @@ namespace qk {
 static thread_local std::string g_error;
 static Ctx g_ctx[64];
 static std::mutex g_mu;
+static std::atomic<long long> g_option[OPT_COUNT];
+
+long long option(Option o) { return g_option[o].load(std::memory_order_relaxed); }
 
 void set_error(const std::string &msg) { g_error = msg; }
 
@@ -103,6 +108,17 @@ void *Call::temp(size_t bytes, bool zero)
     return d;
 }
 
+void Call::release(void *p)
+{
+    for (size_t i = 0; i < temps_.size(); ++i)
+        if (temps_[i] == p) {
+            temps_[i] = temps_.back();
+            temps_.pop_back();
+            cudaFreeAsync(p, stream_);
+            return;
+        }
+}
+
 int Call::sync()
 {
     QK_CUDA(cudaStreamSynchronize(stream_));
@@ -113,10 +129,17 @@ int Call::finish()
 {
     if (status_ != QK_OK) return status_;
     QK_CUDA(cudaGetLastError());
-    for (const Back &b : backs_) QK_CUDA(cudaMemcpyAsync(b.host, b.dev, b.bytes, cudaMemcpyDeviceToHost, stream_));
-    backs_.clear();
-    for (void *t : temps_) QK_CUDA(cudaFreeAsync(t, stream_));
-    temps_.clear();
+    std::vector<Back> backs;
+    backs.swap(backs_);
+    for (const Back &b : backs) QK_CUDA(cudaMemcpyAsync(b.host, b.dev, b.bytes, cudaMemcpyDeviceToHost, stream_));
+    std::vector<void *> temps;
+    temps.swap(temps_);                       // whatever happens below, ~Call must not free these a second time
+    cudaError_t first = cudaSuccess;
+    for (void *t : temps) {
+        const cudaError_t e = cudaFreeAsync(t, stream_);
+        if (first == cudaSuccess) first = e;
+    }
+    QK_CUDA(first);
     if (any_host_) QK_CUDA(cudaStreamSynchronize(stream_));
     return QK_OK;
 }
@@ -140,6 +163,17 @@ extern "C" {
 int qk_abi_version(void) { return QK_ABI_VERSION; }
 
 const char *qk_last_error(void) { return g_error.c_str(); }
+
+int qk_set_option(const char *name, long long value)
+{
+    static const char *const names[OPT_COUNT] = { "perft_kernel", "perft_min_items", "perft_tile_generic", "playout_variant",
+                                                  "dedup_mode" };
+    QK_REQUIRE(name, "qk_set_option: name is NULL");
+    for (int i = 0; i < OPT_COUNT; ++i)
+        if (strcmp(name, names[i]) == 0) { g_option[i].store(value, std::memory_order_relaxed); return QK_OK; }
+    set_error(std::string("qk_set_option: unknown option '") + name + "'");
+    return QK_E_BAD_ARG;
+}
 
 int qk_init(int dev)
 {
@@ -501,6 +535,33 @@ int qk_random_roots(uint64_t seed, uint64_t first, size_t n, int min_plies, int 
     uint4 *d_out = (uint4 *)call.out(out_states, n * 16);
     QK_CHECK(call);
     int rc = launch_random_roots(seed, first, n, min_plies, span, d_out, call.ctx(), call.stream());
+    if (rc != QK_OK) return rc;
+    return call.finish();
+}
+
+int qk_payload_owner(const uint16_t *payloads, size_t n, int world, uint8_t *owner, int dev, void *stream)
+{
+    QK_REQUIRE((payloads && owner) || n == 0, "qk_payload_owner: NULL argument");
+    QK_REQUIRE(world >= 1 && world <= QK_MAX_WORLD, "qk_payload_owner: world out of range");
+    if (n == 0) return QK_OK;
+    QK_BEGIN(call);
+    const uint4 *d_in = (const uint4 *)call.in(payloads, n * 16);
+    uint8_t *d_out = (uint8_t *)call.out(owner, n);
+    QK_CHECK(call);
+    int rc = launch_payload_owner(d_in, n, world, d_out, call.ctx(), call.stream());
+    if (rc != QK_OK) return rc;
+    return call.finish();
+}
+
+int qk_perft_probe(const uint16_t *roots, size_t n_roots, uint32_t *cost, int dev, void *stream)
+{
+    QK_REQUIRE((roots && cost) || n_roots == 0, "qk_perft_probe: NULL argument");
+    if (n_roots == 0) return QK_OK;
+    QK_BEGIN(call);
+    const uint4 *d_roots = (const uint4 *)call.in(roots, n_roots * 16);
+    uint32_t *d_cost = (uint32_t *)call.out(cost, n_roots * 4);
+    QK_CHECK(call);
+    int rc = launch_perft_probe(d_roots, n_roots, d_cost, call.ctx(), call.stream());
     if (rc != QK_OK) return rc;
     return call.finish();
 }

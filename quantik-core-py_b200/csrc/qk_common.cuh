@@ -19,6 +19,11 @@ struct Ctx {
     cudaMemPool_t pool = nullptr;
 };
 
+// Tuning / testing switches (qk_set_option in include/quantik_b200.h).  Process-wide, 0 = the default
+// behaviour; the library never reads the environment.
+enum Option { OPT_PERFT_KERNEL = 0, OPT_PERFT_MIN_ITEMS, OPT_PERFT_TILE_GENERIC, OPT_PLAYOUT_VARIANT, OPT_DEDUP_MODE, OPT_COUNT };
+long long option(Option o);
+
 void set_error(const std::string &msg);
 int cuda_fail(cudaError_t e, const char *what);          // records text, returns QK_E_CUDA
 Ctx *get_ctx(int dev);                                   // nullptr (+error text) when not initialised
@@ -43,6 +48,7 @@ public:
     const void *in(const void *p, size_t bytes);          // nullptr stays nullptr
     void *out(void *p, size_t bytes, bool zero = false);  // nullptr stays nullptr
     void *temp(size_t bytes, bool zero = false);
+    void release(void *temp_ptr);                         // early stream-ordered free of a temp()
     int finish();                                         // copy-backs, frees, sync if host buffers were used
     int sync();
 
@@ -78,6 +84,7 @@ int launch_playouts(const uint4 *roots, size_t n_roots, uint32_t rollouts, uint6
                     int8_t *per_playout, uint8_t *per_plies, void *rootrec_scratch, Ctx *c, cudaStream_t s);
 size_t playout_scratch_bytes(size_t n_roots);
 int launch_random_roots(uint64_t seed, uint64_t first, size_t n, int min_plies, int span, uint4 *out, Ctx *c, cudaStream_t s);
+int launch_perft_probe(const uint4 *roots, size_t n, uint32_t *cost, Ctx *c, cudaStream_t s);
 int run_perft(Call &call, const uint4 *roots, const uint64_t *mult, size_t n_roots, int depth, uint64_t *host_out /*5 x (depth+1)*/);
 int run_dedup(Call &call, const uint4 *states, const uint64_t *mult, size_t n, int color_swap,
               uint16_t *uniq_host_or_dev, uint64_t *uniq_mult, size_t cap, size_t *n_uniq);
@@ -87,6 +94,7 @@ int run_book_level(Call &call, const uint4 *parents, size_t n, int color_swap, u
                    size_t cap, size_t *n_uniq, uint64_t *h_stats);
 struct Peers { void *inbox[QK_MAX_WORLD]; int world; int rank; size_t slots_per_src; };
 size_t inbox_bytes(int world, size_t slots_per_src);
+int launch_payload_owner(const uint4 *payloads, size_t n, int world, uint8_t *owner, Ctx *c, cudaStream_t s);
 int run_dedup_scatter(Call &call, const uint4 *states, const uint64_t *mult, size_t n, int flags, const Peers &peers, uint64_t *h_sent);
 int run_bfs_level_scatter(Call &call, const uint4 *parents, const uint64_t *mult, size_t n, int flags, size_t local_cap,
                           const Peers &peers, uint64_t *h_stats, uint64_t *h_sent);

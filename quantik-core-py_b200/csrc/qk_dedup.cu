@@ -521,6 +521,24 @@ __device__ __forceinline__ int owner_of(u64 hi, u64 lo, int world)
     return (int)__umulhi((uint32_t)(mix(lo, hi) >> 32), (uint32_t)world);
 }
 
+__global__ void __launch_bounds__(kBlock) k_payload_owner(const uint4 *__restrict__ payloads, size_t n, int world, uint8_t *__restrict__ owner)
+{
+    const size_t i = blockIdx.x * (size_t)kBlock + threadIdx.x;
+    if (i >= n) return;
+    const uint4 v = __ldg(payloads + i);
+    // Key128 limbs = big-endian words of the payload bytes (qk_bits.cuh sorted_image / key_to_state)
+    const u64 hi = ((u64)prmt(v.x, 0, 0x0123) << 32) | prmt(v.y, 0, 0x0123), lo = ((u64)prmt(v.z, 0, 0x0123) << 32) | prmt(v.w, 0, 0x0123);
+    owner[i] = (uint8_t)owner_of(hi, lo, world);
+}
+
+int launch_payload_owner(const uint4 *payloads, size_t n, int world, uint8_t *owner, Ctx *c, cudaStream_t s)
+{
+    (void)c;
+    k_payload_owner<<<(unsigned)((n + kBlock - 1) / kBlock), kBlock, 0, s>>>(payloads, n, world, owner);
+    QK_CUDA(cudaGetLastError());
+    return QK_OK;
+}
+
 // local table -> the owners' inboxes.  Per 256 slots a block counts its entries per destination in shared
 // memory, reserves one range per destination in the SOURCE-side cursor (regions are per source, so no remote
 // atomics), then every thread stores its (key, multiplicity) straight into the peer's memory.

@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(kBlock) k_perft_filter_roots(const uint4 *__re
     const unsigned lane = threadIdx.x & 31u;
     u64 m = 0, blocked = 0;
     bool keep = false;
-    unsigned seen = 0;
+    unsigned seen = 0, pieces = 0;
     State4 s = { 0, 0, 0, 0 };
     if (i < n) {
         s = to_state(__ldg(roots + i));
@@ -56,12 +56,17 @@ __global__ void __launch_bounds__(kBlock) k_perft_filter_roots(const uint4 *__re
         int player;
         if (win_status(s) == 0) {                       // a finished root has nothing below it
             if (validate(s, &player) != 0) blocked = m; // generate_legal_moves -> (0, {})  (move.py:223-225)
-            else { keep = true; seen = (1u << player) | ((m >> 32) ? 4u : 0u); }
+            else {
+                keep = true; seen = (1u << player) | ((m >> 32) ? 4u : 0u);
+                pieces = (unsigned)(popc(s.x) + popc(s.y) + popc(s.z) + popc(s.w));
+            }
         }
     }
-    // what the frontier looks like (k_perft_tile has a faster form for one side to move + 32-bit multiplicities)
+    // what the frontier looks like: k_perft_tile has a faster form for one side to move + 32-bit multiplicities,
+    // and the choice tile / lane walk goes by the FULLEST root (flags[1] = most pieces on a kept root)
     seen = __reduce_or_sync(kFull, seen);
-    if (lane == 0 && seen) atomicOr(flags, seen);
+    pieces = __reduce_max_sync(kFull, pieces);
+    if (lane == 0 && seen) { atomicOr(flags, seen); atomicMax(flags + 1, pieces); }
     u64 tot = warp_sum(m), blk = warp_sum(blocked);
     unsigned kmask = __ballot_sync(kFull, keep);
     u64 base = 0;
@@ -80,6 +85,9 @@ __global__ void __launch_bounds__(kBlock) k_perft_filter_roots(const uint4 *__re
 
 // ------------------------------------------------------------------ one level, thread per position
 // _process_parent_state (game_stats.py:384-424): total_moves, wins by the mover, children
+// COUNT_ONLY: the sizing pass -- only the number of children the level will emit (the next frontier is then
+// allocated exactly, not at 64 children per parent)
+template <bool COUNT_ONLY>
 __global__ void __launch_bounds__(kBlock) k_perft_expand(const uint4 *__restrict__ in_states, const u64 *__restrict__ in_mult,
                                                           size_t n, int d, uint4 *__restrict__ out_states,
                                                           u64 *__restrict__ out_mult, u64 *__restrict__ out_count,
@@ -106,9 +114,14 @@ __global__ void __launch_bounds__(kBlock) k_perft_expand(const uint4 *__restrict
         if (mover == 0) { c_w0 = (u64)n_wins * m; c_b0 = n_moves ? 0 : m; }
         else            { c_w1 = (u64)n_wins * m; c_b1 = n_moves ? 0 : m; }
     }
+    uint32_t cnt = (uint32_t)(popc(nl) + popc(nh)), incl = cnt;
+    if (COUNT_ONLY) {
+        const uint32_t total = (uint32_t)__reduce_add_sync(kFull, cnt);
+        if (lane == 0 && total) atomicAdd(out_count, (u64)total);
+        return;
+    }
     c_nodes = warp_sum(c_nodes); c_w0 = warp_sum(c_w0); c_w1 = warp_sum(c_w1); c_b0 = warp_sum(c_b0); c_b1 = warp_sum(c_b1);
     // exclusive scan of the children counts inside the warp, one reservation per warp
-    uint32_t cnt = (uint32_t)(popc(nl) + popc(nh)), incl = cnt;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(kFull, incl, o); if (lane >= (unsigned)o) incl += t; }
     uint32_t total = __shfl_sync(kFull, incl, 31);
@@ -695,12 +708,48 @@ __global__ void __launch_bounds__(kTileWarps * 32) k_perft_tile(const uint4 *__r
         if (ws.acc[k]) atomicAdd(counters + k, ws.acc[k]);
 }
 
+// ------------------------------------------------------------------ cost probe for the static partitioning
+// cost[i] = move sequences of length 2 below root i: what quantik_b200.dist sorts the roots by before it deals
+// them to the ranks (SURVEY 8e "LPT/greedy by probe cost")
+__global__ void __launch_bounds__(kBlock) k_perft_probe(const uint4 *__restrict__ roots, size_t n, uint32_t *__restrict__ cost)
+{
+    const size_t i = blockIdx.x * (size_t)kBlock + threadIdx.x;
+    if (i >= n) return;
+    const State4 s = to_state(__ldg(roots + i));
+    uint32_t c = 0;
+    int player;
+    if (win_status(s) == 0 && validate(s, &player) == 0) {
+        uint32_t lo, hi, wab, wcd;
+        legal_masks(s, player, lo, hi);
+        winning_squares(s, wab, wcd);
+        for (uint32_t w = lo & ~wab; w; w &= w - 1) {
+            int nm, nw;
+            leaf_parent_counts_for(apply_action(s, player, __ffs((int)w) - 1), player ^ 1, nm, nw);
+            c += (uint32_t)nm;
+        }
+        for (uint32_t w = hi & ~wcd; w; w &= w - 1) {
+            int nm, nw;
+            leaf_parent_counts_for(apply_action(s, player, 32 + __ffs((int)w) - 1), player ^ 1, nm, nw);
+            c += (uint32_t)nm;
+        }
+    }
+    cost[i] = c;
+}
+
+int launch_perft_probe(const uint4 *roots, size_t n, uint32_t *cost, Ctx *c, cudaStream_t s)
+{
+    (void)c;
+    k_perft_probe<<<(unsigned)((n + kBlock - 1) / kBlock), kBlock, 0, s>>>(roots, n, cost);
+    QK_CUDA(cudaGetLastError());
+    return QK_OK;
+}
+
 // ------------------------------------------------------------------ host driver
 int run_perft(Call &call, const uint4 *roots, const uint64_t *mult, size_t n_roots, int depth, uint64_t *host_out)
 {
     cudaStream_t s = call.stream();
     Ctx *c = call.ctx();
-    // device block: counters[5][17], frontier size, dfs work counter
+    // device block: counters[5][17], frontier size, dfs work counter, root flags (2 words)
     u64 *d_ctr = (u64 *)call.temp((5 * kRows + 3) * sizeof(u64), true);
     if (!d_ctr) return call.status();
     u64 *d_count = d_ctr + 5 * kRows, *d_next = d_count + 1;
@@ -712,11 +761,11 @@ int run_perft(Call &call, const uint4 *roots, const uint64_t *mult, size_t n_roo
     k_perft_filter_roots<<<(unsigned)((n_roots + kBlock - 1) / kBlock), kBlock, 0, s>>>(
         roots, (const u64 *)mult, n_roots, depth, cur_s, cur_m, d_count, d_ctr, d_flags);
     QK_CUDA(cudaGetLastError());
-    u64 n_cur = 0;
-    unsigned root_flags = 0;
-    QK_CUDA(cudaMemcpyAsync(&n_cur, d_count, sizeof(u64), cudaMemcpyDeviceToHost, s));
-    QK_CUDA(cudaMemcpyAsync(&root_flags, d_flags, sizeof(unsigned), cudaMemcpyDeviceToHost, s));
+    struct { u64 count, next; unsigned flags, max_pieces; } head = { 0, 0, 0, 0 };      // = d_count, d_next, d_flags[0..1]
+    QK_CUDA(cudaMemcpyAsync(&head, d_count, sizeof head, cudaMemcpyDeviceToHost, s));
     QK_CUDA(cudaStreamSynchronize(s));
+    u64 n_cur = head.count;
+    const unsigned root_flags = head.flags;
     const bool one_side = (root_flags & 3u) == 1u || (root_flags & 3u) == 2u, small_mult = (root_flags & 4u) == 0;
     const int root_parity = (root_flags & 2u) ? 1 : 0;
 
@@ -725,9 +774,9 @@ int run_perft(Call &call, const uint4 *roots, const uint64_t *mult, size_t n_roo
     // tile / warp-per-item / plain lane-per-item: depth 6 1.7 / 3.5 / 4.0, depth 7 38 / 105 / 62, depth 8 835 / 2688 / 1290.
     u64 want_warp_items = (u64)c->sms * 4 * kWarps * 8;
     u64 want_lane_items = (u64)c->sms * 2048 * 8;
-    const char *force = getenv("QK_PERFT_KERNEL");              // "tile" / "warp" / "lane": benchmarking aid
-    if (const char *mi = getenv("QK_PERFT_MIN_ITEMS"))          // testing aid: start the depth-first kernels on small frontiers
-        want_warp_items = want_lane_items = strtoull(mi, nullptr, 10);
+    const int force = (int)option(OPT_PERFT_KERNEL);                    // 1 tile / 2 lane / 3 warp: benchmarking aid
+    if (const long long mi = option(OPT_PERFT_MIN_ITEMS))               // testing aid: depth-first kernels on small frontiers
+        want_warp_items = want_lane_items = (u64)mi;
     int d = 0;
     while (n_cur > 0 && d < depth) {
         const int rem = depth - d;
@@ -738,34 +787,41 @@ int run_perft(Call &call, const uint4 *roots, const uint64_t *mult, size_t n_roo
         }
         const bool can_lane = rem <= kLaneFrames + 1;
         const bool can_tile = rem >= 2 && rem <= kTileMaxRem;
-        const bool too_big = n_cur * 64 > (1ull << 28);        // next frontier would not be worth materialising
         // As soon as every lane can have an item: the lane walk with the dealt last level (k_perft_tile) while the
         // target lies in the wide part of the game, the plain lane walk for the narrow end (measured below the
         // 10 946 depth-4 classes, tile / lane: to depth 12 11.7 / 15.6 s, to depth 14 108 / 91 s, to depth 16 147 / 128 s)
-        const bool go = n_cur >= want_lane_items || too_big;
+        bool go = n_cur >= want_lane_items;
+        u64 n_next = 0;
+        if (!go) {
+            // sizing pass: how many children this level emits (the frontier is allocated exactly; a level that
+            // would not be worth materialising is walked depth-first instead)
+            QK_CUDA(cudaMemsetAsync(d_count, 0, sizeof(u64), s));
+            k_perft_expand<true><<<(unsigned)((n_cur + kBlock - 1) / kBlock), kBlock, 0, s>>>(cur_s, cur_m, n_cur, d, nullptr, nullptr,
+                                                                                           d_count, d_ctr);
+            QK_CUDA(cudaGetLastError());
+            QK_CUDA(cudaMemcpyAsync(&n_next, d_count, sizeof(u64), cudaMemcpyDeviceToHost, s));
+            QK_CUDA(cudaStreamSynchronize(s));
+            go = n_next > (1ull << 28);
+        }
         bool use_tile = false, use_lane = false;
         if (go && !force) {
-            uint4 first;
-            QK_CUDA(cudaMemcpyAsync(&first, cur_s, sizeof first, cudaMemcpyDeviceToHost, s));
-            QK_CUDA(cudaStreamSynchronize(s));
-            const int target_pieces = __builtin_popcount(first.x) + __builtin_popcount(first.y) + __builtin_popcount(first.z) +
-                                      __builtin_popcount(first.w) + rem;
+            const int target_pieces = (int)head.max_pieces + depth;      // the fullest root decides
             use_tile = can_tile && target_pieces <= 12;
             use_lane = !use_tile && can_lane;
             use_tile = use_tile || (!use_lane && can_tile);
         }
         bool use_warp = go && !use_tile && !use_lane;           // (cannot happen for depth <= 16; the warp kernel is kept for A/B runs)
         if (force) {                                            // benchmarking aid: the two older kernels
-            use_tile = force[0] == 't' && can_tile && (n_cur >= want_lane_items || too_big);
-            use_lane = force[0] == 'l' && can_lane && (n_cur >= want_lane_items || too_big);
-            use_warp = force[0] == 'w' && (n_cur >= want_warp_items || too_big);
+            use_tile = force == 1 && can_tile && go;
+            use_lane = force == 2 && can_lane && go;
+            use_warp = force == 3 && (n_cur >= want_warp_items || go);
         }
         if (use_tile || use_lane || use_warp) {
             QK_CUDA(cudaMemsetAsync(d_next, 0, sizeof(u64), s));
             if (use_tile) {
                 int per_sm = 0;
                 const size_t smem = kTileWarps * tile_warp_bytes(rem);
-                const bool fast = one_side && small_mult && !getenv("QK_PERFT_TILE_GENERIC");
+                const bool fast = one_side && small_mult && !option(OPT_PERFT_TILE_GENERIC);
                 void (*tile)(const uint4 *, const u64 *, u64, int, int, int, u64 *, u64 *) = fast ? k_perft_tile<true> : k_perft_tile<false>;
                 QK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tile, kTileWarps * 32, smem));
                 tile<<<c->sms * (per_sm > 0 ? per_sm : 1), kTileWarps * 32, smem, s>>>(cur_s, cur_m, n_cur, d, depth,
@@ -780,14 +836,14 @@ int run_perft(Call &call, const uint4 *roots, const uint64_t *mult, size_t n_roo
             QK_CUDA(cudaGetLastError());
             break;
         }
-        uint4 *nxt_s = (uint4 *)call.temp(n_cur * 64 * 16);
-        u64 *nxt_m = (u64 *)call.temp(n_cur * 64 * 8);
+        uint4 *nxt_s = (uint4 *)call.temp((n_next ? n_next : 1) * 16);
+        u64 *nxt_m = (u64 *)call.temp((n_next ? n_next : 1) * 8);
         if (!nxt_s || !nxt_m) return call.status();
         QK_CUDA(cudaMemsetAsync(d_count, 0, sizeof(u64), s));
-        k_perft_expand<<<(unsigned)((n_cur + kBlock - 1) / kBlock), kBlock, 0, s>>>(cur_s, cur_m, n_cur, d, nxt_s, nxt_m, d_count, d_ctr);
+        k_perft_expand<false><<<(unsigned)((n_cur + kBlock - 1) / kBlock), kBlock, 0, s>>>(cur_s, cur_m, n_cur, d, nxt_s, nxt_m, d_count, d_ctr);
         QK_CUDA(cudaGetLastError());
-        QK_CUDA(cudaMemcpyAsync(&n_cur, d_count, sizeof(u64), cudaMemcpyDeviceToHost, s));
-        QK_CUDA(cudaStreamSynchronize(s));
+        call.release(cur_s); call.release(cur_m);               // stream-ordered: freed after the expansion has read them
+        n_cur = n_next;
         cur_s = nxt_s; cur_m = nxt_m;
         ++d;
     }

@@ -269,9 +269,9 @@ int launch_playouts(const uint4 *roots, size_t n_roots, uint32_t rollouts, uint6
     void (*kernel)(const PlayoutArgs) = cutoff ? (pp ? k_playout<true, true> : k_playout<true, false>)
                                                : (pp ? k_playout<false, true> : k_playout<false, false>);
     if (n_roots == 1 && !cutoff && !pp) {
-        const char *v = getenv("QK_PLAYOUT_VARIANT");           // benchmarking aid: general / hoist / (default) fresh
-        if (!v || v[0] == 'f') kernel = k_playout_single<true>;
-        else if (v[0] == 'h') kernel = k_playout_single<false>;
+        const long long v = option(OPT_PLAYOUT_VARIANT);        // benchmarking aid: 0 fresh (default) / 1 hoist / 2 general
+        if (v == 0) kernel = k_playout_single<true>;
+        else if (v == 1) kernel = k_playout_single<false>;
     }
     // persistent grid: exactly as many CTAs as are resident at once (no second wave), fewer only
     // when there are not enough playouts to give each thread one

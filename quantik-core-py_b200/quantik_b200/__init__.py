@@ -16,11 +16,11 @@ from .api import (  # noqa: F401
 )
 from .batch import (  # noqa: F401
     FEATURE_NAMES, SEED_DEFAULT, SEEDED_WEIGHTS, apply_moves, apply_symmetry, bfs_level, book_level, canon_dedup, canonical_keys, canonical_payloads,
-    decode_transform, encode_transform, eval_features, evaluate, guided_playouts, int_issue_peak, movegen_masks, opening_book_summary, orbit_sizes, perft,
+    decode_transform, encode_transform, eval_features, evaluate, guided_playouts, int_issue_peak, movegen_masks, opening_book_summary, orbit_sizes, payload_owner, perft, perft_probe,
     pipe_rates, playouts,
     random_roots, solve, symmetry_table, symmetry_table_rows, win_status,
 )
-from .engines import GpuRolloutEvaluator, gpu_default_evaluate, gpu_simulate  # noqa: F401
+from .engines import GpuRolloutEvaluator, batched_beam_engine, batched_mcts_engine, gpu_default_evaluate, gpu_simulate  # noqa: F401
 from ._native import QuantikB200Error, LIB_PATH  # noqa: F401
 
 __version__ = "0.1.0"

@@ -33,6 +33,7 @@ PROTOTYPES = {
     "qk_init": (c_int, [c_int]),
     "qk_shutdown": (c_int, [c_int]),
     "qk_last_error": (c_char_p, []),
+    "qk_set_option": (c_int, [c_char_p, ctypes.c_longlong]),
     "qk_device_info": (c_int, [c_int, POINTER(c_int), POINTER(c_int)]),
     "qk_movegen_masks": (c_int, [c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "qk_apply_moves": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_int, c_void_p]),
@@ -47,6 +48,7 @@ PROTOTYPES = {
     "qk_book_level": (c_int, [c_void_p, c_size_t, c_int, c_void_p, c_void_p, c_size_t, POINTER(c_size_t), c_void_p,
                               c_int, c_void_p]),
     "qk_inbox_bytes": (c_int, [c_int, c_size_t, POINTER(c_size_t)]),
+    "qk_payload_owner": (c_int, [c_void_p, c_size_t, c_int, c_void_p, c_int, c_void_p]),
     "qk_canon_dedup_scatter": (c_int, [c_void_p, c_void_p, c_size_t, c_int, POINTER(c_void_p), c_int, c_int, c_size_t,
                                        c_void_p, c_int, c_void_p]),
     "qk_bfs_level_scatter": (c_int, [c_void_p, c_void_p, c_size_t, c_int, c_size_t, POINTER(c_void_p), c_int, c_int,
@@ -62,6 +64,7 @@ PROTOTYPES = {
                                    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "qk_solve": (c_int, [c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "qk_random_roots": (c_int, [c_uint64, c_uint64, c_size_t, c_int, c_int, c_void_p, c_int, c_void_p]),
+    "qk_perft_probe": (c_int, [c_void_p, c_size_t, c_void_p, c_int, c_void_p]),
     "qk_perft": (c_int, [c_void_p, c_void_p, c_size_t, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                          c_int, c_void_p]),
     "qk_int_issue_peak": (c_int, [c_int, POINTER(c_double), POINTER(c_double)]),
@@ -108,6 +111,18 @@ def init(dev: int = 0) -> ctypes.CDLL:
                 check(lib.qk_init(dev))
                 _inited.add(dev)
     return lib
+
+
+def set_option(name: str, value: int) -> None:
+    """qk_set_option: tuning / testing switch (see include/quantik_b200.h); 0 restores the default."""
+    check(load().qk_set_option(name.encode(), int(value)))
+
+
+def shutdown(dev: int = 0) -> None:
+    """qk_shutdown(dev); the next call on that device initialises it again."""
+    with _lock:
+        check(load().qk_shutdown(dev))
+        _inited.discard(dev)
 
 
 def device_info(dev: int = 0):

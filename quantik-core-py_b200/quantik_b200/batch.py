@@ -268,6 +268,16 @@ def inbox_bytes(world: int, slots_per_src: int) -> int:
     return int(b.value)
 
 
+def payload_owner(payloads, world: int, device: Optional[int] = None):
+    """Owner rank of each canonical payload (qk_payload_owner) -> uint8 per payload."""
+    s, on_dev, d = _states_in(payloads)
+    d = _dev(device, on_dev, d)
+    lib = N.init(d)
+    out = _out((s.n,), np.uint8, on_dev, d)
+    N.check(lib.qk_payload_owner(s.ptr, s.n, int(world), out.ptr, d, _stream(on_dev, d)))
+    return out.obj
+
+
 def _ptr_array(ptrs):
     return (ctypes.c_void_p * len(ptrs))(*[int(p) for p in ptrs])
 
@@ -482,6 +492,17 @@ def perft(roots, depth: int, mult=None, device: Optional[int] = None) -> Dict[st
     arrs = [np.zeros(depth + 1, np.uint64) for _ in range(5)]
     N.check(lib.qk_perft(s.ptr, m.ptr, s.n, int(depth), *[a.ctypes.data for a in arrs], d, _stream(on_dev, d)))
     return dict(zip(["nodes", "wins_p0", "wins_p1", "blocked_p0_loses", "blocked_p1_loses"], arrs))
+
+
+def perft_probe(roots, device: Optional[int] = None):
+    """Cost probe for the static partitioning of an enumeration (qk_perft_probe): number of move sequences of
+    length 2 below every root -> uint32 per root."""
+    s, on_dev, d = _states_in(roots)
+    d = _dev(device, on_dev, d)
+    lib = N.init(d)
+    out = _out((s.n,), np.uint32, on_dev, d)
+    N.check(lib.qk_perft_probe(s.ptr, s.n, out.ptr, d, _stream(on_dev, d)))
+    return out.obj
 
 
 def symmetry_table_rows(p: Dict[str, np.ndarray]):

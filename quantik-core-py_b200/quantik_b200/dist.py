@@ -81,15 +81,33 @@ def sharded_root_tallies(roots: np.ndarray, rollouts: int, seed: int = B.SEED_DE
     return all_reduce_counts(out, device, group)
 
 
+def partition_by_cost(cost: np.ndarray, world: int):
+    """Static partition of weighted roots ("LPT/greedy by probe cost"): roots in largest-first order of
+    their probe cost (ties by index), dealt in serpentine order 0..w-1, w-1..0, ... -- the vectorised form of
+    greedy longest-processing-time assignment: after every two rounds all ranks hold nearly equal sums.
+    -> list of `world` index arrays (sorted ascending).  Same answer on every rank (pure function of cost)."""
+    cost = np.asarray(cost)
+    order = np.argsort(-cost.astype(np.int64), kind="stable")
+    pos = np.arange(len(order)) % (2 * world)
+    dest = np.where(pos < world, pos, 2 * world - 1 - pos)
+    return [np.sort(order[dest == r]) for r in range(world)]
+
+
 def sharded_perft(roots: np.ndarray, depth: int, mult: Optional[np.ndarray] = None, device: Optional[int] = None,
-                  group=None, perft_fn: Callable[..., Dict[str, np.ndarray]] = B.perft) -> Dict[str, np.ndarray]:
-    """BASELINE configs 2/5: roots dealt round-robin (rank r takes roots r, r+world, ...: sorted
-    canonical roots of similar size end up on different ranks), one all-reduce of the
-    5 x (depth+1) counters."""
+                  group=None, perft_fn: Callable[..., Dict[str, np.ndarray]] = B.perft,
+                  probe_fn: Callable[..., np.ndarray] = B.perft_probe) -> Dict[str, np.ndarray]:
+    """BASELINE configs 2/5: the weighted roots are dealt to the ranks largest-first by a depth-2 probe of their
+    subtrees (partition_by_cost; the reference chunks its frontier by count, examples/generate_opening_book.py:294-332),
+    every rank enumerates below its roots -- inside the GPU the depth-first kernels pull (root, child) items from one
+    atomic queue -- and ONE all-reduce of the 5 x (depth+1) counters closes the job."""
     rank, world = _world(group)
     roots = np.asarray(roots, np.uint16).reshape(-1, 8)
-    mine = roots[rank::world]
-    m = None if mult is None else np.asarray(mult, np.uint64)[rank::world]
+    if world > 1 and len(roots):
+        idx = partition_by_cost(probe_fn(roots, device=device), world)[rank]
+    else:
+        idx = np.arange(len(roots))
+    mine = np.ascontiguousarray(roots[idx])
+    m = None if mult is None else np.ascontiguousarray(np.asarray(mult, np.uint64)[idx])
     names = ["nodes", "wins_p0", "wins_p1", "blocked_p0_loses", "blocked_p1_loses"]
     local = np.zeros((5, depth + 1), np.int64)
     if len(mine):
@@ -114,15 +132,24 @@ def _as_i64_pairs(payloads):
     return torch.from_numpy(a.view(np.int64).reshape(-1, 2))
 
 
+def _mix64(h, l):
+    """qk_dedup.cu `mix` on torch int64 tensors (two's complement wrap-around = the kernel's u64 arithmetic)."""
+    x = (h * -7046029254386353131) ^ ((l + -2960836687051489901) * -4417276706812531889)
+    x = x ^ ((x >> 29) & 0x7FFFFFFFF)                 # logical shift
+    x = x * -4658895280553007687
+    return x ^ ((x >> 32) & 0xFFFFFFFF)
+
+
 def owner_rank(payloads, world: int):
-    """Owner of each canonical payload: a 64-bit mix of its two halves, mod world (torch int64 tensor)."""
+    """Owner of each canonical payload -- the SAME function as the library's owner_of (csrc/qk_dedup.cu): the two
+    big-endian 64-bit halves of the 16 payload bytes, mixed, high 32 bits scaled to [0, world).  Both exchange
+    implementations (NCCL all-to-all here, peer-memory scatter in the library) therefore partition the classes
+    over the ranks identically (torch int64 tensor)."""
     import torch
     p = _as_i64_pairs(payloads)
-    h = p[:, 0] * -7046029254386353131 + p[:, 1] * -4417276706812531889      # wraps mod 2^64
-    h = h ^ (h >> 29)
-    h = h * -4658895280553007687
-    h = h ^ (h >> 32)
-    return torch.remainder(h & 0x7FFFFFFFFFFFFFFF, world)
+    be = p.view(torch.uint8).reshape(-1, 2, 8).flip(-1).contiguous().view(torch.int64).reshape(-1, 2)
+    top = (_mix64(be[:, 1], be[:, 0]) >> 32) & 0xFFFFFFFF
+    return (top * int(world)) >> 32
 
 
 def exchange_by_owner(payloads, mult, group=None):
@@ -275,59 +302,81 @@ class PeerInboxes:
         return int(self.bufs[k][: 8 * self.world].view(torch.int64).sum().item())
 
 
-def _vote(failed: bool, device: int, group=None) -> bool:
-    """All-reduce(max) of a flag: the barrier between scatter and merge, and the agreement to retry."""
-    import torch
-    import torch.distributed as dist
-    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
-        return failed
-    t = torch.tensor([int(failed)], dtype=torch.int32, device=f"cuda:{device}")
-    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
-    return bool(t.item())
+VOTE_OK, VOTE_RETRY, VOTE_FATAL = 0, 1, 2
 
 
-def _max_over_ranks(value: int, device: int, group=None) -> int:
+def _vote(status: int, device: int, group=None, extra: Tuple[int, ...] = ()) -> Tuple[int, ...]:
+    """ONE all-reduce(max) that is (a) the barrier between scatter and merge, (b) the agreement on what happens
+    next -- VOTE_OK, VOTE_RETRY (some region or table was too small) or VOTE_FATAL (some rank failed: every rank
+    raises after the collective instead of one raising before it and the others waiting forever) -- and
+    (c) carries `extra` non-negative integers, each reduced with max.  -> (status, *extra) over all ranks."""
     import torch
     import torch.distributed as dist
+    vals = [int(status)] + [int(x) for x in extra]
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
-        return int(value)
-    t = torch.tensor([int(value)], dtype=torch.int64, device=f"cuda:{device}")
+        return tuple(vals)
+    t = torch.tensor(vals, dtype=torch.int64, device=f"cuda:{device}")
     dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
-    return int(t.item())
+    return tuple(int(v) for v in t.tolist())
+
+
+def _guarded(fn):
+    """Run one local step of a fused protocol.  -> (result, vote status, exception): a short region / table is a
+    retry (QK_E_NOMEM), anything else is fatal -- but the caller still enters the vote."""
+    from ._native import QuantikB200Error
+    try:
+        return fn(), VOTE_OK, None
+    except QuantikB200Error as e:
+        return None, (VOTE_RETRY if e.code == -4 else VOTE_FATAL), e
+    except Exception as e:                      # noqa: BLE001 -- reported to every rank through the vote
+        return None, VOTE_FATAL, e
+
+
+def _raise_if_fatal(status: int, err, what: str) -> None:
+    if status >= VOTE_FATAL:
+        if err is not None:
+            raise err
+        raise RuntimeError(f"{what}: another rank failed (see its log); aborting on every rank")
 
 
 def fused_canon_dedup(states, mult=None, color_swap: bool = False, device: int = 0, group=None,
-                      inboxes: Optional[PeerInboxes] = None, sort_output: bool = False):
-    """sharded_canon_dedup with the exchange fused into the merge (GPU only).  Same return value."""
-    from ._native import QuantikB200Error
+                      inboxes: Optional[PeerInboxes] = None, sort_output: bool = False, n_max: Optional[int] = None):
+    """sharded_canon_dedup with the exchange fused into the merge (GPU only): same partition of the classes over
+    the ranks (owner_rank = the library's owner_of), so the same (payloads this rank owns, their global
+    multiplicities, global number of distinct classes) up to the order of the rows.
+    `n_max` = the largest len(states) over the ranks when the caller knows it (saves the sizing all-reduce)."""
     rank, world = _world(group)
     n = len(states)
-    want = _max_over_ranks(int(1.25 * n / world) + 4096, device, group)     # every local state distinct, evenly owned
+    if n_max is None:
+        n_max = _vote(VOTE_OK, device, group, (n,))[1]
+    want = int(1.25 * n_max / world) + 4096                     # every local state distinct, evenly owned
     if inboxes is None:
         inboxes = PeerInboxes(want, device, group, copies=1)
     inboxes.ensure(want)
     while True:
-        failed = False
-        try:
-            B.canon_dedup_scatter(states, mult, inboxes.ptrs[0], rank, inboxes.slots_per_src, color_swap=color_swap, device=device)
-        except QuantikB200Error as e:
-            if e.code != -4:
-                raise
-            failed = True
-        if not _vote(failed, device, group):
+        _, status, err = _guarded(lambda: B.canon_dedup_scatter(states, mult, inboxes.ptrs[0], rank, inboxes.slots_per_src,
+                                                                 color_swap=color_swap, device=device))
+        status = _vote(status, device, group)[0]
+        _raise_if_fatal(status, err, "fused_canon_dedup")
+        if status == VOTE_OK:
             break
         inboxes.ensure(2 * inboxes.slots_per_src)
     got = inboxes.received(0)
-    mine, mm = B.inbox_merge(inboxes.ptrs[0][rank], world, inboxes.slots_per_src, max(got, 1), device=device, sort_output=sort_output)
-    total = all_reduce_counts(np.array([int(mine.shape[0])], np.int64), device, group)
-    return mine, mm, int(total[0])
+    res, status, err = _guarded(lambda: B.inbox_merge(inboxes.ptrs[0][rank], world, inboxes.slots_per_src, max(got, 1),
+                                                      device=device, sort_output=sort_output))
+    n_mine = int(res[0].shape[0]) if res is not None else 0
+    total = all_reduce_counts(np.array([n_mine, int(status != VOTE_OK)], np.int64), device, group)
+    _raise_if_fatal(VOTE_FATAL if total[1] else VOTE_OK, err, "fused_canon_dedup (merge)")
+    return res[0], res[1], int(total[0])
 
 
 def fused_symmetry_table(max_depth: int, device: int = 0, group=None, inboxes: Optional[PeerInboxes] = None):
     """sharded_symmetry_table with the per-depth exchange fused into the expansion's merge: per depth one
-    qk_bfs_level_scatter, one vote (the barrier), one qk_inbox_merge; the counters are all-reduced once at the end."""
+    qk_bfs_level_scatter, ONE collective (the vote: barrier + retry agreement + the sizes the next depth needs)
+    and one qk_inbox_merge; the counters are all-reduced once at the end.  Inboxes alternate between consecutive
+    depths and nothing else synchronises the ranks, so a fast rank delivers depth d+1 while a slow one still
+    merges depth d."""
     import torch
-    from ._native import QuantikB200Error
     rank, world = _world(group)
     d = int(device)
     if inboxes is None:
@@ -335,34 +384,45 @@ def fused_symmetry_table(max_depth: int, device: int = 0, group=None, inboxes: O
     # the empty board belongs to whoever owns it under the library's hash: let the merge decide -- rank 0 scatters it
     frontier = torch.zeros((1 if rank == 0 else 0, 8), dtype=torch.int16, device=f"cuda:{d}")
     mult = torch.ones(1 if rank == 0 else 0, dtype=torch.int64, device=f"cuda:{d}")
-    B.canon_dedup_scatter(frontier, mult, inboxes.ptrs[1], rank, inboxes.slots_per_src, device=d)
-    _vote(False, d, group)
+    _, status, err = _guarded(lambda: B.canon_dedup_scatter(frontier, mult, inboxes.ptrs[1], rank, inboxes.slots_per_src, device=d))
+    _raise_if_fatal(_vote(status, d, group)[0], err, "fused_symmetry_table (root)")
     frontier, mult = B.inbox_merge(inboxes.ptrs[1][rank], world, inboxes.slots_per_src, 1, device=d)
     levels = np.zeros((max_depth, 7), np.int64)
-    growth = 64.0
+    growth = 64.0                   # children sent per parent at the previous depth, max over ranks (x 1024 on the wire)
+    n_max = 1                       # largest frontier share at this depth, max over ranks
+    carry, carry_err = VOTE_OK, None            # a failed merge is reported through the NEXT vote
     for depth in range(1, max_depth + 1):
         k = depth % 2
         n = int(frontier.shape[0])
-        local_cap = int(min(64 * max(n, 1), max(1 << 12, B.level_margin(n) * growth * n)))
-        want = _max_over_ranks(int(1.25 * local_cap / B.level_margin(n) / world) + 4096, d, group)
-        inboxes.ensure(want)
+        local_cap = int(min(64 * max(n, 1), max(1 << 12, B.level_margin(n) * growth * max(n, 1))))
+        # regions: what the busiest rank will send, spread evenly over the owners (a short region is a retry)
+        inboxes.ensure(int(1.25 * min(64.0, growth) * n_max / world) + 4096)
         while True:
-            failed = False
-            try:
-                st, sent = B.bfs_level_scatter(frontier, mult, inboxes.ptrs[k], rank, inboxes.slots_per_src, local_cap, device=d)
-            except QuantikB200Error as e:
-                if e.code != -4:
-                    raise
-                failed = True
-            if not _vote(failed, d, group):
+            if carry == VOTE_OK:
+                res, status, err = _guarded(lambda: B.bfs_level_scatter(frontier, mult, inboxes.ptrs[k], rank,
+                                                                        inboxes.slots_per_src, local_cap, device=d))
+            else:
+                res, status, err = None, carry, carry_err
+            sent_total = int(res[1].sum()) if res is not None else 0
+            status, sent_max, ratio_max = _vote(status, d, group, (sent_total, int(1024.0 * sent_total / max(n, 1)) + 1))
+            _raise_if_fatal(status, err, f"fused_symmetry_table (depth {depth})")
+            if status == VOTE_OK:
                 break
             local_cap *= 2                      # whichever of the two was short, on whichever rank
             inboxes.ensure(2 * inboxes.slots_per_src)
-        growth = max(0.05, float(sent.sum()) / max(n, 1))
-        got = inboxes.received(k)
-        frontier, mult = B.inbox_merge(inboxes.ptrs[k][rank], world, inboxes.slots_per_src, max(got, 1), device=d)
+        st = res[0]
+        growth = max(0.05, ratio_max / 1024.0)
+        n_max = max(1, int(1.1 * sent_max))     # owners are hash-uniform: no rank receives much more than the busiest sent
+        merged, carry, carry_err = _guarded(lambda: B.inbox_merge(inboxes.ptrs[k][rank], world, inboxes.slots_per_src,
+                                                                  max(inboxes.received(k), 1), device=d))
+        if merged is None:
+            carry = VOTE_FATAL                  # even a "retry" code is fatal here: the peers' data is already delivered
+            continue
+        frontier, mult = merged
         levels[depth - 1, :5] = [st["total_moves"], st["line_wins_p0"], st["line_wins_p1"], st["blocked_p0"], st["blocked_p1"]]
         levels[depth - 1, 5] = int(frontier.shape[0])
         levels[depth - 1, 6] = int(mult.sum()) if len(mult) else 0
+    status = _vote(carry, d, group)[0] if carry != VOTE_OK or world > 1 else VOTE_OK
+    _raise_if_fatal(status, carry_err, "fused_symmetry_table (last merge)")
     tot = all_reduce_counts(levels, d, group)
     return [[int(t[0]), int(t[5]), int(t[1] + t[4]), int(t[2] + t[3]), int(t[6])] for t in tot]

@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""perft timing from the empty board for both depth-first kernels (QK_PERFT_KERNEL=warp|lane|auto)."""
+"""perft timing from the empty board for both depth-first kernels (qk_set_option "perft_kernel")."""
 import os
 import sys
 import time
@@ -14,10 +14,7 @@ e = np.zeros((1, 8), np.uint16)
 Q.perft(e, 4)
 for depth in (6, 7, 8):
     for mode in ("tile", "warp", "lane", "auto"):
-        if mode == "auto":
-            os.environ.pop("QK_PERFT_KERNEL", None)
-        else:
-            os.environ["QK_PERFT_KERNEL"] = mode
+        Q._native.set_option("perft_kernel", {"auto": 0, "tile": 1, "lane": 2, "warp": 3}[mode])
         if depth == 8 and mode == "warp":
             pass
         Q.perft(e, depth)

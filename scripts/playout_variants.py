@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""Config-1 throughput of the playout kernel variants (QK_PLAYOUT_VARIANT = fresh | hoist | general)."""
+"""Config-1 throughput of the playout kernel variants (qk_set_option "playout_variant": fresh | hoist | general)."""
 import os
 import sys
 import time
@@ -14,7 +14,7 @@ import quantik_b200 as Q  # noqa: E402
 root = torch.zeros((1, 8), dtype=torch.int16, device="cuda:0")
 n = 1 << 30
 for variant in ("general", "hoist", "fresh", "general", "hoist", "fresh"):
-    os.environ["QK_PLAYOUT_VARIANT"] = variant
+    Q._native.set_option("playout_variant", {"fresh": 0, "hoist": 1, "general": 2}[variant])
     Q.playouts(root, 1 << 24)
     torch.cuda.synchronize()
     t0 = time.perf_counter()

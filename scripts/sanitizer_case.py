@@ -14,9 +14,9 @@ roots = Q.random_roots(256)
 late = Q.random_roots(256, min_plies=8, span=5)
 print(Q.playouts(e, 4096, per_playout=True)["wins_p0"], Q.playouts(roots, 32)["wins_p0"][:4], Q.playouts(roots, 16, max_plies=3)["draws"][:4])
 for mode in ("warp", "lane"):
-    os.environ["QK_PERFT_KERNEL"] = mode
+    Q._native.set_option("perft_kernel", {"lane": 2, "warp": 3}[mode])
     print(mode, Q.perft(e, 5)["nodes"].tolist(), Q.perft(late, 4)["nodes"].tolist())
-os.environ.pop("QK_PERFT_KERNEL")
+Q._native.set_option("perft_kernel", 0)
 print(Q.canonical_payloads(roots)[:1], Q.orbit_sizes(roots)[:4], Q.movegen_masks(roots)[0][:2], Q.win_status(roots)[:4])
 u, m = Q.canon_dedup(np.repeat(roots, 4, 0))
 print(len(u), int(m.sum()))

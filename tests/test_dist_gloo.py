@@ -39,7 +39,10 @@ def _worker(rank, world, port, q):
     tally = D.sharded_playout_tally(empty, 5001, seed=O.SEED_DEFAULT, playouts_fn=playouts_fn)
     roots = O.make_roots(37)
     per_root = D.sharded_root_tallies(roots, 64, seed=O.SEED_DEFAULT, playouts_fn=playouts_fn)
-    pf = D.sharded_perft(roots[:9], 2, mult=np.arange(1, 10, dtype=np.uint64), perft_fn=perft_fn)
+    def probe_fn(roots, device=None):       # qk_perft_probe: move sequences of length 2 below every root
+        return np.array([int(O.perft(r[None], 2)["nodes"][2]) for r in np.asarray(roots)], np.uint32)
+
+    pf = D.sharded_perft(roots[:9], 2, mult=np.arange(1, 10, dtype=np.uint64), perft_fn=perft_fn, probe_fn=probe_fn)
 
     # the exchange step: global dedup and the partitioned BFS (oracle stand-ins for the two kernels)
     def dedup_fn(states, mult=None, color_swap=False, cap=None, device=None, sort_output=True):
@@ -96,7 +99,16 @@ def test_world2_matches_single_process():
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    got = [q.get(timeout=300) for _ in range(3)]
+    got = []
+    for _ in range(3):
+        for _ in range(120):                    # a rank that died must fail the test at once, not after the timeout
+            try:
+                got.append(q.get(timeout=1))
+                break
+            except Exception:
+                assert all(p.exitcode in (None, 0) for p in procs), [p.exitcode for p in procs]
+        else:
+            raise AssertionError("world-2 workers did not answer within 120 s")
     for p in procs:
         p.join(60)
         assert p.exitcode == 0

@@ -323,20 +323,33 @@ def test_perft_weighted_canonical_roots_and_oracle():
         assert np.array_equal(g[k], o[k]), k
 
 
-def test_perft_lane_kernel_matches_warp_kernel_and_oracle(monkeypatch):
+@pytest.fixture
+def options():
+    """qk_set_option switches (kernel variants that compute the same result), restored to the defaults afterwards."""
+    from quantik_b200 import _native as N
+    touched = set()
+
+    def set_option(name, value):
+        touched.add(name)
+        N.set_option(name, value)
+
+    yield set_option
+    for name in touched:
+        N.set_option(name, 0)
+
+
+def test_perft_lane_kernel_matches_warp_kernel_and_oracle(options):
     e = np.zeros((1, 8), np.uint16)
     roots = O.make_roots(64, seed=4242, min_plies=8, span=4)
     mult = np.arange(1, 65, dtype=np.uint64)
     mid = O.make_roots(3000, seed=17, min_plies=4, span=5)
     ref6 = None
     for mode in ("tile", "tile-generic", "warp", "lane", "tile-small"):
-        monkeypatch.setenv("QK_PERFT_KERNEL", mode[:4])
-        if mode == "tile-generic":      # 64-bit multiplicities / mixed sides-to-move form, on inputs that allow the fast one
-            monkeypatch.setenv("QK_PERFT_TILE_GENERIC", "1")
-        else:
-            monkeypatch.delenv("QK_PERFT_TILE_GENERIC", raising=False)
+        options("perft_kernel", {"tile": 1, "lane": 2, "warp": 3}[mode[:4]])
+        # tile-generic: 64-bit multiplicities / mixed sides-to-move form, on inputs that allow the fast one
+        options("perft_tile_generic", 1 if mode == "tile-generic" else 0)
         if mode == "tile-small":        # the depth-first kernel straight on the 64 mixed-parity roots: every frame depth
-            monkeypatch.setenv("QK_PERFT_MIN_ITEMS", "1")
+            options("perft_min_items", 1)
         p = B.perft(e, 6)
         assert B.symmetry_table_rows(p) == PUBLISHED, mode
         for depth in (2, 3, 5, 7):
@@ -353,8 +366,8 @@ def test_perft_lane_kernel_matches_warp_kernel_and_oracle(monkeypatch):
         ref6 = ref6 or g
         for k in g:
             assert np.array_equal(g[k], ref6[k]), (mode, k)
-    monkeypatch.delenv("QK_PERFT_KERNEL")
-    monkeypatch.delenv("QK_PERFT_MIN_ITEMS")
+    options("perft_kernel", 0)
+    options("perft_min_items", 0)
     # the automatic choice (lane kernel below wide frontiers) on a deep job: depth-4 classes + 6 = depth 10
     d = _npz("depth4_canonical.npz")
     p = B.perft(d["states"], 6, d["mult"])
@@ -705,7 +718,7 @@ def test_fused_exchange_with_emulated_ranks_on_one_gpu():
     assert rows == [list(map(int, r)) for r in B.symmetry_table(6)]
 
 
-def test_single_root_kernel_matches_general_kernel_and_oracle(monkeypatch):
+def test_single_root_kernel_matches_general_kernel_and_oracle(options):
     """Config 1 (one root, tallies only) runs a specialised kernel; it must give the general kernel's and the oracle's tallies."""
     roots = [np.zeros((1, 8), np.uint16), O.make_roots(3, seed=5, min_plies=6, span=3)[1:2],
              np.array([[1, 2, 4, 8, 0, 0, 0, 0]], np.uint16)]           # the last one is already won (row of A B C D)
@@ -713,7 +726,7 @@ def test_single_root_kernel_matches_general_kernel_and_oracle(monkeypatch):
         for n, first in ((1, 0), (1000, 0), (300_001, 12345), (1 << 22, 1 << 40)):
             tallies = {}
             for variant in ("fresh", "hoist", "general"):
-                monkeypatch.setenv("QK_PLAYOUT_VARIANT", variant)
+                options("playout_variant", {"fresh": 0, "hoist": 1, "general": 2}[variant])
                 r = B.playouts(root, n, SEED, first_rollout=first)
                 tallies[variant] = (int(r["wins_p0"][0]), int(r["wins_p1"][0]), int(r["draws"][0]))
                 assert sum(tallies[variant]) == n
@@ -721,4 +734,4 @@ def test_single_root_kernel_matches_general_kernel_and_oracle(monkeypatch):
             if n <= 300_001:
                 o = O.playouts(root, n, SEED, first)
                 assert tallies["fresh"] == (int(o["wins_p0"][0]), int(o["wins_p1"][0]), int(o["draws"][0]))
-    monkeypatch.delenv("QK_PLAYOUT_VARIANT")
+    options("playout_variant", 0)

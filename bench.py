@@ -12,8 +12,10 @@ carries perft nodes/s (config 2), canonical keys/s (config 3) and the config-4 p
 rate under "extra", the integer-issue roofline, the CPU baseline (oracle port on the host
 cores) and the end-to-end number measured through the C-ABI with host buffers.
 
---impl reference times the CPU implementation of the path (the reference is pure Python
-and cannot travel to the GPU box; the C oracle port of it is used, all host threads).
+--impl reference times the reference ITSELF (quantik-core 1.1.0, pure Python: the rollout loop of
+beam_search.py:624-645 on one process per host core) from the recipe-installed oracle/_ref
+(oracle/ref_recipe.py; __graft_entry__.build() populates it where /root/reference exists and it
+travels with the snapshot).  The C/OpenMP oracle port of the same loop is reported beside it.
 """
 from __future__ import annotations
 
@@ -85,9 +87,8 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_baseline(seconds: float = 12.0):
-    """Oracle port (C, OpenMP over all host threads) of the reference's rollout loop on a bounded
-    sample of the same workload: playouts from the empty board."""
+def _port_rate(seconds: float):
+    """C/OpenMP oracle port of the rollout loop on all host threads, about `seconds` of work."""
     import oracle as O
     O.set_num_threads(len(os.sched_getaffinity(0)))            # torchrun exports OMP_NUM_THREADS=1
     empty = np.zeros((1, 8), np.uint16)
@@ -101,41 +102,143 @@ def cpu_baseline(seconds: float = 12.0):
     dt = time.perf_counter() - t
     return {"value": n / dt, "unit": UNIT, "cores": O.num_threads(), "kind": "port",
             "sample": f"{n} empty-board playouts, C oracle (oracle/quantik_oracle.c, OpenMP), {dt:.1f} s; "
-                      f"P0 win rate {int(r['wins_p0'][0]) / n:.4f}",
-            "python_reference_measured": {"value": 559.0, "unit": "playouts/s/core",
-                                          "note": "quantik-core 1.1.0 itself, SURVEY.md section 6 (build container, "
-                                                  "not this box): 3118 playouts/s on 8 processes"}}
+                      f"P0 win rate {int(r['wins_p0'][0]) / n:.4f}"}
+
+
+def _reference_rate(seconds: float):
+    """The reference's own Python rollout loop (BeamSearchEngine._rollout) on every host core, `seconds` per process.
+    -> cpu_baseline dict, or None when oracle/_ref is not installed."""
+    from oracle import ref_recipe
+    if not ref_recipe.available():
+        return None
+    r = ref_recipe.time_reference_playouts(seconds)
+    return {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "reference",
+            "sample": f"{r['playouts']} empty-board playouts by quantik-core's own BeamSearchEngine._rollout "
+                      f"(beam_search.py:624-645, MT19937), {r['cores']} processes x {r['seconds']:.1f} s; "
+                      f"P0 win rate {r['p0_rate']:.4f}"}
+
+
+def cpu_baseline(seconds: float = 12.0):
+    """The path on the box's host cores, bounded sample of the same workload (playouts from the empty board):
+    the reference itself (kind "reference") with the C port of it as a second, labelled number."""
+    port = _port_rate(seconds * 0.6)
+    ref = _reference_rate(seconds)
+    if ref is None:
+        port["note"] = "oracle/_ref missing (build() not run where /root/reference exists): port only"
+        return port
+    ref["c_port"] = port
+    return ref
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import oracle as O
-    O.set_num_threads(len(os.sched_getaffinity(0)))            # torchrun exports OMP_NUM_THREADS=1
-    empty = np.zeros((1, 8), np.uint16)
-    O.playouts(empty, 20000, SEED)
-    t = time.perf_counter()
-    O.playouts(empty, 50000, SEED)
-    rate = 50000 / (time.perf_counter() - t)
-    budget = 150.0 / max(1, args.steps + args.warmup)          # whole run within a few minutes
-    n = int(max(10000, min(rate * min(budget, 15.0), 20_000_000)))
-    for w in range(args.warmup):
-        O.playouts(empty, n, SEED, first_rollout=w * n)
-    t0 = time.perf_counter()
-    for s in range(args.steps):
-        O.playouts(empty, n, SEED, first_rollout=(args.warmup + s) * n)
-    dt = time.perf_counter() - t0
-    value = n * args.steps / dt
-    sample = f"{n} empty-board playouts per step (bounded sample of the 2^30-playout step), C oracle port, all host threads"
+    budget = min(20.0, 150.0 / max(1, args.steps + args.warmup))      # seconds per step: whole run within a few minutes
+    ref = None
+    from oracle import ref_recipe
+    if ref_recipe.available():
+        for _ in range(args.warmup):
+            ref_recipe.time_reference_playouts(min(2.0, budget))
+        n = 0
+        wall = 0.0
+        p0 = 0.0
+        for _ in range(args.steps):
+            r = ref_recipe.time_reference_playouts(budget)
+            n += r["playouts"]
+            wall += r["seconds"]
+            p0 += r["p0_rate"] * r["playouts"]
+            cores = r["cores"]
+        value, ms = n / wall, 1e3 * wall / args.steps
+        sample = (f"{n // max(1, args.steps)} empty-board playouts per step (bounded sample of the 2^30-playout step) by quantik-core "
+                  f"1.1.0 itself: BeamSearchEngine._rollout (beam_search.py:624-645) on {cores} processes; P0 win rate {p0 / n:.4f}")
+        ref = {"value": value, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample, "c_port": _port_rate(5.0)}
+    else:
+        port = _port_rate(10.0)
+        value, ms, sample = port["value"], 1e3 * 10.0, port["sample"] + " (oracle/_ref missing: C port of the reference loop)"
+        ref = port
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u32", "data": "synthetic",
         "config": {"workload": "cfg1-throughput: uniform-random playouts from the empty board", "sample": sample},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": O.num_threads(), "kind": "port", "sample": sample},
+        "cpu_baseline": ref,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
+
+
+def search_speedup(dev: int):
+    """SURVEY 8f-2 end to end, benchmarks/adapters.py:160-259 in small: wall time of search() of the reference's stock
+    engines (pure Python, one playout at a time) against the batched subclasses of the SAME engines
+    (quantik_b200.engines: K leaves / one beam level per launch) on the same position with the same playout budget.
+    The engines come from the recipe-installed reference (oracle/_ref); {} when it is missing."""
+    from oracle import ref_recipe
+    if not ref_recipe.available():
+        return {}
+    ref_recipe.import_reference()
+    import quantik_b200 as Q
+    from quantik_core import beam_search as bs, mcts as mc
+    from quantik_core.core import State
+    state = State.empty()
+    out = {}
+    budget = 4096
+    t0 = time.perf_counter()
+    stock = mc.MCTSEngine(mc.MCTSConfig(max_iterations=budget, random_seed=1))
+    stock.search(state)
+    t_stock = time.perf_counter() - t0
+    Batched = Q.batched_mcts_engine(mc, leaves_per_wave=64, rollouts_per_leaf=64, device=dev)
+    Batched(mc.MCTSConfig(max_iterations=budget, random_seed=1)).search(state)
+    t0 = time.perf_counter()
+    eng = Batched(mc.MCTSConfig(max_iterations=budget, random_seed=1))
+    eng.search(state)
+    t_b = time.perf_counter() - t0
+    big = 1 << 22
+    t0 = time.perf_counter()
+    eng2 = Q.batched_mcts_engine(mc, leaves_per_wave=256, rollouts_per_leaf=1024, device=dev)(mc.MCTSConfig(max_iterations=big, random_seed=1))
+    eng2.search(state)
+    t_big = time.perf_counter() - t0
+    out["mcts_search"] = {"playout_budget": budget, "stock_s": t_stock, "batched_s": t_b, "speedup": t_stock / t_b,
+                          "batched_launches": eng.gpu_launches, "stock_playouts_per_s": budget / t_stock,
+                          "batched_large": {"playout_budget": big, "seconds": t_big, "playouts_per_s": big / t_big,
+                                            "waves": eng2.waves, "launches": eng2.gpu_launches,
+                                            "tree_nodes": int(eng2.tree.storage.node_count)}}
+    cfg = dict(beam_width=8, max_depth=3, rollouts_per_candidate=8, random_seed=1)
+    t0 = time.perf_counter()
+    rs = bs.BeamSearchEngine(bs.BeamSearchConfig(**cfg)).search(state)
+    t_stock = time.perf_counter() - t0
+    BB = Q.batched_beam_engine(bs, device=dev)
+    BB(bs.BeamSearchConfig(**cfg)).search(state)
+    t0 = time.perf_counter()
+    engb = BB(bs.BeamSearchConfig(**cfg))
+    rb = engb.search(state)
+    t_b = time.perf_counter() - t0
+    cfg_big = dict(beam_width=256, max_depth=16, rollouts_per_candidate=4096, random_seed=1)
+    t0 = time.perf_counter()
+    engc = BB(bs.BeamSearchConfig(**cfg_big))
+    rc = engc.search(state)
+    t_big = time.perf_counter() - t0
+    out["beam_search"] = {"config": cfg, "stock_s": t_stock, "stock_rollouts": rs.stats["rollouts"], "batched_s": t_b,
+                          "batched_rollouts": rb.stats["rollouts"], "batched_launches": engb.gpu_launches,
+                          "speedup_per_rollout": (t_stock / max(1, rs.stats["rollouts"])) / (t_b / max(1, rb.stats["rollouts"])),
+                          "batched_large": {"config": cfg_big, "seconds": t_big, "rollouts": rc.stats["rollouts"],
+                                            "rollouts_per_s": rc.stats["rollouts"] / t_big, "launches": engc.gpu_launches,
+                                            "evaluations": rc.stats["evaluations"]}}
+    return out
+
+
+def ncu_summary():
+    """Counters of the dominant kernel as captured by ncu: read at run time from the committed summary
+    (profiles/playout_ncu_latest.json, written by profiles/summarize.py from the .ncu-rep), never typed in here."""
+    path = os.path.join(ROOT, "profiles", "playout_ncu_latest.json")
+    if not os.path.exists(path):
+        return None
+    import hashlib
+    with open(path, "rb") as f:
+        raw = f.read()
+    d = json.loads(raw)
+    d["summary_file"] = "profiles/playout_ncu_latest.json"
+    d["summary_sha256"] = hashlib.sha256(raw).hexdigest()[:16]
+    return d
 
 
 def main():
@@ -147,6 +250,7 @@ def main():
     ap.add_argument("--playouts-per-step", type=int, default=PLAYOUTS_PER_STEP)
     ap.add_argument("--no-extra", action="store_true", help="skip the perft / canonical / config-4 side measurements")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cfg5-full", action="store_true", help="world > 1: skip the full-depth config-5 enumeration (about 130 s / N)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
@@ -227,25 +331,84 @@ def main():
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e = per_step * world * args.steps / float(e2e_s.item())
 
-    # ---------------------------------------------------------------- perft nodes/s at N GPUs (config 5, shortened)
-    # the 10 946 canonical depth-4 classes (weighted) enumerated 6 plies deeper, roots dealt round-robin over the
-    # ranks, ONE all-reduce of the 5 x 7 counters (quantik_b200.dist.sharded_perft)
+    # ---------------------------------------------------------------- strong-scaling jobs at N GPUs
     from quantik_b200 import dist as D
+
+    def timed_job(fn):
+        """barrier, run, sync; -> (result, seconds as the max over ranks)"""
+        barrier()
+        t0 = time.perf_counter()
+        out = fn()
+        torch.cuda.synchronize()
+        t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=f"cuda:{dev}")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return out, float(t.item())
+
     sharded = {}
     d4_path = os.path.join(ROOT, "tests", "golden", "depth4_canonical.npz")
     if not args.no_extra and os.path.exists(d4_path):
+        # config 5, shortened: the 10 946 canonical depth-4 classes (weighted) enumerated 6 plies deeper; roots dealt
+        # largest-first by a depth-2 probe, ONE all-reduce of the 5 x 7 counters (quantik_b200.dist.sharded_perft).
+        # Warm-up = the same call (memory pool, NCCL channel set-up), best of 3 timed runs reported with all three.
         d4 = np.load(d4_path)
-        D.sharded_perft(d4["states"], 3, d4["mult"], device=dev)
-        barrier()
-        t0 = time.perf_counter()
-        p10 = D.sharded_perft(d4["states"], 6, d4["mult"], device=dev)
-        torch.cuda.synchronize()
-        t_perft = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=f"cuda:{dev}")
-        if world > 1:
-            dist.all_reduce(t_perft, op=dist.ReduceOp.MAX)
+        D.sharded_perft(d4["states"], 6, d4["mult"], device=dev)
+        runs = []
+        for _ in range(3):
+            p10, t = timed_job(lambda: D.sharded_perft(d4["states"], 6, d4["mult"], device=dev))
+            runs.append(t)
         assert int(p10["nodes"][2]) == 6241600512 and int(p10["nodes"][4]) == 2097048766464      # GAME_TREE_ANALYSIS.md:9,11
-        sharded = {"perft_cfg5_depth10_weighted_nodes_per_s": float(p10["nodes"][1:].astype(np.float64).sum()) / float(t_perft.item()),
-                   "perft_cfg5_depth10_s": float(t_perft.item()), "perft_cfg5_n_gpus": world}
+        t_perft = min(runs)
+        sharded = {"perft_cfg5_depth10_weighted_nodes_per_s": float(p10["nodes"][1:].astype(np.float64).sum()) / t_perft,
+                   "perft_cfg5_depth10_s": t_perft, "perft_cfg5_depth10_runs_s": runs, "perft_cfg5_n_gpus": world}
+    if not args.no_extra and world > 1:
+        # the exchange step at world > 1 (SURVEY 8e row 3), asserted in-run against the single-GPU result every rank
+        # computes for itself: (1) the complete canonical game tree, frontier partitioned by payload hash, the
+        # children stored straight into their owners' inboxes over NVLink (fused) / NCCL all-to-all (two-step);
+        one_rows = [list(map(int, r)) for r in B.symmetry_table(16, device=dev)]
+        boxes = D.PeerInboxes(1 << 14, dev, copies=2)
+        D.fused_symmetry_table(16, device=dev, inboxes=boxes)          # sizes the inboxes for the deepest level
+        rows_f, t_fused = timed_job(lambda: D.fused_symmetry_table(16, device=dev, inboxes=boxes))
+        assert rows_f == one_rows, "fused partitioned BFS differs from the single-GPU table"
+        del boxes
+        D.sharded_symmetry_table(16, device=dev)
+        rows_n, t_nccl = timed_job(lambda: D.sharded_symmetry_table(16, device=dev))
+        assert rows_n == one_rows, "NCCL partitioned BFS differs from the single-GPU table"
+        # (2) global canonical dedup: every rank holds 2^22 symmetric images of mid-game positions
+        import itertools
+        n_img = 1 << 22
+        pos = B.random_roots(n_img, first=rank * n_img, min_plies=3, span=6, device=dev)
+        table = np.array([B.encode_transform(d4_, False, perm) for perm in itertools.permutations(range(4)) for d4_ in range(8)], np.uint16)
+        codes = table[((np.arange(n_img, dtype=np.uint64) * np.uint64(2654435761) + np.uint64(rank)) % np.uint64(192)).astype(np.int64)]
+        images = torch.from_numpy(np.ascontiguousarray(B.apply_symmetry(pos, codes, device=dev)).view(np.int16)).to(f"cuda:{dev}")
+        dbox = D.PeerInboxes(int(1.25 * n_img / world) + 4096, dev, copies=1)
+        D.fused_canon_dedup(images, None, device=dev, inboxes=dbox, n_max=n_img)
+        (f_own, f_mult, f_global), t_dd = timed_job(lambda: D.fused_canon_dedup(images, None, device=dev, inboxes=dbox, n_max=n_img))
+        (n_own, n_mult, n_global), t_dd_nccl = timed_job(lambda: D.sharded_canon_dedup(images, None, device=dev))
+        f_mass = D.all_reduce_counts(np.array([int(f_mult.sum()), int(n_mult.sum())], np.int64), dev)
+        gathered = [torch.empty_like(images.view(torch.int64)) for _ in range(world)]
+        dist.all_gather(gathered, images.view(torch.int64))
+        if rank == 0:
+            u_all, m_all = B.canon_dedup(torch.cat(gathered), None, device=dev, sort_output=False)
+            assert int(u_all.shape[0]) == f_global == n_global, "global dedup: number of classes differs from one GPU"
+            assert int(f_mass[0]) == world * n_img == int(f_mass[1]) == int(m_all.sum()), "global dedup: multiplicities lost"
+            del u_all, m_all
+        del gathered, dbox, images
+        sharded.update({"fused_bfs_s": t_fused, "nccl_bfs_s": t_nccl, "fused_bfs_canonical_states": int(sum(r[1] for r in rows_f)),
+                        "fused_dedup_keys_per_s": world * n_img / t_dd, "nccl_dedup_keys_per_s": world * n_img / t_dd_nccl,
+                        "fused_dedup_global_classes": int(f_global), "exchange_asserted_equal_to_single_gpu": True})
+        if not args.no_cfg5_full and os.path.exists(d4_path):
+            # config 5 at full depth: the depth-4 classes 12 plies deeper = the whole game tree, every depth's totals
+            # compared with the canonical BFS table (two independent enumerations)
+            p16, t16 = timed_job(lambda: D.sharded_perft(d4["states"], 12, d4["mult"], device=dev))
+            for r in range(1, 13):
+                want = one_rows[4 + r - 1]
+                got = [int(p16["nodes"][r]), int(p16["wins_p0"][r]) + int(p16["blocked_p1_loses"][r - 1]),
+                       int(p16["wins_p1"][r]) + int(p16["blocked_p0_loses"][r - 1]),
+                       int(p16["nodes"][r]) - int(p16["wins_p0"][r]) - int(p16["wins_p1"][r])]
+                assert got == [want[0], want[2], want[3], want[4]], ("config 5 full depth", 4 + r)
+            sharded.update({"cfg5_full_depth_s": t16, "cfg5_full_depth_weighted_nodes": int(p16["nodes"][1:].astype(object).sum()),
+                            "cfg5_full_depth_matches_canonical_bfs": True})
 
     if rank != 0:
         if world > 1:
@@ -255,13 +418,14 @@ def main():
 
     # ---------------------------------------------------------------- rank 0: roofline, side metrics, CPU baseline
     peak_issue = B.int_issue_peak(dev)
+    ncu = ncu_summary()
     sm_mhz = (clocks or {}).get("sm_mhz") or info["sm_clock_khz"] / 1e3
     nominal_peak = info["sm_count"] * 128 * sm_mhz * 1e6          # 4 schedulers x 32 lanes per SM-clock
     achieved = value / world * OPS_PER_PLAYOUT                    # per GPU
     roofline = {
         "bound": "int_issue", "kernel": "k_playout_single<true> (config 1: one root, tallies only; k_playout<false,false> for many roots)",
         "achieved": achieved / 1e12, "peak": nominal_peak / 1e12, "unit": "Tlane-op/s", "frac": achieved / nominal_peak,
-        "traffic": 14592,   # dram__bytes_read+write of one k_playout launch (ncu --set full, profiles/r01i_playout_ncu.txt)
+        "traffic": (ncu or {}).get("dram_bytes_per_launch"),   # ncu --set full, see "ncu" below
         "model": f"{OPS_PER_PLY:.0f} int ops/ply x {PLIES_PER_PLAYOUT} plies/playout (DESIGN.md section 5); peak = SMs x 4 "
                  f"schedulers x 32 lanes x SM clock under load ({sm_mhz:.0f} MHz)",
         "peak_measured_lop3": peak_issue["alu"] / 1e12, "peak_measured_lop3_imad_mix": peak_issue["mixed"] / 1e12,
@@ -272,8 +436,7 @@ def main():
                      "note": "LOP3/SEL/ISETP/SHF/IADD3 share one 64-lane/clk/SM pipe on sm_100: the binding sub-roofline "
                              "(ncu: profiles/)"},
         "hbm": {"algorithmic_bytes_per_step": 16 + 12, "note": "one 16-byte root in, three u32 tallies out: not memory-bound"},
-        "ncu": {"source": "profiles/r01i_playout_ncu.txt", "issue_active_pct": 70.5, "pipe_alu_pct": 62.8,
-                "pipe_fmaheavy_cycles_pct": 68.0, "pipe_xu_pct": 29.3, "lanes_active_per_inst": 31.0},
+        "ncu": ncu,
     }
 
     extra = dict(sharded)
@@ -340,12 +503,16 @@ def main():
         roots = B.random_roots(65536, seed=SEED, device=dev, as_torch=True)
         B.playouts(roots, 1024, SEED)
         torch.cuda.synchronize()
-        c0.record()
-        for _ in range(3):
+        reps4 = []
+        for _ in range(9):                             # a 1.8 ms job: every repetition timed on its own, median reported
+            c0.record()
             r4 = B.playouts(roots, 1024, SEED)
-        c1.record()
-        torch.cuda.synchronize()
-        extra["cfg4_mcts_leaf_playouts_per_s"] = 3 * 65536 * 1024 / (c0.elapsed_time(c1) * 1e-3)
+            c1.record()
+            torch.cuda.synchronize()
+            reps4.append(c0.elapsed_time(c1) * 1e-3)
+        reps4.sort()
+        extra["cfg4_mcts_leaf_playouts_per_s"] = 65536 * 1024 / reps4[len(reps4) // 2]
+        extra["cfg4_ms_min_median_max"] = [1e3 * reps4[0], 1e3 * reps4[len(reps4) // 2], 1e3 * reps4[-1]]
         extra["cfg4_roots"] = 65536
         extra["cfg4_rollouts_per_root"] = 1024
         # eval-guided rollouts (seeded weights, epsilon 0.2) and the exact endgame solver
@@ -358,6 +525,8 @@ def main():
         t0 = time.perf_counter()
         B.solve(late, device=dev)
         extra["solver_positions_per_s"] = (1 << 16) / (time.perf_counter() - t0)
+        if world == 1 and not args.no_cpu_baseline:
+            extra["search_speedup"] = search_speedup(dev)
 
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

@@ -29,6 +29,10 @@ def ref(monkeypatch):
 
     monkeypatch.setattr(B, "playouts", playouts)
     monkeypatch.setattr(B, "guided_playouts", guided)
+    monkeypatch.setattr(B, "movegen_masks", lambda states, device=None: O.movegen_masks(states))
+    monkeypatch.setattr(B, "apply_moves", lambda states, actions, device=None: O.apply_moves(states, actions))
+    monkeypatch.setattr(B, "win_status", lambda states, device=None: O.win_status(states))
+    monkeypatch.setattr(B, "canonical_payloads", lambda states, device=None: O.canonical(states))
     import quantik_core
     return quantik_core
 
@@ -84,3 +88,28 @@ def test_single_state_api_matches_reference_signatures(ref):
         assert hasattr(Q.State, name) and hasattr(R.State, name)
     assert [int(x) for x in Q.WinStatus] == [int(x) for x in game_utils.WinStatus]
     assert Q.Move(0, 1, 2) == Q.Move(0, 1, 2) and (Q.Move(0, 1, 2).player, Q.Move(0, 1, 2).shape) == (0, 1)
+
+
+def test_batched_beam_engine_reproduces_stock_search(ref):
+    import quantik_b200 as Q
+    import engine_cases
+    assert engine_cases.beam_identical_with_deterministic_evaluator(Q, ref)
+
+
+def test_batched_beam_engine_default_evaluator(ref):
+    import oracle as O
+    import quantik_b200 as Q
+    import engine_cases
+
+    def check(roots, rollouts, seed, first):
+        o = O.playouts(roots, rollouts, seed, first)
+        return o["wins_p0"], o["wins_p1"]
+
+    assert engine_cases.beam_default_evaluator_bookkeeping(Q, ref, check)
+
+
+def test_batched_mcts_engine(ref):
+    import quantik_b200 as Q
+    import engine_cases
+    assert engine_cases.mcts_batched_invariants(Q, ref)
+    assert engine_cases.mcts_batched_invariants(Q, ref, guided=True)

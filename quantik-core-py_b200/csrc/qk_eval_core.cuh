@@ -18,53 +18,103 @@ QK_HD uint32_t scope_of_square(int p)
     return ((0xFu << (p & 12)) | (0x1111u << (p & 3)) | (0x33u << (p & 10))) & 0xFFFFu;
 }
 
-// features (evaluation.py:130-194) of a VALID position from `player`'s perspective, as small integers
-// in FEATURE_NAMES order: threat_own, threat_opp, threat_shared, mobility_diff, build_two, build_one.
-QK_HD void eval_features(const State4 &s, int player, int f[6])
+// ---------------------------------------------------------------- the 12 lines at once
+// The reference walks the 12 lines one after the other (evaluation.py:147-189).  Here every line owns a 4-bit field
+// of a 64-bit word (rows 0-3 -> fields 0-3, columns -> 4-7, zones -> 8-11, the order of commons.py:24-48), and a
+// position carries, per line, the number of pieces on it (occ), the number of DISTINCT shapes on it (np) and which
+// shapes those are (pres: bit `shape` of the line's field) -- all updated by one table word when a piece lands.  "Dead line" (a repeated shape,
+// :164-165) is np < occ, occupied == 1/2/3 are bit patterns of the occ field, so build_one / build_two are two
+// popcounts and only lines with three distinct shapes -- the threats, rarely more than two -- are looked at one by one.
+struct EvalPos { uint64_t occ, np, pres; };
+static constexpr uint64_t kLineLsb = 0x0000111111111111ull;
+
+QK_HD uint64_t line_fields(int p)          // 1 in the fields of the three lines through square p
 {
-    const uint32_t line_mask[12] = { 0x000F, 0x00F0, 0x0F00, 0xF000, 0x1111, 0x2222, 0x4444, 0x8888,
-                                     0x0033, 0x00CC, 0x3300, 0xCC00 };                      // commons.py:24-48
-    const int side_to_move = piece_balance(s) == 0 ? 0 : 1;                                 // game_utils.py:226-231
-    const int sign = side_to_move == player ? 1 : -1;
-    uint32_t su[4], union_all = 0;
-    for (int sh = 0; sh < 4; ++sh) { su[sh] = board_word(s, sh) | board_word(s, sh + 4); union_all |= su[sh]; }
-    int threat_own = 0, threat_opp = 0, threat_shared = 0, build_two = 0, build_one = 0;
-    for (int l = 0; l < 12; ++l) {
-        const uint32_t mask = line_mask[l];
-        int n_present = 0, missing = 0;
-        for (int sh = 3; sh >= 0; --sh) {
-            if (su[sh] & mask) ++n_present; else missing = sh;                              // first absent shape
+    const uint32_t lo = (1u << (p & 12)) | (0x10000u << ((p & 3) << 2));
+    const uint32_t hi = 1u << ((p & 8) | ((p & 2) << 1));
+    return ((uint64_t)hi << 32) | lo;
+}
+QK_HD void eval_pos_place(EvalPos &e, int shape, int p)
+{
+    const uint64_t t = line_fields(p);
+    e.occ += t;
+    e.np += t & ~(e.pres >> shape);
+    e.pres |= t << shape;
+}
+QK_HD EvalPos eval_pos(const State4 &s)
+{
+    EvalPos e = { 0, 0, 0 };
+    for (int i = 0; i < 8; ++i)
+        for (uint32_t w = board_word(s, i); w; w &= w - 1) {
+            int p = 0;
+            while (!((w >> p) & 1u)) ++p;
+            eval_pos_place(e, i & 3, p);
         }
-        const int occupied = popc(union_all & mask);
-        if (n_present < occupied) continue;                                                 // dead line (:164-165)
-        if (occupied == 3) {
-            const uint32_t e = mask & ~union_all;
-            int pos = 0;
-            while (!((e >> pos) & 1u)) ++pos;
-            const uint32_t scope = scope_of_square(pos);
-            bool comp[2];
-            for (int side = 0; side < 2; ++side)                                            // :170-175, :99-112
-                comp[side] = popc(board_word(s, side * 4 + missing)) < 2 &&
-                             (board_word(s, (1 - side) * 4 + missing) & scope) == 0;
-            if (comp[player]) ++threat_own;
-            if (comp[1 - player]) ++threat_opp;
-            if (comp[0] && comp[1]) threat_shared += sign;
-        } else if (occupied == 2) build_two += sign;
-        else if (occupied == 1) build_one += sign;
-    }
-    uint32_t lo, hi;
-    legal_masks(s, side_to_move, lo, hi);
-    const int n = popc(lo) + popc(hi);                                                      // count_legal_moves (:115-127)
-    f[0] = threat_own; f[1] = threat_opp; f[2] = threat_shared;
-    f[3] = side_to_move == player ? n : -n;
-    f[4] = build_two; f[5] = build_one;
+    return e;
+}
+QK_HD int popc64(uint64_t v) { return popc((uint32_t)v) + popc((uint32_t)(v >> 32)); }
+QK_HD uint32_t line_squares(int l)         // commons.py:24-48
+{
+    return l < 4 ? 0xFu << (4 * l) : (l < 8 ? 0x1111u << (l - 4) : 0x33u << ((((l - 8) >> 1) << 3) | (((l - 8) & 1) << 1)));
 }
 
-// evaluate (:197-212): weights @ features, accumulated left to right in float64 without contraction
-QK_HD double eval_score(const State4 &s, int player, const double w[6])
+// features (evaluation.py:130-194) of a VALID position from `player`'s perspective, as small integers in
+// FEATURE_NAMES order: threat_own, threat_opp, threat_shared, mobility_diff, build_two, build_one.
+// n_legal = count_legal_moves of the side to move (:115-127).
+QK_HD void eval_features_pos(const State4 &s, const EvalPos &e, int player, int side_to_move, int n_legal, int f[6])
 {
-    int f[6];
-    eval_features(s, player, f);
+    const int sign = side_to_move == player ? 1 : -1;
+    const uint64_t diff = e.occ - e.np;                               // per field, 0..3, never a borrow
+    const uint64_t live = ~(diff | (diff >> 1)) & kLineLsb;           // no repeated shape (:164-165)
+    const uint64_t b0 = e.occ, b1 = e.occ >> 1;
+    const int build_one = popc64(b0 & ~b1 & live), build_two = popc64(b1 & ~b0 & live);
+    int threat_own = 0, threat_opp = 0, threat_shared = 0;
+    uint64_t threats = b0 & b1 & live;                                // three pieces, three shapes
+    if (threats) {
+        const uint32_t all = (s.x | s.y | s.z | s.w), union_all = (all | (all >> 16)) & 0xFFFFu;
+        while (threats) {
+            int bit = 0;
+            const uint32_t tlo = (uint32_t)threats;
+#ifdef __CUDA_ARCH__
+            bit = tlo ? __ffs((int)tlo) - 1 : 32 + __ffs((int)(uint32_t)(threats >> 32)) - 1;
+#else
+            bit = tlo ? __builtin_ctz(tlo) : 32 + __builtin_ctz((uint32_t)(threats >> 32));
+#endif
+            threats &= threats - 1;
+            const int l = bit >> 2;
+            const uint32_t absent = ~(uint32_t)(e.pres >> bit) & 0xFu;        // exactly one bit: the missing shape
+            const int missing = (int)(absent >> 1) - (int)(absent >> 3);      // 1,2,4,8 -> 0,1,2,3
+            const uint32_t empty = line_squares(l) & ~union_all;      // exactly one square
+            int pos = 0;
+#ifdef __CUDA_ARCH__
+            pos = __ffs((int)empty) - 1;
+#else
+            pos = __builtin_ctz(empty);
+#endif
+            const uint32_t scope = scope_of_square(pos);
+            const uint32_t w0 = board_word(s, missing), w1 = board_word(s, 4 + missing);
+            const bool comp0 = popc(w0) < 2 && (w1 & scope) == 0;     // :170-175, :99-112
+            const bool comp1 = popc(w1) < 2 && (w0 & scope) == 0;
+            threat_own += (player ? comp1 : comp0) ? 1 : 0;
+            threat_opp += (player ? comp0 : comp1) ? 1 : 0;
+            if (comp0 && comp1) threat_shared += sign;
+        }
+    }
+    f[0] = threat_own; f[1] = threat_opp; f[2] = threat_shared;
+    f[3] = side_to_move == player ? n_legal : -n_legal;
+    f[4] = sign * build_two; f[5] = sign * build_one;
+}
+
+QK_HD void eval_features(const State4 &s, int player, int f[6])
+{
+    const int side_to_move = piece_balance(s) == 0 ? 0 : 1;                                 // game_utils.py:226-231
+    uint32_t lo, hi;
+    legal_masks(s, side_to_move, lo, hi);
+    eval_features_pos(s, eval_pos(s), player, side_to_move, popc(lo) + popc(hi), f);
+}
+
+QK_HD double eval_dot(const int f[6], const double w[6])
+{
     double acc = 0.0;
     for (int i = 0; i < 6; ++i) {
 #ifdef __CUDA_ARCH__
@@ -76,6 +126,14 @@ QK_HD double eval_score(const State4 &s, int player, const double w[6])
     return acc;
 }
 
+// evaluate (:197-212): weights @ features, accumulated left to right in float64 without contraction
+QK_HD double eval_score(const State4 &s, int player, const double w[6])
+{
+    int f[6];
+    eval_features(s, player, f);
+    return eval_dot(f, w);
+}
+
 // One eval-guided playout (mcts.py:385-437 with _select_rollout_move :345-383).  Stream contract: ply p
 // uses Philox block (rollout lo, rollout hi, 0x80000000 | p/2, root index); word 2*(p%2) is the epsilon
 // draw (explore iff epsilon > 0 and word * 2^-32 < epsilon), word 2*(p%2)+1 the uniform pick.
@@ -83,6 +141,7 @@ QK_HD int guided_playout_one(const State4 &root, uint64_t seed, uint64_t rollout
                              double epsilon, const double w[6], int *plies_out)
 {
     State4 cur = root;
+    EvalPos ev = eval_pos(root);          // carried along: one table word per move instead of a rescan of the board
     int ply = 0, result;
     Philox4 rnd = { { 0, 0, 0, 0 } };
     for (;;) {
@@ -95,7 +154,7 @@ QK_HD int guided_playout_one(const State4 &root, uint64_t seed, uint64_t rollout
         if ((ply & 1) == 0)
             rnd = philox4x32_10((uint32_t)rollout, (uint32_t)(rollout >> 32), 0x80000000u | (uint32_t)(ply >> 1), root_index,
                                 (uint32_t)seed, (uint32_t)(seed >> 32));
-        const uint32_t r_eps = rnd.v[2 * (ply & 1)], r_pick = rnd.v[2 * (ply & 1) + 1];
+        const uint32_t r_eps = (ply & 1) ? rnd.v[2] : rnd.v[0], r_pick = (ply & 1) ? rnd.v[3] : rnd.v[1];
         const uint32_t lo = (uint32_t)mask, hi = (uint32_t)(mask >> 32);
         int action = -1;
         if (epsilon > 0.0 && (double)r_eps * (1.0 / 4294967296.0) < epsilon) {
@@ -112,14 +171,20 @@ QK_HD int guided_playout_one(const State4 &root, uint64_t seed, uint64_t rollout
                 a = mlo ? __builtin_ctz(mlo) : 32 + __builtin_ctz((uint32_t)(m >> 32));
 #endif
                 const State4 child = apply_action(cur, player, a);
+                EvalPos ce = ev;
+                eval_pos_place(ce, a >> 4, a & 15);
                 uint32_t clo, chi;
                 legal_masks(child, 1 - player, clo, chi);
-                if (has_winning_line(child) || (clo | chi) == 0) { action = a; break; }      // decisive move: take it
-                const double sc = eval_score(child, player, w);
+                // decisive move: a line with four shapes, or the opponent cannot answer -- take it
+                if ((ce.np & (kLineLsb << 2)) != 0 || (clo | chi) == 0) { action = a; break; }
+                int f[6];
+                eval_features_pos(child, ce, player, 1 - player, popc(clo) + popc(chi), f);
+                const double sc = eval_dot(f, w);
                 if (action < 0 || sc > best) { best = sc; action = a; }                      // first maximum wins
             }
         }
         cur = apply_action(cur, player, action);
+        eval_pos_place(ev, action >> 4, action & 15);
         ++ply;
     }
     if (plies_out) *plies_out = ply;

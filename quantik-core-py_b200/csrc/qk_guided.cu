@@ -1,8 +1,8 @@
 // qk_guided.cu -- SURVEY 8f-4: the reference's fitted-linear evaluation (evaluation.py:130-212) in batch,
 // and playouts under MCTSEngine._select_rollout_move's eval-guided epsilon-greedy policy (mcts.py:345-383).
-// One position / one playout per thread.  A guided ply scores every child of the position (up to 64
-// evaluations of 12 lines each), so this policy is ~100x the work of a uniform ply and is not the
-// throughput path; it exists so that MCTSConfig(rollout_eval_config=...) has a drop-in too.
+// One position / one playout per thread.  A guided ply scores every child of the position (up to 64 evaluations);
+// the evaluation looks at all 12 lines at once in packed 4-bit fields that the playout carries along
+// (qk_eval_core.cuh: EvalPos), so a child costs about 100 integer instructions plus 11 float64 operations.
 #include "qk_common.cuh"
 #include "qk_eval_core.cuh"
 
@@ -38,9 +38,16 @@ __global__ void __launch_bounds__(kBlock) k_playout_guided(const uint4 *__restri
         const State4 s = { v.x, v.y, v.z, v.w };
         int plies;
         const int res = guided_playout_one(s, seed, first_rollout + j, root_index_base + root, max_plies, epsilon, weights.w, &plies);
-        if (res > 0) { if (wins_p0) atomicAdd(wins_p0 + root, 1u); }
-        else if (res < 0) { if (wins_p1) atomicAdd(wins_p1 + root, 1u); }
-        else if (draws) atomicAdd(draws + root, 1u);
+        // tallies: the lanes of the warp that played for the same root (consecutive ids: almost always all of them)
+        // are summed first, one lane per root issues the atomics
+        const unsigned peers = __match_any_sync(__activemask(), root);
+        const unsigned p0 = __ballot_sync(peers, res > 0), p1 = __ballot_sync(peers, res < 0);
+        if ((unsigned)(__ffs((int)peers) - 1) == (threadIdx.x & 31u)) {
+            const uint32_t n0 = (uint32_t)__popc(p0 & peers), n1 = (uint32_t)__popc(p1 & peers), nd = (uint32_t)__popc(peers) - n0 - n1;
+            if (wins_p0 && n0) atomicAdd(wins_p0 + root, n0);
+            if (wins_p1 && n1) atomicAdd(wins_p1 + root, n1);
+            if (draws && nd) atomicAdd(draws + root, nd);
+        }
         if (per_playout) per_playout[id] = (int8_t)res;
         if (per_plies) per_plies[id] = (uint8_t)plies;
     }

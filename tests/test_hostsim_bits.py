@@ -141,6 +141,21 @@ def test_eval_features_and_guided_policy(hs):
         hs.hs_guided(P(e), ctypes.c_size_t(1), ctypes.c_uint32(m), ctypes.c_uint64(seed), ctypes.c_uint64(0), ctypes.c_uint32(3),
                      ctypes.c_int(-1), ctypes.c_double(eps), P(w), P(oc), P(pl))
         assert np.array_equal(oc, g[name + "_outcome"]) and np.array_equal(pl, g[name + "_plies"]), name
+    # the packed-field evaluation (12 lines at once) against the oracle's line-by-line loop on 20 000 reachable positions,
+    # and guided playouts from mid-game roots against the oracle's
+    big = np.ascontiguousarray(O.make_roots(20000, seed=77, min_plies=0, span=15))
+    for pl in (0, 1):
+        out = np.zeros((len(big), 6))
+        hs.hs_features(P(big), P(np.full(len(big), pl, np.uint8)), ctypes.c_size_t(len(big)), P(out))
+        assert np.array_equal(out, O.features(big, np.full(len(big), pl, np.uint8)))
+    roots = np.ascontiguousarray(O.make_roots(24, seed=5, min_plies=2, span=9))
+    w = np.ascontiguousarray(g["fitted_weights"])
+    for eps, mp in ((0.2, -1), (0.0, -1), (0.5, 4)):
+        oc, pl = np.zeros((24, 40), np.int8), np.zeros((24, 40), np.uint8)
+        hs.hs_guided(P(roots), ctypes.c_size_t(24), ctypes.c_uint32(40), ctypes.c_uint64(seed), ctypes.c_uint64(7), ctypes.c_uint32(0),
+                     ctypes.c_int(mp), ctypes.c_double(eps), P(w), P(oc), P(pl))
+        o = O.guided_playouts(roots, 40, seed, eps, w, 7, 0, mp, True)
+        assert np.array_equal(oc, o["outcome"]) and np.array_equal(pl, o["plies"]), (eps, mp)
 
 
 def test_fuzz_random_boards_vs_oracle(hs):

@@ -516,10 +516,10 @@ def main():
         extra["cfg4_roots"] = 65536
         extra["cfg4_rollouts_per_root"] = 1024
         # eval-guided rollouts (seeded weights, epsilon 0.2) and the exact endgame solver
-        B.guided_playouts(e, 1 << 16, SEED, device=dev)
+        B.guided_playouts(e, 1 << 18, SEED, device=dev)
         t0 = time.perf_counter()
-        B.guided_playouts(e, 1 << 21, SEED, device=dev)
-        extra["guided_playouts_per_s"] = (1 << 21) / (time.perf_counter() - t0)
+        B.guided_playouts(e, 1 << 24, SEED, device=dev)
+        extra["guided_playouts_per_s"] = (1 << 24) / (time.perf_counter() - t0)
         late = B.random_roots(1 << 16, seed=SEED, min_plies=8, span=5, device=dev)
         B.solve(late[:1024], device=dev)
         t0 = time.perf_counter()

@@ -117,6 +117,13 @@ QK_API int qk_orbit_size(const uint16_t *states, size_t n, uint8_t *orbit, int d
 /* qk_apply_symmetry <- SymmetryHandler.apply_symmetry (symmetry.py:252-287).             */
 QK_API int qk_apply_symmetry(const uint16_t *states, const uint16_t *transform, size_t n, uint16_t *out,
                       int dev, void *stream);
+/* qk_apply_symmetry_to_moves <- SymmetryHandler.apply_symmetry_to_move (symmetry.py:425-464), batched: move i =
+ *                      (players[i], actions[i] = shape * 16 + square) under transform[i].  inverse != 0 applies
+ *                      SymmetryTransform.inverse() (symmetry.py:66-85) of each code instead: with the transform
+ *                      qk_canonical reports, that maps a move chosen on the canonical position (an opening-book
+ *                      answer) back to the position that was looked up.                                          */
+QK_API int qk_apply_symmetry_to_moves(const uint8_t *players, const uint8_t *actions, const uint16_t *transform, size_t n,
+                               int inverse, uint8_t *out_players, uint8_t *out_actions, int dev, void *stream);
 /* qk_canon_dedup    <- the canonical merge of game_stats.py:487-505 /
  *                      beam_search.py:526-546 / generate_opening_book.py:458-496:
  *                      canonicalise n states, merge equal payloads, sum multiplicities

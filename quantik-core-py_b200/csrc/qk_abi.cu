@@ -319,6 +319,23 @@ int qk_apply_symmetry(const uint16_t *states, const uint16_t *transform, size_t 
     return call.finish();
 }
 
+int qk_apply_symmetry_to_moves(const uint8_t *players, const uint8_t *actions, const uint16_t *transform, size_t n, int inverse,
+                               uint8_t *out_players, uint8_t *out_actions, int dev, void *stream)
+{
+    QK_REQUIRE((players && actions && transform && out_players && out_actions) || n == 0, "qk_apply_symmetry_to_moves: NULL argument");
+    if (n == 0) return QK_OK;
+    QK_BEGIN(call);
+    const uint8_t *d_pl = (const uint8_t *)call.in(players, n);
+    const uint8_t *d_ac = (const uint8_t *)call.in(actions, n);
+    const uint16_t *d_tr = (const uint16_t *)call.in(transform, n * 2);
+    uint8_t *d_opl = (uint8_t *)call.out(out_players, n);
+    uint8_t *d_oac = (uint8_t *)call.out(out_actions, n);
+    QK_CHECK(call);
+    int rc = launch_apply_symmetry_to_moves(d_pl, d_ac, d_tr, n, inverse, d_opl, d_oac, call.ctx(), call.stream());
+    if (rc != QK_OK) return rc;
+    return call.finish();
+}
+
 int qk_canon_dedup(const uint16_t *states, const uint64_t *mult, size_t n, int color_swap, uint16_t *uniq,
                    uint64_t *uniq_mult, size_t cap, size_t *n_uniq, int dev, void *stream)
 {

@@ -79,6 +79,8 @@ int launch_win(const uint4 *states, size_t n, uint8_t *win, Ctx *c, cudaStream_t
 int launch_canonical(const uint4 *states, size_t n, int color_swap, uint4 *payload, uint16_t *transform, Ctx *c, cudaStream_t s);
 int launch_orbit(const uint4 *states, size_t n, uint8_t *orbit, Ctx *c, cudaStream_t s);
 int launch_apply_symmetry(const uint4 *states, const uint16_t *transform, size_t n, uint4 *out, Ctx *c, cudaStream_t s);
+int launch_apply_symmetry_to_moves(const uint8_t *player, const uint8_t *action, const uint16_t *transform, size_t n, int inverse,
+                                   uint8_t *out_player, uint8_t *out_action, Ctx *c, cudaStream_t s);
 int launch_playouts(const uint4 *roots, size_t n_roots, uint32_t rollouts, uint64_t seed, uint64_t first_rollout,
                     uint32_t root_index_base, int max_plies, uint32_t *wins_p0, uint32_t *wins_p1, uint32_t *draws,
                     int8_t *per_playout, uint8_t *per_plies, void *rootrec_scratch, Ctx *c, cudaStream_t s);

@@ -773,7 +773,10 @@ int run_perft(Call &call, const uint4 *roots, const uint64_t *mult, size_t n_roo
     // (one item per lane, last level dealt out to full warps).  Measured from the empty board, in ms, for
     // tile / warp-per-item / plain lane-per-item: depth 6 1.7 / 3.5 / 4.0, depth 7 38 / 105 / 62, depth 8 835 / 2688 / 1290.
     u64 want_warp_items = (u64)c->sms * 4 * kWarps * 8;
-    u64 want_lane_items = (u64)c->sms * 2048 * 8;
+    // (r02c_experiments.json: the tile kernel is at its best with 4 plies below the items -- the share of one of 8
+    // ranks, 1.2 M items: 23.6 ms started there vs 25.9 ms one level later -- unless the items are about as few as
+    // the lanes: perft(7) from 167 K items 28.4 ms vs 25.0 ms from 6.7 M.  4 items per lane separates the cases.)
+    u64 want_lane_items = (u64)c->sms * 1024 * 4;
     const int force = (int)option(OPT_PERFT_KERNEL);                    // 1 tile / 2 lane / 3 warp: benchmarking aid
     if (const long long mi = option(OPT_PERFT_MIN_ITEMS))               // testing aid: depth-first kernels on small frontiers
         want_warp_items = want_lane_items = (u64)mi;

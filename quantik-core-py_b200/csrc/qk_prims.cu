@@ -90,6 +90,31 @@ __global__ void __launch_bounds__(kBlock) k_apply_symmetry(const uint4 *__restri
         store_state(out, i, apply_symmetry(load_state(states, i), transform[i]));
 }
 
+// SymmetryHandler.apply_symmetry_to_move (symmetry.py:425-464), one move per thread: square through the D4 map
+// (the board map applied to a one-square board), colour toggled by color_swap, shape relabelled to the index of
+// the old shape in shape_perm.  inverse != 0 applies SymmetryTransform.inverse() of the code (symmetry.py:66-85):
+// the map that takes a move found on the canonical position back to the position it was asked for.
+__global__ void __launch_bounds__(kBlock) k_apply_symmetry_to_moves(const uint8_t *__restrict__ player, const uint8_t *__restrict__ action,
+                                                                     const uint16_t *__restrict__ transform, size_t n, int inverse,
+                                                                     uint8_t *__restrict__ out_player, uint8_t *__restrict__ out_action)
+{
+    for (size_t i = blockIdx.x * (size_t)kBlock + threadIdx.x; i < n; i += (size_t)gridDim.x * kBlock) {
+        const uint32_t t = transform[i], a = action[i] & 63u, shape = a >> 4, pos = a & 15u;
+        int d4 = (int)(t & 7u);
+        if (inverse && (d4 == 1 || d4 == 3)) d4 ^= 2;                       // rot90 <-> rot270, the others are involutions
+        const uint32_t moved = d4_apply(1u << pos, d4) & 0xFFFFu;
+        uint32_t new_shape = 0;
+        if (inverse) new_shape = (t >> (4 + 2 * shape)) & 3u;              // inverse permutation: shape_inv[perm[i]] = i
+        else {
+#pragma unroll
+            for (uint32_t k = 0; k < 4; ++k)
+                if (((t >> (4 + 2 * k)) & 3u) == shape) new_shape = k;      // shape_perm.index(shape)
+        }
+        out_player[i] = (uint8_t)((player[i] & 1u) ^ ((t >> 3) & 1u));
+        out_action[i] = (uint8_t)((new_shape << 4) | (uint32_t)(__ffs((int)moved) - 1));
+    }
+}
+
 // ------------------------------------------------------------------ launchers
 // grids: enough CTAs for 8 resident blocks of 256 threads on every SM, then grid-stride
 int launch_movegen(const uint4 *states, size_t n, uint64_t *mask, uint8_t *to_move, uint8_t *status, Ctx *c, cudaStream_t s)
@@ -128,6 +153,14 @@ int launch_orbit(const uint4 *states, size_t n, uint8_t *orbit, Ctx *c, cudaStre
 int launch_apply_symmetry(const uint4 *states, const uint16_t *transform, size_t n, uint4 *out, Ctx *c, cudaStream_t s)
 {
     k_apply_symmetry<<<grid_for(n, kBlock, c->sms, 8), kBlock, 0, s>>>(states, transform, n, out);
+    QK_CUDA(cudaGetLastError());
+    return QK_OK;
+}
+
+int launch_apply_symmetry_to_moves(const uint8_t *player, const uint8_t *action, const uint16_t *transform, size_t n, int inverse,
+                                   uint8_t *out_player, uint8_t *out_action, Ctx *c, cudaStream_t s)
+{
+    k_apply_symmetry_to_moves<<<grid_for(n, kBlock, c->sms, 8), kBlock, 0, s>>>(player, action, transform, n, inverse, out_player, out_action);
     QK_CUDA(cudaGetLastError());
     return QK_OK;
 }

@@ -41,6 +41,7 @@ PROTOTYPES = {
     "qk_canonical": (c_int, [c_void_p, c_size_t, c_int, c_void_p, c_void_p, c_int, c_void_p]),
     "qk_orbit_size": (c_int, [c_void_p, c_size_t, c_void_p, c_int, c_void_p]),
     "qk_apply_symmetry": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_int, c_void_p]),
+    "qk_apply_symmetry_to_moves": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p, c_void_p, c_int, c_void_p]),
     "qk_canon_dedup": (c_int, [c_void_p, c_void_p, c_size_t, c_int, c_void_p, c_void_p, c_size_t,
                                POINTER(c_size_t), c_int, c_void_p]),
     "qk_bfs_level": (c_int, [c_void_p, c_void_p, c_size_t, c_int, c_int, c_void_p, c_void_p, c_size_t, POINTER(c_size_t),

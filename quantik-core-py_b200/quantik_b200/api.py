@@ -431,3 +431,77 @@ def portability_case_report(case_id: str, qfen: str, shape: int, position: int) 
         "move": {"shape": shape, "position": position, "action_index": shape * 16 + position,
                  "is_legal": v.is_valid, "after_qfen": bb_to_qfen(v.new_bb) if v.is_valid else None},
     }
+
+
+def portability_report(cases, contracts_release: str = "", contract_ids=None) -> dict:
+    """The WHOLE ``api-portability-report.v1`` document of api_portability_report.build_report
+    (api_portability_report.py:194-226) for a list of fixture cases ``{"case_id", "qfen", "move": {"shape", "position"}}``
+    (the ``game_state_cases`` of the contracts fixture), every primitive evaluated for all cases in ONE launch:
+    movegen, winner, canonical form, orbit size, the case's move applied.  The fixture / manifest files themselves are
+    the caller's (they live in the contracts repository, not in quantik-core): pass their release and contract ids."""
+    if not isinstance(cases, list) or not cases:
+        raise ValueError("game_state_cases must be a non-empty list")
+    parsed = []
+    for index, case in enumerate(cases):
+        if not isinstance(case, dict):
+            raise ValueError(f"game_state_cases[{index}] must be an object")
+        case_id, qfen, mv = case.get("case_id"), case.get("qfen"), case.get("move")
+        if not isinstance(case_id, str) or not case_id:
+            raise ValueError("game_state_case.case_id must be a non-empty string")
+        if not isinstance(qfen, str):
+            raise ValueError(f"{case_id}: qfen must be a string")
+        if not isinstance(mv, dict):
+            raise ValueError(f"{case_id}: move must be an object")
+        try:
+            bb = bb_from_qfen(qfen)
+        except ValueError as exc:
+            raise ValueError(f"{case_id}: qfen parse failed: {exc}") from exc
+        vals = []
+        for key, upper in (("shape", 3), ("position", 15)):
+            value = mv.get(key)
+            if not isinstance(value, int) or isinstance(value, bool):
+                raise ValueError(f"move.{key} must be an integer")
+            if value < 0 or value > upper:
+                raise ValueError(f"move.{key} must be between 0 and {upper}")
+            vals.append(value)
+        parsed.append((case_id, bb, vals[0], vals[1]))
+    boards = np.array([p[1] for p in parsed], np.uint16).reshape(-1, 8)
+    masks, movers, status = B.movegen_masks(boards)
+    for (case_id, *_), st in zip(parsed, status):
+        if int(st) != 0:
+            raise ValueError(f"{case_id}: invalid game state {ValidationResult(int(st)).name}")
+    wins = B.win_status(boards)
+    canon = B.canonical_payloads(boards)
+    orbits = B.orbit_sizes(boards)
+    actions = np.array([p[2] * 16 + p[3] for p in parsed], np.uint8)
+    # validate_move (move.py:135-167): the fixture move is made by the side to move; legal = its bit of the mask,
+    # except on a finished board, where generate_legal_moves still lists moves but nobody checks the winner
+    legal = ((masks >> actions.astype(np.uint64)) & np.uint64(1)).astype(bool)
+    after = B.apply_moves(boards, actions)
+    out = []
+    for i, (case_id, bb, shape, position) in enumerate(parsed):
+        mask = int(masks[i])
+        indices = [a for a in range(64) if (mask >> a) & 1]
+        winner = {0: "none", 1: "player0", 2: "player1"}[int(wins[i])]
+        side = int(movers[i])
+        if winner != "none":
+            terminal = True
+        elif indices:
+            terminal = False
+        else:
+            terminal, winner = True, ("player1" if side == 0 else "player0")
+        out.append({
+            "case_id": case_id, "qfen": bb_to_qfen(bb), "bitboards": list(bb), "side_to_move": side,
+            "canonical_qfen": bb_to_qfen(tuple(int(x) for x in canon[i])),
+            "canonical_key": (bytes([VERSION, FLAG_CANON]) + np.ascontiguousarray(canon[i]).astype("<u2").tobytes()).hex(),
+            "orbit_size": int(orbits[i]),
+            "legal_action_mask": f"0x{mask:016x}", "legal_action_indices": indices,
+            "terminal": terminal, "winner": winner,
+            "move": {"shape": shape, "position": position, "action_index": shape * 16 + position, "is_legal": bool(legal[i]),
+                     "after_qfen": bb_to_qfen(tuple(int(x) for x in after[i])) if legal[i] else None},
+        })
+    from . import __version__
+    return {"schema": "api-portability-report.v1", "contracts_release": contracts_release,
+            "implementation": {"language": "cuda", "package": "quantik-core-py_b200", "version": __version__},
+            "contract_ids": dict(contract_ids or {}), "cases": sorted(out, key=lambda item: item["case_id"])}
+

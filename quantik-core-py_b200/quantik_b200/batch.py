@@ -177,6 +177,24 @@ def apply_symmetry(states, transforms, device: Optional[int] = None):
     return out.obj
 
 
+def apply_symmetry_to_moves(players, actions, transforms, inverse: bool = False, device: Optional[int] = None):
+    """apply_symmetry_to_move (symmetry.py:425-464) for a batch: move i = (players[i], actions[i] = shape * 16 + square)
+    under transform code i (encode_transform).  inverse=True applies SymmetryTransform.inverse() of every code: with the
+    codes `canonical_payloads(..., want_transform=True)` returns, that takes moves found on canonical positions back to
+    the positions that were looked up.  -> (players, actions) uint8."""
+    on_dev = _is_torch(actions) and actions.is_cuda
+    d = _dev(device, on_dev, actions.device.index if on_dev else 0)
+    lib = N.init(d)
+    a = _aux_in(actions, np.uint8, on_dev, d)
+    pl = _aux_in(players, np.uint8, on_dev, d)
+    t = _aux_in(transforms, np.uint16, on_dev, d)
+    if not (a.n == pl.n == t.n):
+        raise ValueError("one player and one transform per action required")
+    op, oa = _out((a.n,), np.uint8, on_dev, d), _out((a.n,), np.uint8, on_dev, d)
+    N.check(lib.qk_apply_symmetry_to_moves(pl.ptr, a.ptr, t.ptr, a.n, int(bool(inverse)), op.ptr, oa.ptr, d, _stream(on_dev, d)))
+    return op.obj, oa.obj
+
+
 def canon_dedup(states, mult=None, color_swap: bool = False, cap: Optional[int] = None, device: Optional[int] = None,
                 sort_output: bool = True):
     """Canonicalise, merge equal payloads, sum multiplicities (game_stats.py:487-505).
@@ -466,6 +484,31 @@ def solve(states, device: Optional[int] = None):
     oc, pl, act = _out((s.n,), np.int8, on_dev, d), _out((s.n,), np.uint8, on_dev, d), _out((s.n,), np.uint8, on_dev, d)
     N.check(lib.qk_solve(s.ptr, s.n, oc.ptr, pl.ptr, act.ptr, d, _stream(on_dev, d)))
     return oc.obj, pl.obj, act.obj
+
+
+def solve_moves(states, device: Optional[int] = None):
+    """Exact value of EVERY legal move of each position: one qk_movegen_masks, one qk_apply_moves and one qk_solve over all
+    children.  -> (score (N, 64) int16, optimal (N,) uint64): score[i, a] = the mover's result of action a as
+    +(64 - plies) for a win in `plies` plies, -(64 - plies) for a loss (sooner wins and later losses score higher, the
+    order of MinimaxEngine's W - ply, minimax.py:354-369), 0 for an illegal action; optimal[i] = mask of the actions with
+    the best score.  The reference's best_move is one member of that set -- which one depends on the principal variation
+    its shallower, heuristic iterations happened to leave (minimax.py:258-268), not on the game value; qk_solve reports
+    the lowest member."""
+    s, _, _ = _states_in(states)
+    host = np.asarray(states.cpu().numpy() if _is_torch(states) else states).view(np.uint16).reshape(-1, 8)
+    masks, _, _ = movegen_masks(host, device=device)
+    bits = np.unpackbits(np.ascontiguousarray(masks).view(np.uint8).reshape(-1, 8), axis=1, bitorder="little")
+    pi, act = np.nonzero(bits)
+    score = np.zeros((len(host), 64), np.int16)
+    if len(pi):
+        kids = apply_moves(host[pi], act.astype(np.uint8), device=device)
+        oc, pl, _ = solve(kids, device=device)
+        # the child's value is its mover's: negate, one ply further from the parent
+        score[pi, act] = -(np.asarray(oc, np.int16) * (64 - (np.asarray(pl, np.int16) + 1)))
+    best = np.where(bits.astype(bool), score, np.int16(-32768)).max(axis=1, keepdims=True)
+    opt = (bits.astype(bool) & (score == best)).astype(np.uint8)
+    optimal = np.packbits(opt, axis=1, bitorder="little").view(np.uint64).ravel()
+    return score, optimal
 
 
 def random_roots(n: int, seed: int = SEED_DEFAULT, first: int = 0, min_plies: int = 5, span: int = 7,

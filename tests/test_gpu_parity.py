@@ -106,6 +106,18 @@ def test_fixture_cases_and_api_records():
     for rec in _meta()["api_portability_cases"]:
         ours = Q.portability_case_report(rec["case_id"], rec["qfen"], *moves[rec["case_id"]])
         assert ours == rec, rec["case_id"]
+    # ... and the whole api-portability-report.v1 document (build_report, :194-226) from one batched pass over the fixture
+    fixture = [{"case_id": r["case_id"], "qfen": r["qfen"], "move": {"shape": moves[r["case_id"]][0], "position": moves[r["case_id"]][1]}}
+               for r in reversed(_meta()["api_portability_cases"])]
+    doc = Q.portability_report(fixture, contracts_release="test", contract_ids={"qfen": "qfen.v1"})
+    assert doc["schema"] == "api-portability-report.v1" and doc["contracts_release"] == "test" and doc["contract_ids"] == {"qfen": "qfen.v1"}
+    assert doc["cases"] == sorted(_meta()["api_portability_cases"], key=lambda r: r["case_id"])
+    json.dumps(doc, sort_keys=True)
+    for bad in ([], [{"case_id": "", "qfen": "..../..../..../....", "move": {"shape": 0, "position": 0}}],
+                [{"case_id": "x", "qfen": "..../..../..../....", "move": {"shape": 4, "position": 0}}],
+                [{"case_id": "x", "qfen": "AA../..../..../....", "move": {"shape": 0, "position": 5}}]):      # invalid game state
+        with pytest.raises(ValueError):
+            Q.portability_report(bad)
 
 
 def test_dataset_sample1000_sha256_and_orbit_dedup():
@@ -148,6 +160,39 @@ def test_symmetry_images_and_single_state_api():
     firsts = np.array([Q.apply_move((0,) * 8, Q.Move(0, s, p)) for s in range(4) for p in range(16)], np.uint16)
     uniq, mult = B.canon_dedup(firsts)
     assert len(uniq) == 3 and sorted(mult.tolist()) == [16, 16, 32]
+
+
+def test_apply_symmetry_to_moves_batched():
+    """qk_apply_symmetry_to_moves against the reference's own images (apply_symmetry_to_move, symmetry.py:425-464), the
+    oracle on every (transform, move) pair, and the property that makes it useful: moving then mapping = mapping then moving."""
+    import itertools
+    g = _npz("symmetry_images.npz")
+    mi, mo = g["move_in"].astype(np.int64), g["move_out"].astype(np.int64)
+    pl, ac = B.apply_symmetry_to_moves(mi[:, 0], mi[:, 1] * 16 + mi[:, 2], _enc(g["transform"]))
+    assert np.array_equal(pl, mo[:, 0]) and np.array_equal(ac, mo[:, 1] * 16 + mo[:, 2])
+    # all 384 transforms x 128 moves against the oracle's scalar restatement, and the inverse map undoes every one
+    codes, players, actions, want = [], [], [], []
+    for d4, cs, perm in itertools.product(range(8), (False, True), itertools.permutations(range(4))):
+        for player, a in itertools.product((0, 1), range(64)):
+            codes.append(B.encode_transform(d4, cs, perm)); players.append(player); actions.append(a)
+            want.append(O.apply_symmetry_to_move(player, a >> 4, a & 15, d4, cs, perm))
+    codes, players, actions, want = np.array(codes, np.uint16), np.array(players, np.uint8), np.array(actions, np.uint8), np.array(want)
+    pl, ac = B.apply_symmetry_to_moves(players, actions, codes)
+    assert np.array_equal(pl, want[:, 0]) and np.array_equal(ac, want[:, 1] * 16 + want[:, 2])
+    bp, ba = B.apply_symmetry_to_moves(pl, ac, codes, inverse=True)
+    assert np.array_equal(bp, players) and np.array_equal(ba, actions)
+    # book lookup round trip: canonicalise a position, pick a legal move THERE, map it back with inverse=True: it is legal
+    # on the original position and leads to the same canonical class
+    roots = O.make_roots(5000, seed=21, min_plies=0, span=12)
+    canon, tr = B.canonical_payloads(roots, want_transform=True)
+    cmask, cmover, _ = B.movegen_masks(canon)
+    keep = cmask != 0
+    roots, canon, tr, cmask, cmover = roots[keep], canon[keep], tr[keep], cmask[keep], cmover[keep]
+    first = np.array([(int(m) & -int(m)).bit_length() - 1 for m in cmask], np.uint8)           # lowest legal action on the canonical board
+    bp, ba = B.apply_symmetry_to_moves(cmover, first, tr, inverse=True)
+    rmask, rmover, _ = B.movegen_masks(roots)
+    assert np.array_equal(bp, rmover) and np.all((rmask >> ba.astype(np.uint64)) & np.uint64(1))
+    assert np.array_equal(B.canonical_payloads(B.apply_moves(roots, ba)), B.canonical_payloads(B.apply_moves(canon, first)))
 
 
 def test_canonical_properties_at_full_size():
@@ -548,6 +593,14 @@ def test_exact_endgame_solver():
     g = _npz("solver.npz")
     oc, pl, act = B.solve(g["states"])
     assert np.array_equal(oc.astype(float) * (float(g["win"]) - pl), g["score"])          # MinimaxEngine.solve(...).score
+    # MinimaxEngine.solve(...).best_move: one of the optimal moves (which one depends on the reference's iterative-deepening
+    # history); the set of ALL optimal moves must contain it, and qk_solve's own move is the lowest member of that set
+    score, optimal = B.solve_moves(g["states"])
+    ref_a = g["best_action"].astype(np.uint64)
+    assert np.all((optimal >> ref_a) & np.uint64(1))
+    live = act != 255
+    assert np.array_equal(act[live], np.array([(int(m) & -int(m)).bit_length() - 1 for m in optimal[live]], np.uint8))
+    assert np.array_equal(score[np.arange(len(act))[live], act[live]], (oc.astype(np.int16) * (64 - pl.astype(np.int16)))[live])
     o = O.solve(g["states"])
     assert np.array_equal(oc, o[0]) and np.array_equal(pl, o[1]) and np.array_equal(act, o[2])
     # 3000 positions with 4..9 empty squares + finished / blocked / invalid ones against the oracle negamax
@@ -657,6 +710,9 @@ def test_exchange_step_functions_at_world_size_one_and_two_gpus():
     # owners partition the classes evenly enough to be useful
     owners = D.owner_rank(u, 8).numpy()
     assert np.bincount(owners, minlength=8).min() > len(u) // 16
+    # the NCCL path's owner function (torch) is the library's (qk_payload_owner): both exchanges partition alike
+    for w in (1, 2, 3, 8, 16):
+        assert np.array_equal(D.owner_rank(u, w).numpy(), B.payload_owner(u, w).astype(np.int64)), w
     if torch.cuda.device_count() >= 2:
         root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
         import socket

@@ -9,6 +9,7 @@
 //   k_dedup_compact  table -> dense (key, multiplicity) arrays
 //   k_bitonic_step   sorts the distinct keys in payload byte order (deterministic output)
 #include "qk_common.cuh"
+#include <math.h>
 #include "qk_bits.cuh"
 #include "qk_perft_core.cuh"
 
@@ -55,15 +56,12 @@ __global__ void __launch_bounds__(kBlock) k_dedup_fill(TSlot *table, size_t slot
     }
 }
 
-// Adds multiplicity m to key (khi_new, klo_new), creating the entry when it is new.  -> true when THIS call
-// created it.  Distinct keys are counted by the callers in registers and added to the global counter once per
-// warp at the end of the kernel (flush_claims): a per-insert atomic on one address serialises in one L2 slice.
-__device__ __forceinline__ bool table_insert(TSlot *table, size_t slots, u64 khi_new, u64 klo_new, u64 m,
-                                             u64 *all_ones_count, int *overflow)
+// Adds multiplicity m to key (khi_new, klo_new), creating the entry when it is new, probing linearly from `slot`.
+// -> true when THIS call created it.  Distinct keys are counted by the callers in registers and added to the global
+// counter once per warp at the end of the kernel (flush_claims): a per-insert atomic on one address serialises in
+// one L2 slice.
+__device__ __forceinline__ bool table_insert_at(TSlot *table, size_t slots, size_t slot, u64 khi_new, u64 klo_new, u64 m, int *overflow)
 {
-    if ((khi_new & klo_new) == ~0ull) { atomicAdd(all_ones_count, m); return false; }   // the payload that equals the empty marker
-    // any table size (not only powers of two: the table is filled and scanned once per call, so its size is time)
-    size_t slot = (size_t)__umul64hi(mix(khi_new, klo_new), (u64)slots);
     const size_t max_probe = slots - 1 < kMaxProbe ? slots - 1 : kMaxProbe;
     for (size_t probe = 0; probe <= max_probe; ++probe, slot = slot + 1 == slots ? 0 : slot + 1) {
         // fast path: one 128-bit load; a slot caught half-way through another thread's
@@ -79,6 +77,13 @@ __device__ __forceinline__ bool table_insert(TSlot *table, size_t slots, u64 khi
     }
     *overflow = 1;      // no room within kMaxProbe slots: the host retries with a larger table
     return false;
+}
+__device__ __forceinline__ bool table_insert(TSlot *table, size_t slots, u64 khi_new, u64 klo_new, u64 m,
+                                             u64 *all_ones_count, int *overflow)
+{
+    if ((khi_new & klo_new) == ~0ull) { atomicAdd(all_ones_count, m); return false; }   // the payload that equals the empty marker
+    // any table size (not only powers of two: the table is filled and scanned once per call, so its size is time)
+    return table_insert_at(table, slots, (size_t)__umul64hi(mix(khi_new, klo_new), (u64)slots), khi_new, klo_new, m, overflow);
 }
 
 // every lane of the warp must call this (after its loops): one atomic per warp and kernel
@@ -374,6 +379,101 @@ __global__ void __launch_bounds__(kBlock) k_book_expand_insert(const uint4 *__re
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Two-level insert.  A table for tens of millions of classes is far larger than the 126 MB L2, and every insert
+// into it is a random DRAM sector: read for the probe, written back after the multiplicity's RED, read again by the
+// next duplicate (ncu, profiles/r01g_*: 80 B of DRAM reads per key against 24 B of key + multiplicity).  Here the
+// keys are first ROUTED by the high hash bits into `parts` buckets (pass A: streaming writes), then the buckets are
+// merged one at a time into ONE table that is small enough to stay in L2 and is reused for every bucket
+// (pass B: the probes, the CAS and the RED are L2 hits; the table never travels to DRAM), and each bucket's classes
+// are appended to the output as soon as it is merged.  DRAM sees every key twice, sequentially.
+//   Buckets are cut per producing block -- sub-bucket (part, block) is a private range with its cursor in shared
+// memory -- so routing needs no global atomics; a block's share of a part is binomial, the ranges are sized at the
+// mean + 6 sigma, and an overflowing range sends the whole call back to the one-level path.
+static constexpr int kMaxParts = 1024;
+static constexpr size_t kL2TableBytes = 40u << 20;          // one part's table: what reliably stays resident next to the streams
+
+__device__ __forceinline__ void route(u64 hi, u64 lo, int parts, uint32_t part_slots, int &part, uint32_t &slot)
+{
+    const u64 h = mix(hi, lo);
+    part = (int)__umulhi((uint32_t)(h >> 32), (uint32_t)parts);
+    slot = __umulhi((uint32_t)h, part_slots);
+}
+
+struct Buckets {
+    Slot *keys;              // [parts][blocks][sub_cap]
+    u64 *mults;              // same shape, or null when every multiplicity is 1
+    unsigned *counts;        // [parts][blocks]
+    int parts;
+    unsigned blocks;
+    uint32_t sub_cap, part_slots;
+};
+
+__device__ __forceinline__ void bucket_put(const Buckets &b, unsigned *s_cur, u64 hi, u64 lo, u64 m, u64 *all_ones_count, int *overflow)
+{
+    if ((hi & lo) == ~0ull) { atomicAdd(all_ones_count, m); return; }       // the payload that equals the empty marker
+    int part;
+    uint32_t slot;
+    route(hi, lo, b.parts, b.part_slots, part, slot);
+    const unsigned pos = atomicAdd(&s_cur[part], 1u);
+    if (pos >= b.sub_cap) { *overflow = 1; return; }
+    const size_t at = ((size_t)part * b.blocks + blockIdx.x) * b.sub_cap + pos;
+    b.keys[at].hi = hi; b.keys[at].lo = lo;
+    if (b.mults) b.mults[at] = m;
+}
+
+template <bool COLOR_SWAP>
+__global__ void __launch_bounds__(kBlock) k_bucket_states(const uint4 *__restrict__ states, const u64 *__restrict__ mult, size_t n,
+                                                           size_t per_block, Buckets b, u64 *all_ones_count, int *overflow)
+{
+    extern __shared__ unsigned s_cur[];
+    for (int k = threadIdx.x; k < b.parts; k += kBlock) s_cur[k] = 0;
+    __syncthreads();
+    const size_t begin = blockIdx.x * per_block, end = begin + per_block < n ? begin + per_block : n;
+    for (size_t i = begin + threadIdx.x; i < end; i += kBlock) {
+        const uint4 v = __ldg(states + i);
+        const State4 st = { v.x, v.y, v.z, v.w };
+        const State4 c = canonical<COLOR_SWAP>(st);
+        bucket_put(b, s_cur, ((u64)prmt(c.x, 0, 0x0123) << 32) | prmt(c.y, 0, 0x0123), ((u64)prmt(c.z, 0, 0x0123) << 32) | prmt(c.w, 0, 0x0123),
+                   mult ? mult[i] : 1ull, all_ones_count, overflow);
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < b.parts; k += kBlock)
+        b.counts[(size_t)k * b.blocks + blockIdx.x] = s_cur[k] < b.sub_cap ? s_cur[k] : b.sub_cap;
+}
+
+// pass B, first half: every sub-bucket of one part into the L2-resident table
+__global__ void __launch_bounds__(kBlock) k_part_insert(Buckets b, int part, TSlot *table, u64 *n_unique, int *overflow, u64 max_unique)
+{
+    unsigned claims = 0;
+    for (unsigned blk = blockIdx.x; blk < b.blocks; blk += gridDim.x) {
+        const size_t sub = (size_t)part * b.blocks + blk, base = sub * b.sub_cap;
+        const unsigned cnt = b.counts[sub];
+        for (unsigned i = threadIdx.x; i < cnt; i += kBlock) {
+            const ulonglong2 k = *reinterpret_cast<const ulonglong2 *>(b.keys + base + i);
+            const uint32_t slot = __umulhi((uint32_t)mix(k.x, k.y), b.part_slots);
+            claims += table_insert_at(table, b.part_slots, slot, k.x, k.y, b.mults ? b.mults[base + i] : 1ull, overflow) ? 1u : 0u;
+        }
+    }
+    flush_claims(claims, n_unique, overflow, max_unique);
+}
+
+// pass B, second half: the part's classes are appended to the dense (key, multiplicity) arrays and the table is
+// left empty for the next part (part_slots is a multiple of 256: warps scan it converged)
+__global__ void __launch_bounds__(kBlock) k_part_drain(TSlot *table, uint32_t part_slots, Slot *keys, u64 *mults, u64 *cursor, u64 max_out)
+{
+    for (size_t i = blockIdx.x * (size_t)kBlock + threadIdx.x; i < part_slots; i += (size_t)gridDim.x * kBlock) {
+        const TSlot k = load_entry(table, i);
+        const bool have = !(k.hi == ~0ull && k.lo == ~0ull);
+        const u64 o = compact_slot(have, cursor);
+        if (have) {
+            if (o < max_out) { keys[o].hi = k.hi; keys[o].lo = k.lo; mults[o] = k.count; }
+            const ulonglong4 e = { ~0ull, ~0ull, 0ull, 0ull };
+            *reinterpret_cast<ulonglong4 *>(table + i) = e;
+        }
+    }
+}
+
 // ------------------------------------------------------------------ host side
 struct DedupTable { TSlot *table; u64 *meta; size_t slots; u64 max_unique; };
 
@@ -391,6 +491,42 @@ static int dedup_begin(Call &call, size_t expected_unique, DedupTable &t)
     t.max_unique = (u64)(expected_unique < 512 ? 512 : expected_unique);
     k_dedup_fill<<<grid_for(t.slots, kBlock, call.ctx()->sms, 8), kBlock, 0, s>>>(t.table, t.slots);
     QK_CUDA(cudaGetLastError());
+    return QK_OK;
+}
+
+// dense (keys, mults)[0, nu) in arrays with room for `padded` + 1 entries (padded = a power of two >= nu and >= kTile when
+// `sort`) -> the caller's buffers, in payload byte order when `sort`; the all-ones class (kept outside the tables) last
+static int dedup_emit_dense(Call &call, Slot *keys, u64 *mults, size_t padded, size_t nu, bool special, u64 special_mult,
+                            uint16_t *uniq, uint64_t *uniq_mult, size_t *n_uniq, bool sort)
+{
+    cudaStream_t s = call.stream();
+    Ctx *c = call.ctx();
+    if (sort) {
+        k_pad<<<grid_for(padded - nu + 1, kBlock, c->sms, 8), kBlock, 0, s>>>(keys, mults, nu, padded);
+        const unsigned tile_grid = grid_for(padded / kTile * kBlock, kBlock, c->sms, 8);
+        k_bitonic_tile<<<tile_grid, kBlock, 0, s>>>(keys, mults, padded, 2, kTile);
+        for (size_t k = 2 * (size_t)kTile; k <= padded; k <<= 1) {
+            for (size_t j = k >> 1; j >= kTile; j >>= 1)
+                k_bitonic_step<<<grid_for(padded, kBlock, c->sms, 8), kBlock, 0, s>>>(keys, mults, padded, j, k);
+            k_bitonic_tile<<<tile_grid, kBlock, 0, s>>>(keys, mults, padded, k, k);
+        }
+        QK_CUDA(cudaGetLastError());
+    }
+    if (special) {   // the all-ones payload sorts last by construction
+        Slot ones = { ~0ull, ~0ull };
+        QK_CUDA(cudaMemcpyAsync(keys + nu, &ones, sizeof ones, cudaMemcpyHostToDevice, s));
+        QK_CUDA(cudaMemcpyAsync(mults + nu, &special_mult, sizeof(u64), cudaMemcpyHostToDevice, s));
+        QK_CUDA(cudaStreamSynchronize(s));
+        ++nu;
+    }
+    *n_uniq = nu;
+    if (nu && (uniq || uniq_mult)) {
+        uint4 *d_uniq = (uint4 *)call.out(uniq, nu * 16);
+        u64 *d_um = (u64 *)call.out(uniq_mult, nu * 8);
+        if (call.status() != QK_OK) return call.status();
+        k_emit<<<grid_for(nu, kBlock, c->sms, 8), kBlock, 0, s>>>(keys, mults, nu, d_uniq, d_um);
+        QK_CUDA(cudaGetLastError());
+    }
     return QK_OK;
 }
 
@@ -434,31 +570,75 @@ static int dedup_finish(Call &call, DedupTable &t, uint16_t *uniq, uint64_t *uni
     u64 *mults = (u64 *)call.temp((padded + 1) * sizeof(u64));
     if (!keys || !mults) return call.status();
     k_dedup_compact<<<grid_for(t.slots, kBlock, c->sms, 8), kBlock, 0, s>>>(t.table, t.slots, keys, mults, t.meta + 2);
-    k_pad<<<grid_for(padded - nu + 1, kBlock, c->sms, 8), kBlock, 0, s>>>(keys, mults, nu, padded);
-    const unsigned tile_grid = grid_for(padded / kTile * kBlock, kBlock, c->sms, 8);
-    k_bitonic_tile<<<tile_grid, kBlock, 0, s>>>(keys, mults, padded, 2, kTile);
-    for (size_t k = 2 * (size_t)kTile; k <= padded; k <<= 1) {
-        for (size_t j = k >> 1; j >= kTile; j >>= 1)
-            k_bitonic_step<<<grid_for(padded, kBlock, c->sms, 8), kBlock, 0, s>>>(keys, mults, padded, j, k);
-        k_bitonic_tile<<<tile_grid, kBlock, 0, s>>>(keys, mults, padded, k, k);
+    QK_CUDA(cudaGetLastError());
+    return dedup_emit_dense(call, keys, mults, padded, nu, special, h_meta[1], uniq, uniq_mult, n_uniq, true);
+}
+
+// Plan of a two-level merge of `n_keys` keys with at most `expected_unique` classes (see the kernels above).
+static bool plan_two_level(size_t n_keys, size_t expected_unique, int sms, Buckets &b, size_t &per_block)
+{
+    const size_t slots = expected_unique + expected_unique / 2 + 2;
+    size_t parts = (slots * sizeof(TSlot) + kL2TableBytes - 1) / kL2TableBytes;
+    if (parts < 2) parts = 2;
+    if (parts > (size_t)kMaxParts) return false;
+    // hash-uniform shares: mean + 6 sigma of the classes of one part, 1.5 slots per class, a multiple of 256
+    const double mean = (double)expected_unique / (double)parts;
+    size_t part_slots = (size_t)(1.5 * (mean + 6.0 * sqrt(mean) + 64.0));
+    part_slots = (part_slots + 255) / 256 * 256;
+    if (part_slots >= (1ull << 32)) return false;
+    b.parts = (int)parts;
+    b.part_slots = (uint32_t)part_slots;
+    b.blocks = (unsigned)sms * 4;
+    per_block = (n_keys + b.blocks - 1) / b.blocks;
+    per_block = (per_block + kBlock - 1) / kBlock * kBlock;
+    const double share = (double)per_block / (double)parts;
+    b.sub_cap = (uint32_t)(share + 6.0 * sqrt(share) + 32.0);
+    return true;
+}
+
+// pass B for every part + the tail.  meta = n_unique, all-ones mult, cursor, overflow (as DedupTable::meta)
+static int merge_buckets(Call &call, const Buckets &b, u64 *meta, size_t expected_unique, uint16_t *uniq, uint64_t *uniq_mult,
+                         size_t cap, size_t *n_uniq, bool sort_output, const char *who, bool *fallback)
+{
+    cudaStream_t s = call.stream();
+    Ctx *c = call.ctx();
+    *fallback = false;
+    TSlot *table = (TSlot *)call.temp((size_t)b.part_slots * sizeof(TSlot));
+    size_t padded = kTile;
+    while (padded < expected_unique) padded <<= 1;
+    if (!sort_output) padded = expected_unique;
+    Slot *keys = (Slot *)call.temp((padded + 1) * sizeof(Slot));
+    u64 *mults = (u64 *)call.temp((padded + 1) * sizeof(u64));
+    if (!table || !keys || !mults) return call.status();
+    k_dedup_fill<<<grid_for(b.part_slots, kBlock, c->sms, 8), kBlock, 0, s>>>(table, b.part_slots);
+    const u64 max_unique = (u64)(expected_unique < 512 ? 512 : expected_unique);
+    const unsigned insert_grid = b.blocks < (unsigned)c->sms * 8 ? b.blocks : (unsigned)c->sms * 8;
+    for (int part = 0; part < b.parts; ++part) {
+        k_part_insert<<<insert_grid, kBlock, 0, s>>>(b, part, table, meta, (int *)(meta + 3), max_unique);
+        k_part_drain<<<grid_for(b.part_slots, kBlock, c->sms, 8), kBlock, 0, s>>>(table, b.part_slots, keys, mults, meta + 2, (u64)padded);
     }
     QK_CUDA(cudaGetLastError());
-    if (special) {   // the all-ones payload sorts last by construction
-        Slot ones = { ~0ull, ~0ull };
-        QK_CUDA(cudaMemcpyAsync(keys + nu, &ones, sizeof ones, cudaMemcpyHostToDevice, s));
-        QK_CUDA(cudaMemcpyAsync(mults + nu, &h_meta[1], sizeof(u64), cudaMemcpyHostToDevice, s));
-        QK_CUDA(cudaStreamSynchronize(s));
-        ++nu;
+    u64 h_meta[4];
+    QK_CUDA(cudaMemcpyAsync(h_meta, meta, sizeof h_meta, cudaMemcpyDeviceToHost, s));
+    QK_CUDA(cudaStreamSynchronize(s));
+    if ((int)h_meta[3] != 0) { *fallback = true; return QK_OK; }         // a range or the part table was too small
+    const size_t nu = (size_t)h_meta[0];
+    const bool special = h_meta[1] != 0;
+    if (nu + (special ? 1 : 0) > cap && (uniq || uniq_mult)) {
+        *n_uniq = nu + (special ? 1 : 0);
+        set_error(std::string(who) + ": more distinct canonical states than `cap`");
+        return QK_E_NOMEM;
     }
-    *n_uniq = nu;
-    if (nu && (uniq || uniq_mult)) {
-        uint4 *d_uniq = (uint4 *)call.out(uniq, nu * 16);
-        u64 *d_um = (u64 *)call.out(uniq_mult, nu * 8);
-        if (call.status() != QK_OK) return call.status();
-        k_emit<<<grid_for(nu, kBlock, c->sms, 8), kBlock, 0, s>>>(keys, mults, nu, d_uniq, d_um);
-        QK_CUDA(cudaGetLastError());
-    }
-    return QK_OK;
+    return dedup_emit_dense(call, keys, mults, padded, nu, special, h_meta[1], uniq, uniq_mult, n_uniq, sort_output);
+}
+
+static int alloc_buckets(Call &call, Buckets &b, bool with_mults)
+{
+    const size_t entries = (size_t)b.parts * b.blocks * b.sub_cap;
+    b.keys = (Slot *)call.temp(entries * sizeof(Slot));
+    b.mults = with_mults ? (u64 *)call.temp(entries * sizeof(u64)) : nullptr;
+    b.counts = (unsigned *)call.temp((size_t)b.parts * b.blocks * sizeof(unsigned));
+    return (!b.keys || !b.counts || (with_mults && !b.mults)) ? call.status() : QK_OK;
 }
 
 int run_dedup(Call &call, const uint4 *states, const uint64_t *mult, size_t n, int color_swap,
@@ -466,10 +646,33 @@ int run_dedup(Call &call, const uint4 *states, const uint64_t *mult, size_t n, i
 {
     cudaStream_t s = call.stream();
     Ctx *c = call.ctx();
-    DedupTable t;
-    int rc = dedup_begin(call, n < cap ? n : cap, t);
-    if (rc != QK_OK) return rc;
     const bool unsorted = (color_swap & QK_DEDUP_UNSORTED) != 0;
+    const size_t expected = n < cap ? n : cap;
+    // two-level merge when the one-level table would not stay in L2 (qk_set_option "dedup_mode": 1 = never, 2 = always)
+    const long long mode = option(OPT_DEDUP_MODE);
+    Buckets b;
+    size_t per_block = 0;
+    if (mode != 1 && (mode == 2 || (expected + expected / 2) * sizeof(TSlot) > 2 * kL2TableBytes) &&
+        plan_two_level(n, expected, c->sms, b, per_block)) {
+        int rc = alloc_buckets(call, b, mult != nullptr);
+        if (rc != QK_OK) return rc;
+        u64 *meta = (u64 *)call.temp(10 * sizeof(u64), true);
+        if (!meta) return call.status();
+        const size_t smem = (size_t)b.parts * sizeof(unsigned);
+        if (color_swap & 1)
+            k_bucket_states<true><<<b.blocks, kBlock, smem, s>>>(states, (const u64 *)mult, n, per_block, b, meta + 1, (int *)(meta + 3));
+        else
+            k_bucket_states<false><<<b.blocks, kBlock, smem, s>>>(states, (const u64 *)mult, n, per_block, b, meta + 1, (int *)(meta + 3));
+        QK_CUDA(cudaGetLastError());
+        bool fallback = false;
+        rc = merge_buckets(call, b, meta, expected, uniq, uniq_mult, cap, n_uniq, !unsorted, "qk_canon_dedup", &fallback);
+        if (rc != QK_OK || !fallback) return rc;
+        call.release(b.keys); call.release(b.counts);
+        if (b.mults) call.release(b.mults);
+    }
+    DedupTable t;
+    int rc = dedup_begin(call, expected, t);
+    if (rc != QK_OK) return rc;
     if (color_swap & 1)
         k_dedup_insert<true><<<grid_for(n, kBlock, c->sms, 8), kBlock, 0, s>>>(states, (const u64 *)mult, n, t.table, t.slots,
                                                                              t.meta, t.meta + 1, (int *)(t.meta + 3), t.max_unique);

@@ -34,8 +34,11 @@ if "bfs" in what:
     out["bfs16_s"] = best(lambda: Q.symmetry_table(16))
 if "dedup" in what:
     pos = Q.random_roots(1 << 24, min_plies=3, span=6, as_torch=True)
-    t = best(lambda: Q.canon_dedup(pos, None, sort_output=False), 5)
-    out["dedup_2p24_keys_per_s"] = (1 << 24) / t
+    for mode, name in ((1, "one_level"), (2, "two_level")):
+        N.set_option("dedup_mode", mode)
+        t = best(lambda: Q.canon_dedup(pos, None, sort_output=False), 5)
+        out[f"dedup_2p24_{name}_keys_per_s"] = (1 << 24) / t
+    N.set_option("dedup_mode", 0)
     del pos
 if "guided" in what:
     e = np.zeros((1, 8), np.uint16)

@@ -32,6 +32,21 @@ def _enc(t):
     return (t[:, 0] | (t[:, 1] << 3) | (t[:, 2] << 4) | (t[:, 3] << 6) | (t[:, 4] << 8) | (t[:, 5] << 10)).astype(np.uint16)
 
 
+@pytest.fixture
+def options():
+    """qk_set_option switches (kernel variants that compute the same result), restored to the defaults afterwards."""
+    from quantik_b200 import _native as N
+    touched = set()
+
+    def set_option(name, value):
+        touched.add(name)
+        N.set_option(name, value)
+
+    yield set_option
+    for name in touched:
+        N.set_option(name, 0)
+
+
 def _random_positions(n, seed=1234):
     """reachable positions of every depth + corrupted ones, generated with the oracle"""
     a = O.make_roots(n // 2, seed=seed, min_plies=0, span=13)
@@ -248,6 +263,34 @@ def test_canon_dedup_vs_oracle_with_multiplicities():
     assert np.array_equal(uniq[-1], ones[0]) and int(um[-1]) == 5
 
 
+def test_two_level_merge_equals_one_level_table(options):
+    """qk_canon_dedup's two paths -- one table (the reference's one dictionary, game_stats.py:487-505) and keys routed into
+    L2-sized parts that are merged one at a time -- give the same classes and multiplicities: small inputs (forced), weighted,
+    colour-swap mode, the all-ones payload, sorted and table order, and a 2^22-key set where the automatic choice is two-level."""
+    import torch
+    rng = np.random.default_rng(11)
+    small = _random_positions(30_000, seed=3)
+    small = np.concatenate([small, small[:7000], np.full((3, 8), 0xFFFF, np.uint16)])
+    wts = rng.integers(1, 1 << 40, len(small)).astype(np.uint64)
+    big = B.random_roots(1 << 22, seed=99, min_plies=2, span=8)
+    for states, mult, cs in ((small, None, False), (small, wts, False), (small, wts, True), (big, None, False)):
+        res = {}
+        for mode in (1, 2):
+            options("dedup_mode", mode)
+            u, m = B.canon_dedup(states, mult, color_swap=cs)
+            res[mode] = (u, m)
+            tu, tm = B.canon_dedup(torch.from_numpy(states.view(np.int16)).cuda(), None if mult is None else torch.from_numpy(mult.view(np.int64)).cuda(),
+                                   color_swap=cs, sort_output=False)
+            tu, tm = tu.cpu().numpy().view(np.uint16), tm.cpu().numpy().view(np.uint64)
+            order = np.lexsort(tu.astype("<u2").view(np.uint8).reshape(-1, 16).T[::-1])
+            assert np.array_equal(tu[order], u) and np.array_equal(tm[order], m), (mode, "unsorted path")
+        assert np.array_equal(res[1][0], res[2][0]) and np.array_equal(res[1][1], res[2][1])
+        assert int(res[2][1].sum()) == (len(states) if mult is None else int(mult.sum()))
+    options("dedup_mode", 0)
+    u0, m0 = B.canon_dedup(big)
+    assert np.array_equal(u0, res[1][0]) and np.array_equal(m0, res[1][1])
+
+
 # ----------------------------------------------------------------------------- playouts
 def test_playouts_vs_reference_rules_goldens():
     p = _npz("playouts_philox.npz")
@@ -372,21 +415,6 @@ def test_perft_weighted_canonical_roots_and_oracle():
     g, o = B.perft(sp, 3), O.perft(sp, 3)
     for k in o:
         assert np.array_equal(g[k], o[k]), k
-
-
-@pytest.fixture
-def options():
-    """qk_set_option switches (kernel variants that compute the same result), restored to the defaults afterwards."""
-    from quantik_b200 import _native as N
-    touched = set()
-
-    def set_option(name, value):
-        touched.add(name)
-        N.set_option(name, value)
-
-    yield set_option
-    for name in touched:
-        N.set_option(name, 0)
 
 
 def test_perft_lane_kernel_matches_warp_kernel_and_oracle(options):

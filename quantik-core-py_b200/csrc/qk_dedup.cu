@@ -390,8 +390,17 @@ __global__ void __launch_bounds__(kBlock) k_book_expand_insert(const uint4 *__re
 //   Buckets are cut per producing block -- sub-bucket (part, block) is a private range with its cursor in shared
 // memory -- so routing needs no global atomics; a block's share of a part is binomial, the ranges are sized at the
 // mean + 6 sigma, and an overflowing range sends the whole call back to the one-level path.
+//   What it buys (profiles/r02_atomics_rate.txt, r02_insert_rate.txt): random probe / RED / 128-bit CAS run at
+// 2.2 / 1.8 / 1.0 x 10^11 per second on an L2-resident table against 4.1 / 2.2 / 2.2 x 10^10 on a 1 GiB one, and an
+// insert is a probe, a RED and (first arrival, or a duplicate racing it) a CAS: about 2.7 x 10^10 inserts/s in L2.
+// The merge is bound by the L2's atomic units either way, not by DRAM bytes; the two-level form is 1.5x the
+// one-level one on 2^24 keys, and is NOT used for the BFS expansion, whose 2.7 x 10^10 children/s already equal it.
 static constexpr int kMaxParts = 1024;
-static constexpr size_t kL2TableBytes = 40u << 20;          // one part's table: what reliably stays resident next to the streams
+// one part's table.  Measured on 2^24 keys (scripts/dedup_case.py, whole call): 24 MiB parts 2.01 ms, 40 MiB 1.64 ms,
+// 64 MiB 1.36 ms, 96 MiB 1.23 ms (one-level table: 1.85 ms) -- fewer, larger parts win as long as the table still
+// fits the 126 MB L2 next to the bucket streams.
+static constexpr size_t kL2TableBytes = 96u << 20;
+static size_t l2_table_bytes() { const long long mb = option(OPT_DEDUP_PART_MB); return mb > 0 ? (size_t)mb << 20 : kL2TableBytes; }
 
 __device__ __forceinline__ void route(u64 hi, u64 lo, int parts, uint32_t part_slots, int &part, uint32_t &slot)
 {
@@ -442,35 +451,110 @@ __global__ void __launch_bounds__(kBlock) k_bucket_states(const uint4 *__restric
         b.counts[(size_t)k * b.blocks + blockIdx.x] = s_cur[k] < b.sub_cap ? s_cur[k] : b.sub_cap;
 }
 
-// pass B, first half: every sub-bucket of one part into the L2-resident table
+// pass B, first half: every sub-bucket of one part into the L2-resident table.  Four keys per thread at a time: the
+// four key loads, then the four probe loads are in flight together (a probe read early may be stale, which is safe:
+// a slot only ever changes from empty to a key, an "empty" that is no longer true fails its CAS and a key stays).
+static constexpr int kInsertBatch = 4;
 __global__ void __launch_bounds__(kBlock) k_part_insert(Buckets b, int part, TSlot *table, u64 *n_unique, int *overflow, u64 max_unique)
 {
     unsigned claims = 0;
     for (unsigned blk = blockIdx.x; blk < b.blocks; blk += gridDim.x) {
         const size_t sub = (size_t)part * b.blocks + blk, base = sub * b.sub_cap;
         const unsigned cnt = b.counts[sub];
-        for (unsigned i = threadIdx.x; i < cnt; i += kBlock) {
-            const ulonglong2 k = *reinterpret_cast<const ulonglong2 *>(b.keys + base + i);
-            const uint32_t slot = __umulhi((uint32_t)mix(k.x, k.y), b.part_slots);
-            claims += table_insert_at(table, b.part_slots, slot, k.x, k.y, b.mults ? b.mults[base + i] : 1ull, overflow) ? 1u : 0u;
+        for (unsigned i0 = threadIdx.x; i0 < cnt; i0 += kBlock * kInsertBatch) {
+            ulonglong2 key[kInsertBatch], raw[kInsertBatch];
+            u64 m[kInsertBatch];
+            uint32_t slot[kInsertBatch];
+#pragma unroll
+            for (int k = 0; k < kInsertBatch; ++k) {
+                const unsigned i = i0 + k * kBlock;
+                key[k] = make_ulonglong2(~0ull, ~0ull);
+                m[k] = 1ull;
+                if (i < cnt) {
+                    key[k] = *reinterpret_cast<const ulonglong2 *>(b.keys + base + i);
+                    if (b.mults) m[k] = b.mults[base + i];
+                }
+            }
+            unsigned pending = 0;
+#pragma unroll
+            for (int k = 0; k < kInsertBatch; ++k) {
+                slot[k] = __umulhi((uint32_t)mix(key[k].x, key[k].y), b.part_slots);
+                if (i0 + k * kBlock < cnt) pending |= 1u << k;
+            }
+            // probe rounds in step for the whole batch: the loads of a round go out together, then its claims, then
+            // the answers are looked at; a key whose slot holds another key moves one slot on and joins the next round
+            // (finishing each key's chain on its own made the warp wait for 4 chains one after the other)
+            for (uint32_t round = 0; pending; ++round) {
+                if (round > kMaxProbe || round >= b.part_slots) { *overflow = 1; break; }
+#pragma unroll
+                for (int k = 0; k < kInsertBatch; ++k)
+                    if ((pending >> k) & 1u) raw[k] = __ldcv(reinterpret_cast<const ulonglong2 *>(table + slot[k]));
+                unsigned tried = 0;
+#pragma unroll
+                for (int k = 0; k < kInsertBatch; ++k)
+                    if (((pending >> k) & 1u) && (raw[k].x == ~0ull || raw[k].y == ~0ull)) {
+                        tried |= 1u << k;
+                        cas128(table + slot[k], ~0ull, ~0ull, key[k].x, key[k].y, raw[k].x, raw[k].y);
+                    }
+#pragma unroll
+                for (int k = 0; k < kInsertBatch; ++k) {
+                    if (!((pending >> k) & 1u)) continue;
+                    const bool claimed = ((tried >> k) & 1u) && raw[k].x == ~0ull && raw[k].y == ~0ull;
+                    if (claimed || (raw[k].x == key[k].x && raw[k].y == key[k].y)) {
+                        atomicAdd(&table[slot[k]].count, m[k]);                    // game_stats.py:487-505
+                        claims += claimed ? 1u : 0u;
+                        pending &= ~(1u << k);
+                    } else {
+                        slot[k] = slot[k] + 1 == b.part_slots ? 0 : slot[k] + 1;
+                    }
+                }
+            }
         }
     }
     flush_claims(claims, n_unique, overflow, max_unique);
 }
 
 // pass B, second half: the part's classes are appended to the dense (key, multiplicity) arrays and the table is
-// left empty for the next part (part_slots is a multiple of 256: warps scan it converged)
+// left empty for the next part.  A block takes a contiguous run of kDrainItems x 256 slots, counts its entries and
+// reserves their place with ONE atomic (a warp-level reservation made the single cursor the bottleneck: 37 000
+// same-address atomics per part).  part_slots is a multiple of 256.
+static constexpr int kDrainItems = 4;
 __global__ void __launch_bounds__(kBlock) k_part_drain(TSlot *table, uint32_t part_slots, Slot *keys, u64 *mults, u64 *cursor, u64 max_out)
 {
-    for (size_t i = blockIdx.x * (size_t)kBlock + threadIdx.x; i < part_slots; i += (size_t)gridDim.x * kBlock) {
-        const TSlot k = load_entry(table, i);
-        const bool have = !(k.hi == ~0ull && k.lo == ~0ull);
-        const u64 o = compact_slot(have, cursor);
-        if (have) {
-            if (o < max_out) { keys[o].hi = k.hi; keys[o].lo = k.lo; mults[o] = k.count; }
-            const ulonglong4 e = { ~0ull, ~0ull, 0ull, 0ull };
-            *reinterpret_cast<ulonglong4 *>(table + i) = e;
+    __shared__ unsigned s_warp[kBlock / 32];
+    __shared__ u64 s_base;
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    for (size_t run = blockIdx.x * (size_t)(kBlock * kDrainItems); run < part_slots; run += (size_t)gridDim.x * kBlock * kDrainItems) {
+        TSlot e[kDrainItems];
+        unsigned mask[kDrainItems], mine = 0;
+#pragma unroll
+        for (int k = 0; k < kDrainItems; ++k) {
+            const size_t i = run + (size_t)k * kBlock + threadIdx.x;
+            e[k].hi = ~0ull; e[k].lo = ~0ull; e[k].count = 0;
+            if (i < part_slots) e[k] = load_entry(table, i);
+            mask[k] = __ballot_sync(0xFFFFFFFFu, !(e[k].hi == ~0ull && e[k].lo == ~0ull));
+            mine += (unsigned)__popc(mask[k]);
         }
+        if (lane == 0) s_warp[warp] = mine;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned total = 0;
+            for (unsigned w = 0; w < kBlock / 32; ++w) { const unsigned c = s_warp[w]; s_warp[w] = total; total += c; }
+            s_base = total ? atomicAdd(cursor, (u64)total) : 0ull;
+        }
+        __syncthreads();
+        u64 o = s_base + s_warp[warp];
+#pragma unroll
+        for (int k = 0; k < kDrainItems; ++k) {
+            if ((mask[k] >> lane) & 1u) {
+                const u64 at = o + (u64)__popc(mask[k] & ((1u << lane) - 1u));
+                if (at < max_out) { keys[at].hi = e[k].hi; keys[at].lo = e[k].lo; mults[at] = e[k].count; }
+                const ulonglong4 empty = { ~0ull, ~0ull, 0ull, 0ull };
+                *reinterpret_cast<ulonglong4 *>(table + run + (size_t)k * kBlock + threadIdx.x) = empty;
+            }
+            o += (u64)__popc(mask[k]);
+        }
+        __syncthreads();
     }
 }
 
@@ -578,7 +662,7 @@ static int dedup_finish(Call &call, DedupTable &t, uint16_t *uniq, uint64_t *uni
 static bool plan_two_level(size_t n_keys, size_t expected_unique, int sms, Buckets &b, size_t &per_block)
 {
     const size_t slots = expected_unique + expected_unique / 2 + 2;
-    size_t parts = (slots * sizeof(TSlot) + kL2TableBytes - 1) / kL2TableBytes;
+    size_t parts = (slots * sizeof(TSlot) + l2_table_bytes() - 1) / l2_table_bytes();
     if (parts < 2) parts = 2;
     if (parts > (size_t)kMaxParts) return false;
     // hash-uniform shares: mean + 6 sigma of the classes of one part, 1.5 slots per class, a multiple of 256
@@ -615,7 +699,8 @@ static int merge_buckets(Call &call, const Buckets &b, u64 *meta, size_t expecte
     const unsigned insert_grid = b.blocks < (unsigned)c->sms * 8 ? b.blocks : (unsigned)c->sms * 8;
     for (int part = 0; part < b.parts; ++part) {
         k_part_insert<<<insert_grid, kBlock, 0, s>>>(b, part, table, meta, (int *)(meta + 3), max_unique);
-        k_part_drain<<<grid_for(b.part_slots, kBlock, c->sms, 8), kBlock, 0, s>>>(table, b.part_slots, keys, mults, meta + 2, (u64)padded);
+        k_part_drain<<<grid_for((b.part_slots + kDrainItems - 1) / kDrainItems, kBlock, c->sms, 8), kBlock, 0, s>>>(table, b.part_slots, keys, mults,
+                                                                                                                  meta + 2, (u64)padded);
     }
     QK_CUDA(cudaGetLastError());
     u64 h_meta[4];
@@ -652,7 +737,7 @@ int run_dedup(Call &call, const uint4 *states, const uint64_t *mult, size_t n, i
     const long long mode = option(OPT_DEDUP_MODE);
     Buckets b;
     size_t per_block = 0;
-    if (mode != 1 && (mode == 2 || (expected + expected / 2) * sizeof(TSlot) > 2 * kL2TableBytes) &&
+    if (mode != 1 && (mode == 2 || (expected + expected / 2) * sizeof(TSlot) > 2 * l2_table_bytes()) &&
         plan_two_level(n, expected, c->sms, b, per_block)) {
         int rc = alloc_buckets(call, b, mult != nullptr);
         if (rc != QK_OK) return rc;

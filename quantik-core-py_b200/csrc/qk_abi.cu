@@ -518,10 +518,11 @@ int qk_playouts_guided(const uint16_t *roots, size_t n_roots, uint32_t rollouts_
     uint32_t *d_dr = (uint32_t *)call.out(draws, n_roots * 4, true);
     int8_t *d_pp = (int8_t *)call.out(per_playout, total);
     uint8_t *d_pl = (uint8_t *)call.out(per_plies, total);
+    void *d_lines = call.temp(guided_scratch_bytes(n_roots));
     QK_CHECK(call);
     if (rollouts_per_root == 0) return call.finish();
     int rc = launch_playouts_guided(d_roots, n_roots, rollouts_per_root, seed, first_rollout, root_index_base, max_plies, epsilon,
-                                    weights, d_w0, d_w1, d_dr, d_pp, d_pl, call.ctx(), call.stream());
+                                    weights, d_w0, d_w1, d_dr, d_pp, d_pl, d_lines, call.ctx(), call.stream());
     if (rc != QK_OK) return rc;
     return call.finish();
 }

@@ -103,9 +103,11 @@ int run_bfs_level_scatter(Call &call, const uint4 *parents, const uint64_t *mult
 int run_inbox_merge(Call &call, const void *my_inbox, int world, size_t slots_per_src, int sort_output,
                     uint16_t *uniq, uint64_t *uniq_mult, size_t cap, size_t *n_uniq);
 int launch_eval_features(const uint4 *states, const uint8_t *player, size_t n, double *features, Ctx *c, cudaStream_t s);
+size_t guided_scratch_bytes(size_t n_roots);
 int launch_playouts_guided(const uint4 *roots, size_t n_roots, uint32_t rollouts, uint64_t seed, uint64_t first_rollout,
                            uint32_t root_index_base, int max_plies, double epsilon, const double *weights, uint32_t *wins_p0,
-                           uint32_t *wins_p1, uint32_t *draws, int8_t *per_playout, uint8_t *per_plies, Ctx *c, cudaStream_t s);
+                           uint32_t *wins_p1, uint32_t *draws, int8_t *per_playout, uint8_t *per_plies, void *line_scratch, Ctx *c,
+                           cudaStream_t s);
 int launch_solve(const uint4 *states, size_t n, unsigned long long *counter, int8_t *outcome, uint8_t *plies, uint8_t *best_action,
                  Ctx *c, cudaStream_t s);
 int run_issue_peak(Ctx *c, double *alu, double *mixed);

@@ -134,54 +134,104 @@ QK_HD double eval_score(const State4 &s, int player, const double w[6])
     return eval_dot(f, w);
 }
 
+// The greedy move of a position (the non-exploring branch of _select_rollout_move, mcts.py:362-383): the first
+// decisive child, else the first child with the best evaluation.  -> action; cur must have a legal move.
+QK_HD int guided_greedy_action(const State4 &cur, const EvalPos &ev, int player, uint64_t mask, const double w[6])
+{
+    int action = -1;
+    double best = 0.0;
+    for (uint64_t m = mask; m; m &= m - 1) {
+        int a = 0;
+        const uint32_t mlo = (uint32_t)m;
+#ifdef __CUDA_ARCH__
+        a = mlo ? __ffs((int)mlo) - 1 : 32 + __ffs((int)(uint32_t)(m >> 32)) - 1;
+#else
+        a = mlo ? __builtin_ctz(mlo) : 32 + __builtin_ctz((uint32_t)(m >> 32));
+#endif
+        const State4 child = apply_action(cur, player, a);
+        EvalPos ce = ev;
+        eval_pos_place(ce, a >> 4, a & 15);
+        uint32_t clo, chi;
+        legal_masks(child, 1 - player, clo, chi);
+        // decisive move: a line with four shapes, or the opponent cannot answer -- take it
+        if ((ce.np & (kLineLsb << 2)) != 0 || (clo | chi) == 0) return a;
+        int f[6];
+        eval_features_pos(child, ce, player, 1 - player, popc(clo) + popc(chi), f);
+        const double sc = eval_dot(f, w);
+        if (action < 0 || sc > best) { best = sc; action = a; }                              // first maximum wins
+    }
+    return action;
+}
+
+// The greedy line of a root: what a playout does as long as it never explores.  Every playout of the root follows
+// it up to its first exploring ply, so its moves are worked out ONCE per root (k_guided_lines) instead of once per
+// playout -- from the empty board that is the 64-child scan of ply 0 for every playout, the 49-child scan of ply 1
+// for 80 % of them, ...  len = greedy moves until the game ends; result = who wins there (+1 P0 / -1 P1).
+struct __attribute__((aligned(32))) GuidedLine { uint8_t action[16]; uint8_t len; int8_t result; uint8_t player; uint8_t pad[13]; };
+
+QK_HD GuidedLine guided_line(const State4 &root, const double w[6])
+{
+    GuidedLine g;
+    for (int i = 0; i < 16; ++i) g.action[i] = 0;
+    g.len = 0; g.result = 0; g.player = 0;
+    State4 cur = root;
+    EvalPos ev = eval_pos(root);
+    for (int ply = 0;; ++ply) {
+        const int ws = win_status(cur);
+        if (ws) { g.result = (int8_t)(ws == 1 ? 1 : -1); break; }
+        int player, status;
+        const uint64_t mask = movegen(cur, &player, &status);
+        if (ply == 0) g.player = (uint8_t)player;
+        if (mask == 0) { g.result = (int8_t)(player == 0 ? -1 : 1); break; }
+        const int a = guided_greedy_action(cur, ev, player, mask, w);
+        g.action[ply] = (uint8_t)a;
+        g.len = (uint8_t)(ply + 1);
+        cur = apply_action(cur, player, a);
+        eval_pos_place(ev, a >> 4, a & 15);
+    }
+    return g;
+}
+
 // One eval-guided playout (mcts.py:385-437 with _select_rollout_move :345-383).  Stream contract: ply p
 // uses Philox block (rollout lo, rollout hi, 0x80000000 | p/2, root index); word 2*(p%2) is the epsilon
 // draw (explore iff epsilon > 0 and word * 2^-32 < epsilon), word 2*(p%2)+1 the uniform pick.
 QK_HD int guided_playout_one(const State4 &root, uint64_t seed, uint64_t rollout, uint32_t root_index, int max_plies,
-                             double epsilon, const double w[6], int *plies_out)
+                             double epsilon, const double w[6], int *plies_out, const GuidedLine *line = nullptr)
 {
     State4 cur = root;
     EvalPos ev = eval_pos(root);          // carried along: one table word per move instead of a rescan of the board
     int ply = 0, result;
+    bool on_line = line != nullptr;       // no exploring ply so far: the position is the line's
     Philox4 rnd = { { 0, 0, 0, 0 } };
     for (;;) {
         if (max_plies >= 0 && ply >= max_plies) { result = 0; break; }
-        const int ws = win_status(cur);
-        if (ws) { result = ws == 1 ? 1 : -1; break; }
-        int player, status;
-        const uint64_t mask = movegen(cur, &player, &status);
-        if (mask == 0) { result = player == 0 ? -1 : 1; break; }
+        int player = 0;
+        uint64_t mask = 0;
+        if (on_line) {
+            if (ply == (int)line->len) { result = line->result; break; }        // the line's own end: a win or a blocked mover
+            player = (line->player + ply) & 1;
+        } else {
+            const int ws = win_status(cur);
+            if (ws) { result = ws == 1 ? 1 : -1; break; }
+            int status;
+            mask = movegen(cur, &player, &status);
+            if (mask == 0) { result = player == 0 ? -1 : 1; break; }
+        }
         if ((ply & 1) == 0)
             rnd = philox4x32_10((uint32_t)rollout, (uint32_t)(rollout >> 32), 0x80000000u | (uint32_t)(ply >> 1), root_index,
                                 (uint32_t)seed, (uint32_t)(seed >> 32));
         const uint32_t r_eps = (ply & 1) ? rnd.v[2] : rnd.v[0], r_pick = (ply & 1) ? rnd.v[3] : rnd.v[1];
-        const uint32_t lo = (uint32_t)mask, hi = (uint32_t)(mask >> 32);
         int action = -1;
         if (epsilon > 0.0 && (double)r_eps * (1.0 / 4294967296.0) < epsilon) {
+            if (on_line) { int status; mask = movegen(cur, &player, &status); }
+            const uint32_t lo = (uint32_t)mask, hi = (uint32_t)(mask >> 32);
             const int n = popc(lo) + popc(hi);
             action = select_bit64(lo, hi, popc(lo), (int)mulhi(r_pick, (uint32_t)n));
+            on_line = on_line && action == (int)line->action[ply];              // an exploring ply may still pick the line's move
+        } else if (on_line) {
+            action = line->action[ply];
         } else {
-            double best = 0.0;
-            for (uint64_t m = mask; m; m &= m - 1) {
-                int a = 0;
-                const uint32_t mlo = (uint32_t)m;
-#ifdef __CUDA_ARCH__
-                a = mlo ? __ffs((int)mlo) - 1 : 32 + __ffs((int)(uint32_t)(m >> 32)) - 1;
-#else
-                a = mlo ? __builtin_ctz(mlo) : 32 + __builtin_ctz((uint32_t)(m >> 32));
-#endif
-                const State4 child = apply_action(cur, player, a);
-                EvalPos ce = ev;
-                eval_pos_place(ce, a >> 4, a & 15);
-                uint32_t clo, chi;
-                legal_masks(child, 1 - player, clo, chi);
-                // decisive move: a line with four shapes, or the opponent cannot answer -- take it
-                if ((ce.np & (kLineLsb << 2)) != 0 || (clo | chi) == 0) { action = a; break; }
-                int f[6];
-                eval_features_pos(child, ce, player, 1 - player, popc(clo) + popc(chi), f);
-                const double sc = eval_dot(f, w);
-                if (action < 0 || sc > best) { best = sc; action = a; }                      // first maximum wins
-            }
+            action = guided_greedy_action(cur, ev, player, mask, w);
         }
         cur = apply_action(cur, player, action);
         eval_pos_place(ev, action >> 4, action & 15);

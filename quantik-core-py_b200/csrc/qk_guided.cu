@@ -25,9 +25,21 @@ __global__ void __launch_bounds__(kBlock) k_eval_features(const uint4 *__restric
     }
 }
 
+// the greedy line of every root (qk_eval_core.cuh: GuidedLine), one thread per root
+__global__ void __launch_bounds__(kBlock) k_guided_lines(const uint4 *__restrict__ roots, uint64_t n_roots, const EvalWeights weights,
+                                                          GuidedLine *__restrict__ lines)
+{
+    const uint64_t i = blockIdx.x * (uint64_t)kBlock + threadIdx.x;
+    if (i >= n_roots) return;
+    const uint4 v = __ldg(roots + i);
+    const State4 s = { v.x, v.y, v.z, v.w };
+    lines[i] = guided_line(s, weights.w);
+}
+
 __global__ void __launch_bounds__(kBlock) k_playout_guided(const uint4 *__restrict__ roots, uint64_t n_roots, uint32_t rollouts,
                                                             uint64_t seed, uint64_t first_rollout, uint32_t root_index_base,
                                                             int max_plies, double epsilon, const EvalWeights weights,
+                                                            const GuidedLine *__restrict__ lines,
                                                             uint32_t *wins_p0, uint32_t *wins_p1, uint32_t *draws,
                                                             int8_t *per_playout, uint8_t *per_plies)
 {
@@ -37,7 +49,8 @@ __global__ void __launch_bounds__(kBlock) k_playout_guided(const uint4 *__restri
         const uint4 v = __ldg(roots + root);
         const State4 s = { v.x, v.y, v.z, v.w };
         int plies;
-        const int res = guided_playout_one(s, seed, first_rollout + j, root_index_base + root, max_plies, epsilon, weights.w, &plies);
+        const int res = guided_playout_one(s, seed, first_rollout + j, root_index_base + root, max_plies, epsilon, weights.w, &plies,
+                                           lines ? lines + root : nullptr);
         // tallies: the lanes of the warp that played for the same root (consecutive ids: almost always all of them)
         // are summed first, one lane per root issues the atomics
         const unsigned peers = __match_any_sync(__activemask(), root);
@@ -60,15 +73,25 @@ int launch_eval_features(const uint4 *states, const uint8_t *player, size_t n, d
     return QK_OK;
 }
 
+size_t guided_scratch_bytes(size_t n_roots) { return n_roots * sizeof(GuidedLine); }
+
 int launch_playouts_guided(const uint4 *roots, size_t n_roots, uint32_t rollouts, uint64_t seed, uint64_t first_rollout,
                            uint32_t root_index_base, int max_plies, double epsilon, const double *weights, uint32_t *wins_p0,
-                           uint32_t *wins_p1, uint32_t *draws, int8_t *per_playout, uint8_t *per_plies, Ctx *c, cudaStream_t s)
+                           uint32_t *wins_p1, uint32_t *draws, int8_t *per_playout, uint8_t *per_plies, void *line_scratch, Ctx *c,
+                           cudaStream_t s)
 {
     EvalWeights w;
     for (int i = 0; i < 6; ++i) w.w[i] = weights[i];
     const size_t total = n_roots * (size_t)rollouts;
+    // the greedy line pays off as soon as a root is played a few times (it costs about one non-exploring playout);
+    // with epsilon = 1 no playout ever follows it
+    GuidedLine *lines = (line_scratch && rollouts >= 4 && epsilon < 1.0) ? (GuidedLine *)line_scratch : nullptr;
+    if (lines) {
+        k_guided_lines<<<(unsigned)((n_roots + kBlock - 1) / kBlock), kBlock, 0, s>>>(roots, n_roots, w, lines);
+        QK_CUDA(cudaGetLastError());
+    }
     k_playout_guided<<<grid_for(total, kBlock, c->sms, 16), kBlock, 0, s>>>(roots, n_roots, rollouts, seed, first_rollout,
-                                                                            root_index_base, max_plies, epsilon, w, wins_p0,
+                                                                            root_index_base, max_plies, epsilon, w, lines, wins_p0,
                                                                             wins_p1, draws, per_playout, per_plies);
     QK_CUDA(cudaGetLastError());
     return QK_OK;

@@ -65,12 +65,18 @@ void hs_features(const uint16_t *s, const uint8_t *pl, size_t n, double *out)
 void hs_guided(const uint16_t *roots, size_t n_roots, uint32_t rollouts, uint64_t seed, uint64_t first, uint32_t root_base,
                int max_plies, double eps, const double *w, int8_t *outcome, uint8_t *plies)
 {
-    for (size_t r = 0; r < n_roots; ++r)
+    // same policy as launch_playouts_guided: the root's greedy line is worked out once and followed until the first exploring ply
+    for (size_t r = 0; r < n_roots; ++r) {
+        const bool use_line = rollouts >= 4 && eps < 1.0;
+        GuidedLine line;
+        if (use_line) line = guided_line(ld(roots + 8 * r), w);
         for (uint32_t j = 0; j < rollouts; ++j) {
             int pl;
-            outcome[r * rollouts + j] = (int8_t)guided_playout_one(ld(roots + 8 * r), seed, first + j, root_base + (uint32_t)r, max_plies, eps, w, &pl);
+            outcome[r * rollouts + j] = (int8_t)guided_playout_one(ld(roots + 8 * r), seed, first + j, root_base + (uint32_t)r, max_plies, eps, w, &pl,
+                                                                   use_line ? &line : nullptr);
             plies[r * rollouts + j] = (uint8_t)pl;
         }
+    }
 }
 int hs_select(uint32_t lo, uint32_t hi, int k) { return select_bit64(lo, hi, popc(lo), k); }
 #ifdef QK_HOSTSIM_PLAYOUT

@@ -150,12 +150,12 @@ def test_eval_features_and_guided_policy(hs):
         assert np.array_equal(out, O.features(big, np.full(len(big), pl, np.uint8)))
     roots = np.ascontiguousarray(O.make_roots(24, seed=5, min_plies=2, span=9))
     w = np.ascontiguousarray(g["fitted_weights"])
-    for eps, mp in ((0.2, -1), (0.0, -1), (0.5, 4)):
-        oc, pl = np.zeros((24, 40), np.int8), np.zeros((24, 40), np.uint8)
-        hs.hs_guided(P(roots), ctypes.c_size_t(24), ctypes.c_uint32(40), ctypes.c_uint64(seed), ctypes.c_uint64(7), ctypes.c_uint32(0),
+    for eps, mp, nr in ((0.2, -1, 40), (0.0, -1, 40), (0.5, 4, 40), (0.3, -1, 3), (1.0, -1, 40)):      # 3 rollouts: no greedy line
+        oc, pl = np.zeros((24, nr), np.int8), np.zeros((24, nr), np.uint8)
+        hs.hs_guided(P(roots), ctypes.c_size_t(24), ctypes.c_uint32(nr), ctypes.c_uint64(seed), ctypes.c_uint64(7), ctypes.c_uint32(0),
                      ctypes.c_int(mp), ctypes.c_double(eps), P(w), P(oc), P(pl))
-        o = O.guided_playouts(roots, 40, seed, eps, w, 7, 0, mp, True)
-        assert np.array_equal(oc, o["outcome"]) and np.array_equal(pl, o["plies"]), (eps, mp)
+        o = O.guided_playouts(roots, nr, seed, eps, w, 7, 0, mp, True)
+        assert np.array_equal(oc, o["outcome"]) and np.array_equal(pl, o["plies"]), (eps, mp, nr)
 
 
 def test_fuzz_random_boards_vs_oracle(hs):

@@ -113,6 +113,23 @@ QK_HD void eval_features(const State4 &s, int player, int f[6])
     eval_features_pos(s, eval_pos(s), player, side_to_move, popc(lo) + popc(hi), f);
 }
 
+// the same sum with the six products looked up: tab[i * kEvalTabStride + 64 + v] = w[i] * v for |v| <= 64 (every
+// feature is a count of lines or moves), computed once per kernel with the same rounding.  Saves the six
+// int -> float64 conversions and multiplications per position, the slowest instructions of the evaluation.
+static constexpr int kEvalTabStride = 132;
+QK_HD double eval_dot_tab(const int f[6], const double *tab)
+{
+    double acc = 0.0;
+    for (int i = 0; i < 6; ++i) {
+#ifdef __CUDA_ARCH__
+        acc = __dadd_rn(acc, tab[i * kEvalTabStride + 64 + f[i]]);
+#else
+        acc += tab[i * kEvalTabStride + 64 + f[i]];
+#endif
+    }
+    return acc;
+}
+
 QK_HD double eval_dot(const int f[6], const double w[6])
 {
     double acc = 0.0;
@@ -136,10 +153,24 @@ QK_HD double eval_score(const State4 &s, int player, const double w[6])
 
 // The greedy move of a position (the non-exploring branch of _select_rollout_move, mcts.py:362-383): the first
 // decisive child, else the first child with the best evaluation.  -> action; cur must have a legal move.
-QK_HD int guided_greedy_action(const State4 &cur, const EvalPos &ev, int player, uint64_t mask, const double w[6])
+// what the player NOT to move could play on `cur` -- the starting point of every child's reply count: after the
+// mover puts shape s on square p the opponent loses p for every shape and the scope of p for shape s, nothing else
+// (the opponent's own pieces, hence its exhausted shapes, are unchanged).
+QK_HD void child_reply_masks(uint32_t opp_lo, uint32_t opp_hi, int action, uint32_t &clo, uint32_t &chi)
+{
+    const int p = action & 15, s = action >> 4;
+    const uint32_t bit2 = 0x00010001u << p, closed = scope_of_square(p) << ((s & 1) << 4);
+    clo = opp_lo & ~bit2 & ~(s < 2 ? closed : 0u);
+    chi = opp_hi & ~bit2 & ~(s < 2 ? 0u : closed);
+}
+
+QK_HD int guided_greedy_action(const State4 &cur, const EvalPos &ev, int player, uint64_t mask, const double w[6],
+                               const double *tab = nullptr)
 {
     int action = -1;
     double best = 0.0;
+    uint32_t opp_lo, opp_hi;
+    legal_masks(cur, 1 - player, opp_lo, opp_hi);
     for (uint64_t m = mask; m; m &= m - 1) {
         int a = 0;
         const uint32_t mlo = (uint32_t)m;
@@ -148,16 +179,15 @@ QK_HD int guided_greedy_action(const State4 &cur, const EvalPos &ev, int player,
 #else
         a = mlo ? __builtin_ctz(mlo) : 32 + __builtin_ctz((uint32_t)(m >> 32));
 #endif
-        const State4 child = apply_action(cur, player, a);
         EvalPos ce = ev;
         eval_pos_place(ce, a >> 4, a & 15);
         uint32_t clo, chi;
-        legal_masks(child, 1 - player, clo, chi);
+        child_reply_masks(opp_lo, opp_hi, a, clo, chi);
         // decisive move: a line with four shapes, or the opponent cannot answer -- take it
         if ((ce.np & (kLineLsb << 2)) != 0 || (clo | chi) == 0) return a;
         int f[6];
-        eval_features_pos(child, ce, player, 1 - player, popc(clo) + popc(chi), f);
-        const double sc = eval_dot(f, w);
+        eval_features_pos(apply_action(cur, player, a), ce, player, 1 - player, popc(clo) + popc(chi), f);
+        const double sc = tab ? eval_dot_tab(f, tab) : eval_dot(f, w);
         if (action < 0 || sc > best) { best = sc; action = a; }                              // first maximum wins
     }
     return action;

@@ -36,6 +36,66 @@ __global__ void __launch_bounds__(kBlock) k_guided_lines(const uint4 *__restrict
     lines[i] = guided_line(s, weights.w);
 }
 
+// ---- the playout kernel: 32 playouts per warp, one ply per iteration for all of them.
+// A lane whose playout is still on its root's greedy line takes the line's move; a lane that needs a greedy move of
+// its own has to score every child of its position.  When only a few lanes of the warp are in that situation -- the
+// first plies, where positions have 40-64 children and most playouts are still on the line -- the warp scores THEIR
+// children together, one child per lane (a lane-serial scan would keep 32 lanes waiting for the few); when most lanes
+// need one, every lane scans its own children.  Same moves either way (first decisive child, else first maximum).
+static constexpr unsigned kFull = 0xFFFFFFFFu;
+__device__ __forceinline__ uint64_t sortable(double d)      // order-preserving map double -> u64 (no NaNs, no -0.0 here)
+{
+    const long long bits = __double_as_longlong(d);
+    return (uint64_t)(bits ^ ((bits >> 63) | (long long)0x8000000000000000ull));
+}
+__device__ __forceinline__ uint64_t shfl64(uint64_t v, int src)
+{
+    return ((uint64_t)__shfl_sync(kFull, (uint32_t)(v >> 32), src) << 32) | __shfl_sync(kFull, (uint32_t)v, src);
+}
+
+// the greedy move of lane `src`'s position, worked out by the whole warp; every lane returns it
+__device__ __forceinline__ int warp_greedy_action(int src, const State4 &cur, const EvalPos &ev, int player, uint64_t mask, const double *tab)
+{
+    const unsigned lane = threadIdx.x & 31u;
+    State4 c;
+    c.x = __shfl_sync(kFull, cur.x, src); c.y = __shfl_sync(kFull, cur.y, src);
+    c.z = __shfl_sync(kFull, cur.z, src); c.w = __shfl_sync(kFull, cur.w, src);
+    EvalPos e;
+    e.occ = shfl64(ev.occ, src); e.np = shfl64(ev.np, src); e.pres = shfl64(ev.pres, src);
+    const int pl = __shfl_sync(kFull, player, src);
+    const uint64_t mk = shfl64(mask, src);
+    const uint32_t lo = (uint32_t)mk, hi = (uint32_t)(mk >> 32);
+    const int nlo = __popc(lo), n = nlo + __popc(hi);
+    uint32_t opp_lo, opp_hi;
+    legal_masks(c, 1 - pl, opp_lo, opp_hi);
+    uint64_t best_key = 0;
+    int best_a = -1;
+    for (int k0 = 0; k0 < n; k0 += 32) {
+        const int k = k0 + (int)lane;
+        const bool have = k < n;
+        const int a = select_bit64(lo, hi, nlo, have ? k : 0);
+        EvalPos ce = e;
+        eval_pos_place(ce, a >> 4, a & 15);
+        uint32_t clo, chi;
+        child_reply_masks(opp_lo, opp_hi, a, clo, chi);
+        const bool decisive = have && ((ce.np & (kLineLsb << 2)) != 0 || (clo | chi) == 0);
+        const unsigned dmask = __ballot_sync(kFull, decisive);
+        if (dmask) return __shfl_sync(kFull, a, __ffs((int)dmask) - 1);      // children are in ascending order: the first one
+        int f[6];
+        eval_features_pos(apply_action(c, pl, a), ce, pl, 1 - pl, __popc(clo) + __popc(chi), f);
+        const uint64_t key = sortable(eval_dot_tab(f, tab));
+        // first maximum of the round: highest key, lowest lane among equals
+        const uint32_t kh = have ? (uint32_t)(key >> 32) : 0u, mh = __reduce_max_sync(kFull, kh);
+        const bool cand = have && kh == mh;
+        const uint32_t kl = cand ? (uint32_t)key : 0u, ml = __reduce_max_sync(kFull, kl);
+        const int wl = __ffs((int)__ballot_sync(kFull, cand && kl == ml)) - 1;
+        const uint64_t round_key = ((uint64_t)mh << 32) | ml;
+        const int round_a = __shfl_sync(kFull, a, wl);
+        if (best_a < 0 || round_key > best_key) { best_key = round_key; best_a = round_a; }
+    }
+    return best_a;
+}
+
 __global__ void __launch_bounds__(kBlock) k_playout_guided(const uint4 *__restrict__ roots, uint64_t n_roots, uint32_t rollouts,
                                                             uint64_t seed, uint64_t first_rollout, uint32_t root_index_base,
                                                             int max_plies, double epsilon, const EvalWeights weights,
@@ -43,26 +103,98 @@ __global__ void __launch_bounds__(kBlock) k_playout_guided(const uint4 *__restri
                                                             uint32_t *wins_p0, uint32_t *wins_p1, uint32_t *draws,
                                                             int8_t *per_playout, uint8_t *per_plies)
 {
+    __shared__ double s_tab[6 * kEvalTabStride];
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+        for (int v = threadIdx.x; v < kEvalTabStride; v += kBlock) s_tab[i * kEvalTabStride + v] = __dmul_rn(weights.w[i], (double)(v - 64));
+    __syncthreads();
     const uint64_t total = n_roots * rollouts;
-    for (uint64_t id = blockIdx.x * (uint64_t)kBlock + threadIdx.x; id < total; id += (uint64_t)gridDim.x * kBlock) {
-        const uint32_t root = (uint32_t)(id / rollouts), j = (uint32_t)(id % rollouts);
+    const unsigned lane = threadIdx.x & 31u;
+    const uint64_t warp0 = (blockIdx.x * (uint64_t)kBlock + threadIdx.x) >> 5, n_warps = ((uint64_t)gridDim.x * kBlock) >> 5;
+    for (uint64_t base = warp0 * 32; base < total; base += n_warps * 32) {
+        const uint64_t id = base + lane;
+        bool done = id >= total;
+        const uint32_t root = done ? 0u : (uint32_t)(id / rollouts), j = done ? 0u : (uint32_t)(id % rollouts);
         const uint4 v = __ldg(roots + root);
-        const State4 s = { v.x, v.y, v.z, v.w };
-        int plies;
-        const int res = guided_playout_one(s, seed, first_rollout + j, root_index_base + root, max_plies, epsilon, weights.w, &plies,
-                                           lines ? lines + root : nullptr);
+        State4 cur = { v.x, v.y, v.z, v.w };
+        EvalPos ev = eval_pos(cur);
+        const GuidedLine *line = lines ? lines + root : nullptr;
+        bool on_line = line != nullptr;
+        const uint64_t rollout = first_rollout + j;
+        int result = 0, plies = 0;
+        Philox4 rnd = { { 0, 0, 0, 0 } };
+        for (int ply = 0;; ++ply) {
+            // ---- is the game over?  (mcts.py:412 cut-off, :414-419 winner, :427-429 blocked mover)
+            int player = 0;
+            uint64_t mask = 0;
+            if (!done) {
+                if (max_plies >= 0 && ply >= max_plies) { result = 0; done = true; }
+                else if (on_line) {
+                    if (ply == (int)line->len) { result = line->result; done = true; }
+                    else player = (line->player + ply) & 1;
+                } else {
+                    const int ws = win_status(cur);
+                    if (ws) { result = ws == 1 ? 1 : -1; done = true; }
+                    else {
+                        int status;
+                        mask = movegen(cur, &player, &status);
+                        if (mask == 0) { result = player == 0 ? -1 : 1; done = true; }
+                    }
+                }
+                if (done) plies = ply;
+            }
+            if (!__any_sync(kFull, !done)) break;
+            if ((ply & 1) == 0)
+                rnd = philox4x32_10((uint32_t)rollout, (uint32_t)(rollout >> 32), 0x80000000u | (uint32_t)(ply >> 1), root_index_base + root,
+                                    (uint32_t)seed, (uint32_t)(seed >> 32));
+            // ---- the move: exploring pick, the line's move, or a greedy move of its own
+            int action = 0;
+            bool need = false;
+            if (!done) {
+                const uint32_t r_eps = (ply & 1) ? rnd.v[2] : rnd.v[0], r_pick = (ply & 1) ? rnd.v[3] : rnd.v[1];
+                if (epsilon > 0.0 && (double)r_eps * (1.0 / 4294967296.0) < epsilon) {
+                    if (on_line) { int status; mask = movegen(cur, &player, &status); }
+                    const uint32_t lo = (uint32_t)mask, hi = (uint32_t)(mask >> 32);
+                    action = select_bit64(lo, hi, __popc(lo), (int)__umulhi(r_pick, (uint32_t)(__popc(lo) + __popc(hi))));
+                    on_line = on_line && action == (int)line->action[ply];
+                } else if (on_line) action = line->action[ply];
+                else need = true;
+            }
+            unsigned need_mask = __ballot_sync(kFull, need);
+            if (need_mask) {
+                const int n_mine = need ? __popc((uint32_t)mask) + __popc((uint32_t)(mask >> 32)) : 0;
+                const int n_max = __reduce_max_sync(kFull, n_mine);
+                // together: one round of ~160 instructions per 32 children of every lane in need; each on its own: the
+                // longest scan, ~115 instructions per child
+                if (__popc(need_mask) * ((n_max + 31) / 32) * 160 < n_max * 115) {
+                    for (; need_mask; need_mask &= need_mask - 1) {
+                        const int src = __ffs((int)need_mask) - 1;
+                        const int a = warp_greedy_action(src, cur, ev, player, mask, s_tab);
+                        if ((int)lane == src) action = a;
+                    }
+                } else if (need) action = guided_greedy_action(cur, ev, player, mask, weights.w, s_tab);
+            }
+            if (!done) {
+                cur = apply_action(cur, player, action);
+                eval_pos_place(ev, action >> 4, action & 15);
+            }
+        }
         // tallies: the lanes of the warp that played for the same root (consecutive ids: almost always all of them)
         // are summed first, one lane per root issues the atomics
-        const unsigned peers = __match_any_sync(__activemask(), root);
-        const unsigned p0 = __ballot_sync(peers, res > 0), p1 = __ballot_sync(peers, res < 0);
-        if ((unsigned)(__ffs((int)peers) - 1) == (threadIdx.x & 31u)) {
-            const uint32_t n0 = (uint32_t)__popc(p0 & peers), n1 = (uint32_t)__popc(p1 & peers), nd = (uint32_t)__popc(peers) - n0 - n1;
-            if (wins_p0 && n0) atomicAdd(wins_p0 + root, n0);
-            if (wins_p1 && n1) atomicAdd(wins_p1 + root, n1);
-            if (draws && nd) atomicAdd(draws + root, nd);
+        const bool valid = id < total;
+        const unsigned active = __ballot_sync(kFull, valid);
+        if (valid) {
+            const unsigned peers = __match_any_sync(active, root);
+            const unsigned p0 = __ballot_sync(active, result > 0) & peers, p1 = __ballot_sync(active, result < 0) & peers;
+            if ((unsigned)(__ffs((int)peers) - 1) == lane) {
+                const uint32_t n0 = (uint32_t)__popc(p0), n1 = (uint32_t)__popc(p1), nd = (uint32_t)__popc(peers) - n0 - n1;
+                if (wins_p0 && n0) atomicAdd(wins_p0 + root, n0);
+                if (wins_p1 && n1) atomicAdd(wins_p1 + root, n1);
+                if (draws && nd) atomicAdd(draws + root, nd);
+            }
+            if (per_playout) per_playout[id] = (int8_t)result;
+            if (per_plies) per_plies[id] = (uint8_t)plies;
         }
-        if (per_playout) per_playout[id] = (int8_t)res;
-        if (per_plies) per_plies[id] = (uint8_t)plies;
     }
 }
 

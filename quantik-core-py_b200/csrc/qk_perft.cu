@@ -776,7 +776,11 @@ int run_perft(Call &call, const uint4 *roots, const uint64_t *mult, size_t n_roo
     // (r02c_experiments.json: the tile kernel is at its best with 4 plies below the items -- the share of one of 8
     // ranks, 1.2 M items: 23.6 ms started there vs 25.9 ms one level later -- unless the items are about as few as
     // the lanes: perft(7) from 167 K items 28.4 ms vs 25.0 ms from 6.7 M.  4 items per lane separates the cases.)
-    u64 want_lane_items = (u64)c->sms * 1024 * 4;
+    //  Deep remainders are the opposite case: subtrees 10 plies deep differ in size by orders of magnitude, and only many
+    //  items per lane even that out -- config 5 at full depth on 8 GPUs: 22.2 s started from 1.2 M items per rank, 16 s
+    //  from 50 M -- so the low threshold applies to remainders of at most 4 plies.)
+    const u64 want_lane_items_shallow = (u64)c->sms * 1024 * 4, want_lane_items_deep = (u64)c->sms * 2048 * 8;
+    u64 want_lane_items = 0;
     const int force = (int)option(OPT_PERFT_KERNEL);                    // 1 tile / 2 lane / 3 warp: benchmarking aid
     if (const long long mi = option(OPT_PERFT_MIN_ITEMS))               // testing aid: depth-first kernels on small frontiers
         want_warp_items = want_lane_items = (u64)mi;
@@ -793,7 +797,7 @@ int run_perft(Call &call, const uint4 *roots, const uint64_t *mult, size_t n_roo
         // As soon as every lane can have an item: the lane walk with the dealt last level (k_perft_tile) while the
         // target lies in the wide part of the game, the plain lane walk for the narrow end (measured below the
         // 10 946 depth-4 classes, tile / lane: to depth 12 11.7 / 15.6 s, to depth 14 108 / 91 s, to depth 16 147 / 128 s)
-        bool go = n_cur >= want_lane_items;
+        bool go = n_cur >= (want_lane_items ? want_lane_items : (rem <= 4 ? want_lane_items_shallow : want_lane_items_deep));
         u64 n_next = 0;
         if (!go) {
             // sizing pass: how many children this level emits (the frontier is allocated exactly; a level that

@@ -18,7 +18,7 @@ depth = int(sys.argv[2]) if len(sys.argv) > 2 else 6
 d4 = np.load(os.path.join(ROOT, "tests", "golden", "depth4_canonical.npz"))
 idx = D.partition_by_cost(Q.perft_probe(d4["states"]), world)[0]
 s, m = np.ascontiguousarray(d4["states"][idx]), np.ascontiguousarray(d4["mult"][idx])
-for i in range(3):
+for i in range(int(sys.argv[3]) if len(sys.argv) > 3 else 3):
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     Q.perft(s, depth, m)

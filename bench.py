@@ -439,6 +439,14 @@ def main():
         "ncu": ncu,
     }
 
+    # useful ply-slots / executed ply-slots of the playout kernel: a finished lane waits for the next 4-ply boundary
+    # (measured on 2^20 playouts of the same stream; the ~0.14 blocked-mover steps per game, which also take a slot,
+    # are not visible in the per-playout length and are left out)
+    sample = B.playouts(np.zeros((1, 8), np.uint16), 1 << 20, SEED, per_playout=True, device=dev)
+    lens = np.asarray(sample["plies"], np.int64).ravel()
+    roofline["slot_efficiency"] = float(lens.sum()) / float((4 * ((lens + 3) // 4)).sum())
+    roofline["mean_plies_measured"] = float(lens.mean())
+
     extra = dict(sharded)
     if not args.no_extra:
         # config 2: exhaustive perft from the empty board to depth 6 (bit-exact counts asserted)

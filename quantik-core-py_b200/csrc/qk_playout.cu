@@ -35,6 +35,7 @@ struct PlayoutArgs {
     uint32_t *wins_p0, *wins_p1, *draws;
     int8_t *per_playout;
     uint8_t *per_plies;
+    uint32_t one, zero;      // 1 and 0 the compiler cannot see (k_playout_pred: keeps small additions on the FMA pipe)
 };
 
 __global__ void __launch_bounds__(kBlock) k_prepare_roots(const uint4 *__restrict__ states, size_t n, RootRec *__restrict__ out)
@@ -248,6 +249,83 @@ __global__ void QK_PLAYOUT_BOUNDS k_playout_single(const PlayoutArgs a)
     flush_tallies(a, 0u, acc_n, acc_p0, 0u);
 }
 
+// Config 1 again, third version: the ply is ply_pred (predicated PTX, qk_playout_core.cuh) and the loop around it has
+// no branch but the exit test -- the refill is three predicated LDS.128 of the root record, the game in flight is
+// the all-ones / zero word `act`, and the tallies are one counter (games won by the root's mover; the number of
+// games a thread plays is known in advance).
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <int MIN_CTAS>
+__global__ void __launch_bounds__(kBlock, MIN_CTAS) k_playout_pred(const PlayoutArgs a)
+{
+    __shared__ __align__(128) uint32_t s_lut[QK_MOVE_LUT_BYTES / 4];
+    __shared__ __align__(16) uint16_t s_sel16[2048];
+    __shared__ __align__(16) uint4 s_root[3];
+    if (threadIdx.x < 3) {
+        uint4 v = __ldg(reinterpret_cast<const uint4 *>(a.roots) + threadIdx.x);
+        if (threadIdx.x == 0) v.x = ~v.x;          // occupied -> free squares
+        s_root[threadIdx.x] = v;
+    }
+    const uint32_t lut_addr = smem_addr(s_lut), root_addr = smem_addr(s_root);
+    for (uint32_t i = threadIdx.x; i < QK_MOVE_LUT_BYTES / 4; i += kBlock) s_lut[i] = move_lut_image_word(i);
+    for (uint32_t i = threadIdx.x; i < 2048; i += kBlock) s_sel16[i] = (uint16_t)sel16_entry(i, lut_addr);
+    __syncthreads();
+    PredConsts pc;
+    pc.sel_addr = smem_addr(s_sel16);
+    pc.col_lo = (threadIdx.x & 7u) * 16u; pc.col_hi = pc.col_lo + 4096u;
+    pc.one = a.one; pc.zero = a.zero;
+
+    const uint64_t tid = blockIdx.x * (uint64_t)kBlock + threadIdx.x;
+    const uint64_t begin = tid * a.chunk;
+    uint32_t jn = 0, jend = 0;             // next playout this thread starts, and one past its last
+    if (begin < a.total) {
+        jn = (uint32_t)begin;
+        jend = (uint32_t)(begin + a.chunk < a.total ? begin + a.chunk : a.total);
+    }
+    const uint32_t games = jend - jn;
+    const uint32_t flags = s_root[2].w;
+    const bool a_is_p0 = (flags & 1u) == 0;
+    const uint32_t immediate = (flags >> QK_ROOT_IMMEDIATE_SHIFT) & 3u;
+    uint32_t acc = 0;                      // games won by role A
+    if (immediate) {                       // the root is decided: every playout is that result (mcts.py:412 order)
+        acc = ((immediate == 1) == a_is_p0) ? games : 0u;
+        jn = jend;
+    }
+
+    PlayState st = {};
+    uint32_t act = 0, block = 0;
+    const uint64_t rollout_base = a.first_rollout - 1;     // the game in flight is playout jn - 1
+    for (;;) {
+        // ---- 4-ply boundary: threads without a game in flight start their next one
+        asm volatile(
+            "{\n"
+            " .reg .pred pi, pr;\n"
+            " .reg .b32 fl;\n"
+            " setp.eq.u32 pi, %13, 0;\n"
+            " setp.lt.and.u32 pr, %11, %14, pi;\n"
+            " @pr ld.shared.v4.u32 {%0, %1, %2, %3}, [%15];\n"
+            " @pr ld.shared.v4.u32 {%4, %5, %6, %7}, [%15+16];\n"
+            " @pr ld.shared.v4.u32 {%8, %9, %10, fl}, [%15+32];\n"
+            " @pr add.u32 %11, %11, 1;\n"
+            " @pr mov.b32 %12, 0;\n"
+            " @pr mov.b32 %13, 0xFFFFFFFF;\n"
+            "}\n"
+            : "+r"(st.free2), "+r"(st.ra_lo), "+r"(st.ra_hi), "+r"(st.rb_lo), "+r"(st.rb_hi), "+r"(st.ta_lo), "+r"(st.ta_hi),
+              "+r"(st.tb_lo), "+r"(st.tb_hi), "+r"(st.lp_lo), "+r"(st.lp_hi), "+r"(jn), "+r"(block), "+r"(act)
+            : "r"(jend), "r"(root_addr));
+        if (!__any_sync(kFull, act != 0u)) break;   // nobody plays and (checked above) nobody could start: done
+
+        // ---- one Philox block = four plies, roles alternate A B A B
+        const Philox4 rnd = stream_block(a.seed, rollout_base + jn, a.root_index_base, block);
+        ++block;
+        ply_pred<0>(st, rnd.v[0], pc, act, acc);
+        ply_pred<1>(st, rnd.v[1], pc, act, acc);
+        ply_pred<0>(st, rnd.v[2], pc, act, acc);
+        ply_pred<1>(st, rnd.v[3], pc, act, acc);
+    }
+    flush_tallies(a, 0u, games, a_is_p0 ? acc : games - acc, 0u);
+}
+
 size_t playout_scratch_bytes(size_t n_roots) { return n_roots * sizeof(RootRec); }
 
 int launch_playouts(const uint4 *roots, size_t n_roots, uint32_t rollouts, uint64_t seed, uint64_t first_rollout,
@@ -264,6 +342,7 @@ int launch_playouts(const uint4 *roots, size_t n_roots, uint32_t rollouts, uint6
     a.seed = seed; a.first_rollout = first_rollout; a.rollouts = rollouts; a.root_index_base = root_index_base;
     a.max_plies = max_plies;
     a.wins_p0 = wins_p0; a.wins_p1 = wins_p1; a.draws = draws; a.per_playout = per_playout; a.per_plies = per_plies;
+    a.one = 1u; a.zero = 0u;
 
     const bool cutoff = max_plies >= 0, pp = per_playout || per_plies;
     void (*kernel)(const PlayoutArgs) = cutoff ? (pp ? k_playout<true, true> : k_playout<true, false>)
@@ -272,6 +351,9 @@ int launch_playouts(const uint4 *roots, size_t n_roots, uint32_t rollouts, uint6
         const long long v = option(OPT_PLAYOUT_VARIANT);        // benchmarking aid: 0 fresh (default) / 1 hoist / 2 general
         if (v == 0) kernel = k_playout_single<true>;
         else if (v == 1) kernel = k_playout_single<false>;
+        else if (v == 3) kernel = k_playout_pred<5>;
+        else if (v == 4) kernel = k_playout_pred<6>;
+        else if (v == 5) kernel = k_playout_pred<4>;
     }
     // persistent grid: exactly as many CTAs as are resident at once (no second wave), fewer only
     // when there are not enough playouts to give each thread one

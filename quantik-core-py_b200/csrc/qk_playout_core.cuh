@@ -259,6 +259,142 @@ __device__ __forceinline__ void ply_step_fma(PlayState &st, uint32_t rnd, const 
     const uint32_t all4 = st.lp_lo & st.lp_hi;
     win = (all4 & (all4 >> 16)) != 0;
 }
+
+// ---------------------------------------------------------------- one ply, predicated (device only)
+// Third instruction selection of the same function.  The popcount descent is PREDICATED execution, written in
+// PTX because the compiler turns the C++ form into compare + select pairs on the ALU pipe:
+//       p = (k >= c);   @p k -= c;   @p w >>= 16;   @p move-table row += ...
+// -- one ISETP and one SHF on the ALU pipe per level, the rest on the FMA pipe, where the multiply-add form above
+// needs five instructions per level plus rematerialised constants.  The three predicates (which half / lane /
+// byte holds the k-th legal action) only steer the ADDRESS of a 64-entry move table whose 32-byte entries are
+// pre-masked for (half, lane, square): scope and line bits already routed to the lo / hi register, lane masks
+// ready -- so the state update is eight unconditional LOP3s and no lane arithmetic.  A mover without a legal
+// action (n = 0: k = 0 and all three predicates hold) lands, through the byte table's entries for the empty byte,
+// on a 65th entry that changes nothing but sets bit 15 of all four shapes' line sets: "blocked" then comes out of
+// the SAME test as a completed line, as the sign bit of  lines & lines << 16 & act  (act = all-ones while the
+// game runs, zero afterwards).  Free squares are cleared by subtraction (the bit is set whenever the move is
+// real) and the line test shifts LEFT: both forms the FMA pipe can take, which the ALU pipe -- the busier one,
+// DESIGN.md section 5 -- cannot offload otherwise; `one` / `zero` are kernel parameters (so that ptxas keeps
+// x = one * c + x  an IMAD instead of folding it back into an ALU-pipe add).
+// `acc` counts the games role A wins (A = the root's mover): the mover of an even ply wins by completing a
+// line, the mover of an odd ply makes A win by being blocked (beam_search.py:633-635,641-642).
+// A lane whose game is over keeps executing plies on a meaningless state until the next 4-ply boundary:
+// every quantity stays in range (k < popcount of the word it indexes), nothing is tallied (act == 0).
+struct __attribute__((aligned(16))) MoveLut { uint32_t scope_lo, scope_hi, lines_lo, lines_hi, bit2, l_lo, l_hi, pad; };
+// Shared-memory layout: two planes (entry words 0-3, words 4-7), each entry replicated into the eight 16-byte columns
+// of a 128-byte row; a lane reads column lane % 8, so a 128-bit load of 32 different entries is conflict-free
+// (four wavefronts, the minimum for 512 bytes) whatever the entries are.
+enum { QK_MOVE_LUT_ENTRIES = 65, QK_MOVE_LUT_PLANE = QK_MOVE_LUT_ENTRIES * 128, QK_MOVE_LUT_BYTES = 2 * QK_MOVE_LUT_PLANE,
+       QK_MOVE_LUT_BLOCKED_ROW = 4 * 1792 };
+// word `wi` of entry `entry` = square | lane << 4 | half << 5; entry 64 = "the mover is blocked"
+QK_HD uint32_t move_lut_word(uint32_t entry, uint32_t wi)
+{
+    if (entry >= 64u) return (wi == 2u || wi == 3u) ? 0x80008000u : 0u;
+    const SquareLut q = square_lut((int)(entry & 15u));
+    const uint32_t lane = (entry & 16u) ? 0xFFFF0000u : 0x0000FFFFu, hi = (entry >> 5) & 1u;
+    const uint32_t v[8] = { hi ? 0u : q.scope2 & lane, hi ? q.scope2 & lane : 0u, hi ? 0u : q.lines2 & lane,
+                            hi ? q.lines2 & lane : 0u, q.bit2, hi ? 0u : lane, hi ? lane : 0u, 0u };
+    return v[wi & 7u];
+}
+// 16-bit byte table for the predicated ply: shared-memory address of the move-table entry of the k-th set bit of a
+// byte in row 0 (the row offset, QK_MOVE_LUT_BLOCKED_ROW for the empty byte, is added by the ply)
+QK_HD uint32_t sel16_entry(uint32_t index, uint32_t lut_addr)
+{
+    if ((index >> 3) == 0u) return lut_addr + 64u * 128u - QK_MOVE_LUT_BLOCKED_ROW;
+    return lut_addr + 128u * kth_in_byte(index >> 3, index & 7u);
+}
+// 32-bit word `w` of the shared-memory image of the move table
+QK_HD uint32_t move_lut_image_word(uint32_t w)
+{
+    const uint32_t plane = w / (QK_MOVE_LUT_PLANE / 4u), rem = w % (QK_MOVE_LUT_PLANE / 4u);
+    return move_lut_word(rem / 32u, (rem & 3u) + 4u * plane);
+}
+
+// shared-memory address of the 16-bit byte table, the lane's column in the move table (+ the row offset of shapes C,D),
+// and the opaque 1 and 0
+struct PredConsts { uint32_t sel_addr, col_lo, col_hi, one, zero; };
+
+// lut / sel16 live in shared memory; ROLE 0: role A moves
+template <int ROLE>
+__device__ __forceinline__ void ply_pred(PlayState &st, uint32_t rnd, const PredConsts &pc, uint32_t &act, uint32_t &acc)
+{
+    uint32_t &rm_lo = ROLE ? st.rb_lo : st.ra_lo, &rm_hi = ROLE ? st.rb_hi : st.ra_hi;   // mover
+    uint32_t &ro_lo = ROLE ? st.ra_lo : st.rb_lo, &ro_hi = ROLE ? st.ra_hi : st.rb_hi;   // other
+    uint32_t &tm_lo = ROLE ? st.tb_lo : st.ta_lo, &tm_hi = ROLE ? st.tb_hi : st.ta_hi;
+    uint32_t e0x, e0y, e0z, e0w, e1x, e1y, e1z, e1w;
+    asm("{\n"
+        " .reg .pred p0, p1, p2;\n"
+        " .reg .b32 ll, lh, nl, nh, n, k, w, t, c, row, ad;\n"
+        " .reg .b16 eh;\n"
+        " lop3.b32 ll, %8, %9, 0, 0x30;\n"              /* legal, shapes A,B: free & ~closed */
+        " lop3.b32 lh, %8, %10, 0, 0x30;\n"             /* legal, shapes C,D */
+        " popc.b32 nl, ll;\n"
+        " popc.b32 nh, lh;\n"
+        " add.u32 n, nl, nh;\n"
+        " mul.hi.u32 k, %11, n;\n"                      /* uniform pick: k-th legal action, ascending */
+        " setp.ge.u32 p0, k, nl;\n"                     /* 64 -> 32 */
+        " selp.b32 w, lh, ll, p0;\n"
+        " selp.b32 row, %15, %14, p0;\n"
+        " @p0 sub.u32 k, k, nl;\n"
+        " shl.b32 t, w, 16;\n"                          /* 32 -> 16 */
+        " popc.b32 c, t;\n"
+        " setp.ge.u32 p1, k, c;\n"
+        " @p1 shr.u32 w, w, 16;\n"
+        " @p1 sub.u32 k, k, c;\n"
+        " @p1 mad.lo.u32 row, %13, 2048, row;\n"
+        " shl.b32 t, w, 24;\n"                          /* 16 -> 8 */
+        " popc.b32 c, t;\n"
+        " setp.ge.u32 p2, k, c;\n"
+        " @p2 shr.u32 w, w, 8;\n"
+        " @p2 sub.u32 k, k, c;\n"
+        " @p2 mad.lo.u32 row, %13, 1024, row;\n"
+        " and.b32 t, w, 0xFF;\n"                        /* 8 -> 1 from the byte table */
+        " mad.lo.u32 ad, t, 8, k;\n"
+        " mad.lo.u32 ad, ad, 2, %12;\n"                 /* 16-bit entries */
+        " ld.shared.u16 eh, [ad];\n"
+        " cvt.u32.u16 ad, eh;\n"
+        " add.u32 ad, ad, row;\n"
+        " ld.shared.v4.u32 {%0, %1, %2, %3}, [ad];\n"
+        " ld.shared.v4.u32 {%4, %5, %6, %7}, [ad+8320];\n"
+        "}\n"
+        : "=r"(e0x), "=r"(e0y), "=r"(e0z), "=r"(e0w), "=r"(e1x), "=r"(e1y), "=r"(e1z), "=r"(e1w)
+        : "r"(st.free2), "r"(rm_lo), "r"(rm_hi), "r"(rnd), "r"(pc.sel_addr), "r"(pc.one), "r"(pc.col_lo), "r"(pc.col_hi));
+    static_assert(QK_MOVE_LUT_PLANE == 8320, "the second plane's offset is spelled out in the PTX above");
+    ro_lo |= e0x;              ro_hi |= e0y;              // opponent may no longer use this shape in my scope
+    rm_lo |= tm_lo & e1y;      rm_hi |= tm_hi & e1z;      // second piece of the shape: lane exhausted for me
+    tm_lo |= e1y;              tm_hi |= e1z;
+    st.lp_lo |= e0z;           st.lp_hi |= e0w;           // lines that now contain the shape
+    st.free2 -= e1x;                                      // square no longer free
+    // has_winning_line (a line holding all four shapes) or blocked (the sign bit), while the game runs
+    if (ROLE == 0)
+        asm("{\n"
+            " .reg .pred pf, pa;\n"
+            " .reg .b32 a4, t;\n"
+            " and.b32 a4, %2, %3;\n"
+            " shl.b32 t, a4, 16;\n"
+            " lop3.b32 t, a4, t, %0, 0x80;\n"
+            " setp.ne.s32 pf, t, 0;\n"                  /* the game ends with this ply */
+            " setp.gt.s32 pa, t, 0;\n"                  /* A completed a line */
+            " @pa mad.lo.u32 %1, %4, %4, %1;\n"
+            " @pf mul.lo.u32 %0, %0, %5;\n"
+            "}\n"
+            : "+r"(act), "+r"(acc)
+            : "r"(st.lp_lo), "r"(st.lp_hi), "r"(pc.one), "r"(pc.zero));
+    else
+        asm("{\n"
+            " .reg .pred pf, pa;\n"
+            " .reg .b32 a4, t;\n"
+            " and.b32 a4, %2, %3;\n"
+            " shl.b32 t, a4, 16;\n"
+            " lop3.b32 t, a4, t, %0, 0x80;\n"
+            " setp.ne.s32 pf, t, 0;\n"
+            " setp.lt.s32 pa, t, 0;\n"                  /* B cannot move: A wins */
+            " @pa mad.lo.u32 %1, %4, %4, %1;\n"
+            " @pf mul.lo.u32 %0, %0, %5;\n"
+            "}\n"
+            : "+r"(act), "+r"(acc)
+            : "r"(st.lp_lo), "r"(st.lp_hi), "r"(pc.one), "r"(pc.zero));
+}
 #endif
 
 // ---------------------------------------------------------------- scalar playout

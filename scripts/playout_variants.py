@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""Config-1 throughput of the playout kernel variants (qk_set_option "playout_variant": fresh | hoist | general)."""
+"""Config-1 throughput of the playout kernel variants (qk_set_option "playout_variant") and a tally cross-check."""
 import os
 import sys
 import time
@@ -9,12 +9,35 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "quantik-core-py_b200"))
+sys.path.insert(0, ROOT)
 import quantik_b200 as Q  # noqa: E402
+import quantik_b200.batch as B  # noqa: E402
+from oracle import oracle as O  # noqa: E402
+
+VARIANTS = {"fresh": 0, "hoist": 1, "general": 2, "pred5": 3, "pred6": 4, "pred4": 5}
+names = sys.argv[1:] or ["fresh", "pred5", "pred6", "pred4"]
+
+roots = [np.zeros((1, 8), np.uint16), O.make_roots(3, seed=5, min_plies=6, span=3)[1:2], O.make_roots(9, seed=7, min_plies=9, span=3)[4:5],
+         np.array([[1, 2, 4, 8, 0, 0, 0, 0]], np.uint16)]
+bad = 0
+for ri, root in enumerate(roots):
+    for n, first in ((1, 0), (1000, 0), (300_001, 12345), (1 << 22, 1 << 40)):
+        want = None
+        for v in ["general"] + names:
+            Q._native.set_option("playout_variant", VARIANTS[v])
+            r = B.playouts(root, n, 20260101, first_rollout=first)
+            t = (int(r["wins_p0"][0]), int(r["wins_p1"][0]), int(r["draws"][0]))
+            if want is None:
+                want = t
+            elif t != want:
+                bad += 1
+                print("MISMATCH root", ri, "n", n, "first", first, v, t, "general", want, flush=True)
+print("tally cross-check:", "OK" if not bad else f"{bad} mismatches", flush=True)
 
 root = torch.zeros((1, 8), dtype=torch.int16, device="cuda:0")
 n = 1 << 30
-for variant in ("general", "hoist", "fresh", "general", "hoist", "fresh"):
-    Q._native.set_option("playout_variant", {"fresh": 0, "hoist": 1, "general": 2}[variant])
+for variant in names + names:
+    Q._native.set_option("playout_variant", VARIANTS[variant])
     Q.playouts(root, 1 << 24)
     torch.cuda.synchronize()
     t0 = time.perf_counter()

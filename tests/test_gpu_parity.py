@@ -815,12 +815,12 @@ def test_single_root_kernel_matches_general_kernel_and_oracle(options):
     for root in roots:
         for n, first in ((1, 0), (1000, 0), (300_001, 12345), (1 << 22, 1 << 40)):
             tallies = {}
-            for variant in ("fresh", "hoist", "general"):
-                options("playout_variant", {"fresh": 0, "hoist": 1, "general": 2}[variant])
+            for variant in ("fresh", "hoist", "general", "pred5", "pred6", "pred4"):
+                options("playout_variant", {"fresh": 0, "hoist": 1, "general": 2, "pred5": 3, "pred6": 4, "pred4": 5}[variant])
                 r = B.playouts(root, n, SEED, first_rollout=first)
                 tallies[variant] = (int(r["wins_p0"][0]), int(r["wins_p1"][0]), int(r["draws"][0]))
                 assert sum(tallies[variant]) == n
-            assert tallies["fresh"] == tallies["hoist"] == tallies["general"], (n, first, tallies)
+            assert len(set(tallies.values())) == 1, (n, first, tallies)
             if n <= 300_001:
                 o = O.playouts(root, n, SEED, first)
                 assert tallies["fresh"] == (int(o["wins_p0"][0]), int(o["wins_p1"][0]), int(o["draws"][0]))

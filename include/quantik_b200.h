@@ -80,7 +80,8 @@ QK_API const char *qk_last_error(void);
  *   "perft_tile_generic"  1: k_perft_tile without the one-side / 32-bit-multiplicity fast form
  *   "playout_variant"     0 auto | 1 single-root kernel, root record hoisted | 2 general kernel for one root
  *   "dedup_mode"          0 auto | 1 one-level table insert | 2 partitioned (two-level) insert
- *   "dedup_part_mb"       > 0: size in MiB of the L2-resident table one part of the two-level insert is merged in  */
+ *   "dedup_part_mb"       > 0: size in MiB of the L2-resident table one part of the two-level insert is merged in
+ *   "playout_grab"        > 0: playouts a lane of the single-root playout kernel takes from the work queue at a time  */
 QK_API int qk_set_option(const char *name, long long value);
 /* SM count and clock (kHz) of an initialised device; either pointer may be NULL. */
 QK_API int qk_device_info(int dev, int *sm_count, int *sm_clock_khz);

@@ -36,6 +36,8 @@ struct PlayoutArgs {
     int8_t *per_playout;
     uint8_t *per_plies;
     uint32_t one, zero;      // 1 and 0 the compiler cannot see (k_playout_pred: keeps small additions on the FMA pipe)
+    uint32_t *queue;         // k_playout_pred: next playout nobody has taken yet (zeroed before the launch)
+    uint32_t grab;           // k_playout_pred: playouts a lane takes from the queue at a time
 };
 
 __global__ void __launch_bounds__(kBlock) k_prepare_roots(const uint4 *__restrict__ states, size_t n, RootRec *__restrict__ out)
@@ -255,6 +257,16 @@ __global__ void QK_PLAYOUT_BOUNDS k_playout_single(const PlayoutArgs a)
 // games a thread plays is known in advance).
 __device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+#ifdef QK_PLAYOUT_TIMELINE      // experiment build (scripts/playout_timeline.py): when does each warp start and finish?
+__device__ unsigned long long g_timeline[4 * 16384];
+__device__ __forceinline__ unsigned long long globaltimer()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#endif
+
 template <int MIN_CTAS>
 __global__ void __launch_bounds__(kBlock, MIN_CTAS) k_playout_pred(const PlayoutArgs a)
 {
@@ -270,32 +282,55 @@ __global__ void __launch_bounds__(kBlock, MIN_CTAS) k_playout_pred(const Playout
     for (uint32_t i = threadIdx.x; i < QK_MOVE_LUT_BYTES / 4; i += kBlock) s_lut[i] = move_lut_image_word(i);
     for (uint32_t i = threadIdx.x; i < 2048; i += kBlock) s_sel16[i] = (uint16_t)sel16_entry(i, lut_addr);
     __syncthreads();
+#ifdef QK_PLAYOUT_TIMELINE
+    const unsigned long long t_begin = globaltimer();
+#endif
     PredConsts pc;
     pc.sel_addr = smem_addr(s_sel16);
     pc.col_lo = (threadIdx.x & 7u) * 16u; pc.col_hi = pc.col_lo + 4096u;
     pc.one = a.one; pc.zero = a.zero;
 
-    const uint64_t tid = blockIdx.x * (uint64_t)kBlock + threadIdx.x;
-    const uint64_t begin = tid * a.chunk;
-    uint32_t jn = 0, jend = 0;             // next playout this thread starts, and one past its last
-    if (begin < a.total) {
-        jn = (uint32_t)begin;
-        jend = (uint32_t)(begin + a.chunk < a.total ? begin + a.chunk : a.total);
+    // Work is not dealt out in advance: the warp scheduler favours some warps of an SM over others (with equal shares
+    // the slowest quarter of the warps finished at 1.8x the time of the fastest, and the SM ran the last fifth of the
+    // kernel with a quarter of its warps), so every lane takes `grab` playouts at a time from one queue, always
+    // holding its current range [jn, jend) and the start of its next one (taken ahead of time, so that the atomic's
+    // latency is never waited for).
+    const uint32_t total = (uint32_t)a.total, grab = a.grab;
+    constexpr uint32_t kExhausted = 0xFFFFFFFFu;
+    uint32_t jn, jend, jnext;              // next playout this lane starts, one past its range, its next range
+    {
+        uint32_t base = 0;
+        if ((threadIdx.x & 31u) == 0) base = atomicAdd(a.queue, 64u * grab);
+        base = __shfl_sync(kFull, base, 0);
+        jn = base + (threadIdx.x & 31u) * grab;
+        jnext = jn + 32u * grab;
+        jend = jn + grab < total ? jn + grab : total;
+        if (jn >= total) { jn = jend = 0; jnext = kExhausted; }
     }
-    const uint32_t games = jend - jn;
     const uint32_t flags = s_root[2].w;
     const bool a_is_p0 = (flags & 1u) == 0;
     const uint32_t immediate = (flags >> QK_ROOT_IMMEDIATE_SHIFT) & 3u;
-    uint32_t acc = 0;                      // games won by role A
+    uint32_t acc = 0, games = jend - jn;   // games won by role A, games played (every game that is started is finished)
     if (immediate) {                       // the root is decided: every playout is that result (mcts.py:412 order)
+        games = (blockIdx.x == 0 && threadIdx.x == 0) ? total : 0u;
         acc = ((immediate == 1) == a_is_p0) ? games : 0u;
-        jn = jend;
+        jn = jend = 0; jnext = kExhausted;
     }
 
     PlayState st = {};
     uint32_t act = 0, block = 0;
     const uint64_t rollout_base = a.first_rollout - 1;     // the game in flight is playout jn - 1
     for (;;) {
+        // ---- a lane that has used up its range moves on to the one it holds in reserve and reserves another
+        if (act == 0u && jn == jend && jnext != kExhausted) {
+            jn = jnext;
+            if (jn >= total) { jn = jend = 0; jnext = kExhausted; }
+            else {
+                jend = jn + grab < total ? jn + grab : total;
+                jnext = atomicAdd(a.queue, grab);
+                games += jend - jn;
+            }
+        }
         // ---- 4-ply boundary: threads without a game in flight start their next one
         asm volatile(
             "{\n"
@@ -324,9 +359,25 @@ __global__ void __launch_bounds__(kBlock, MIN_CTAS) k_playout_pred(const Playout
         ply_pred<1>(st, rnd.v[3], pc, act, acc);
     }
     flush_tallies(a, 0u, games, a_is_p0 ? acc : games - acc, 0u);
+#ifdef QK_PLAYOUT_TIMELINE
+    if ((threadIdx.x & 31u) == 0) {
+        const uint32_t w = blockIdx.x * (kBlock / 32) + threadIdx.x / 32;
+        uint32_t smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        if (w < 16384) { g_timeline[4 * w] = t_begin; g_timeline[4 * w + 1] = globaltimer(); g_timeline[4 * w + 2] = smid; g_timeline[4 * w + 3] = games; }
+    }
+#endif
 }
+#ifdef QK_PLAYOUT_TIMELINE
+}  // namespace qk
+extern "C" __attribute__((visibility("default"))) int qk_debug_timeline(unsigned long long *out, size_t n)
+{
+    return (int)cudaMemcpyFromSymbol(out, qk::g_timeline, n * sizeof(unsigned long long));
+}
+namespace qk {
+#endif
 
-size_t playout_scratch_bytes(size_t n_roots) { return n_roots * sizeof(RootRec); }
+size_t playout_scratch_bytes(size_t n_roots) { return n_roots * sizeof(RootRec) + 16; }   // + the work-queue counter
 
 int launch_playouts(const uint4 *roots, size_t n_roots, uint32_t rollouts, uint64_t seed, uint64_t first_rollout,
                     uint32_t root_index_base, int max_plies, uint32_t *wins_p0, uint32_t *wins_p1, uint32_t *draws,
@@ -343,11 +394,12 @@ int launch_playouts(const uint4 *roots, size_t n_roots, uint32_t rollouts, uint6
     a.max_plies = max_plies;
     a.wins_p0 = wins_p0; a.wins_p1 = wins_p1; a.draws = draws; a.per_playout = per_playout; a.per_plies = per_plies;
     a.one = 1u; a.zero = 0u;
+    a.queue = reinterpret_cast<uint32_t *>(recs + n_roots); a.grab = 1;
 
     const bool cutoff = max_plies >= 0, pp = per_playout || per_plies;
     void (*kernel)(const PlayoutArgs) = cutoff ? (pp ? k_playout<true, true> : k_playout<true, false>)
                                                : (pp ? k_playout<false, true> : k_playout<false, false>);
-    if (n_roots == 1 && !cutoff && !pp) {
+    if (n_roots == 1 && !cutoff && !pp && a.total <= 0xFFFFFFFFull - (1ull << 27)) {
         const long long v = option(OPT_PLAYOUT_VARIANT);        // benchmarking aid: 0 fresh (default) / 1 hoist / 2 general
         if (v == 0) kernel = k_playout_single<true>;
         else if (v == 1) kernel = k_playout_single<false>;
@@ -365,6 +417,14 @@ int launch_playouts(const uint4 *roots, size_t n_roots, uint32_t rollouts, uint6
     unsigned grid = (unsigned)((threads + kBlock - 1) / kBlock);
     a.chunk = (a.total + (uint64_t)grid * kBlock - 1) / ((uint64_t)grid * kBlock);
     if (a.chunk >= (1ull << 32)) { set_error("qk_playouts: more than 2^32 playouts per thread"); return QK_E_BAD_ARG; }
+    if (kernel == k_playout_pred<4> || kernel == k_playout_pred<5> || kernel == k_playout_pred<6>) {
+        // lanes take their playouts from a queue, `grab` at a time: small enough that the lanes run dry together at the
+        // end (about 1/16 of a lane's share), large enough that the counter is not a hot spot
+        const long long g = option(OPT_PLAYOUT_GRAB);
+        uint64_t share = a.total / ((uint64_t)grid * kBlock * 16);
+        a.grab = g > 0 ? (uint32_t)(g < 256 ? g : 256) : (uint32_t)(share < 1 ? 1 : share > 64 ? 64 : share);
+        QK_CUDA(cudaMemsetAsync(a.queue, 0, 4, s));
+    }
     kernel<<<grid, kBlock, 0, s>>>(a);
     QK_CUDA(cudaGetLastError());
     return QK_OK;

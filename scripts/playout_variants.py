@@ -15,7 +15,8 @@ import quantik_b200.batch as B  # noqa: E402
 from oracle import oracle as O  # noqa: E402
 
 VARIANTS = {"fresh": 0, "hoist": 1, "general": 2, "pred5": 3, "pred6": 4, "pred4": 5}
-names = sys.argv[1:] or ["fresh", "pred5", "pred6", "pred4"]
+names = [a for a in sys.argv[1:] if not a.startswith("grab=")] or ["fresh", "pred5", "pred6", "pred4"]
+grabs = [int(a[5:]) for a in sys.argv[1:] if a.startswith("grab=")] or [0]
 
 roots = [np.zeros((1, 8), np.uint16), O.make_roots(3, seed=5, min_plies=6, span=3)[1:2], O.make_roots(9, seed=7, min_plies=9, span=3)[4:5],
          np.array([[1, 2, 4, 8, 0, 0, 0, 0]], np.uint16)]
@@ -36,8 +37,9 @@ print("tally cross-check:", "OK" if not bad else f"{bad} mismatches", flush=True
 
 root = torch.zeros((1, 8), dtype=torch.int16, device="cuda:0")
 n = 1 << 30
-for variant in names + names:
+for variant, grab in [(v, g) for g in grabs for v in names] * 2:
     Q._native.set_option("playout_variant", VARIANTS[variant])
+    Q._native.set_option("playout_grab", grab)
     Q.playouts(root, 1 << 24)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
@@ -45,4 +47,4 @@ for variant in names + names:
         r = Q.playouts(root, n, first_rollout=i * n)
     torch.cuda.synchronize()
     dt = (time.perf_counter() - t0) / 3
-    print(f"{variant:8s} {n / dt:.4e} playouts/s  p0 {int(r['wins_p0'][0]) / n:.5f}", flush=True)
+    print(f"{variant:8s} grab {grab:3d} {n / dt:.4e} playouts/s  p0 {int(r['wins_p0'][0]) / n:.5f}", flush=True)

@@ -377,6 +377,98 @@ extern "C" __attribute__((visibility("default"))) int qk_debug_timeline(unsigned
 namespace qk {
 #endif
 
+// Configs with many roots (BASELINE config 4, the batched engines' leaves), tallies only, played to the end: the same
+// ply and the same queue, whose items are (root, slice of `grab` rollouts) -- a lane's range never straddles two roots,
+// so the root's record address, its index in the random stream and the tallies' destination change only in the
+// rarely taken range switch; a root that is already decided is accounted for there without being played.
+template <int MIN_CTAS>
+__global__ void __launch_bounds__(kBlock, MIN_CTAS) k_playout_pred_roots(const PlayoutArgs a)
+{
+    __shared__ __align__(128) uint32_t s_lut[QK_MOVE_LUT_BYTES / 4];
+    __shared__ __align__(16) uint16_t s_sel16[2048];
+    const uint32_t lut_addr = smem_addr(s_lut);
+    for (uint32_t i = threadIdx.x; i < QK_MOVE_LUT_BYTES / 4; i += kBlock) s_lut[i] = move_lut_image_word(i);
+    for (uint32_t i = threadIdx.x; i < 2048; i += kBlock) s_sel16[i] = (uint16_t)sel16_entry(i, lut_addr);
+    __syncthreads();
+    PredConsts pc;
+    pc.sel_addr = smem_addr(s_sel16);
+    pc.col_lo = (threadIdx.x & 7u) * 16u; pc.col_hi = pc.col_lo + 4096u;
+    pc.one = a.one; pc.zero = a.zero;
+
+    const uint32_t grab = a.grab, slices = (a.rollouts + grab - 1) / grab;     // slices per root
+    const uint32_t items = (uint32_t)(a.total);                                // here: number of (root, slice) items
+    constexpr uint32_t kExhausted = 0xFFFFFFFFu;
+    uint32_t qnext;                         // the item this lane plays next
+    {
+        uint32_t base = 0;
+        if ((threadIdx.x & 31u) == 0) base = atomicAdd(a.queue, 32u);
+        qnext = __shfl_sync(kFull, base, 0) + (threadIdx.x & 31u);
+    }
+    uint32_t j = 0, jend = 0;               // next rollout of the current root this lane starts, one past its slice
+    uint32_t root = 0, acc = 0, games = 0;  // current root, games of it won by its mover, games of it played
+    bool a_is_p0 = true;
+    const uint4 *rp = reinterpret_cast<const uint4 *>(a.roots);
+
+    PlayState st = {};
+    uint32_t act = 0, block = 0;
+    const uint64_t rollout_base = a.first_rollout - 1;     // the game in flight is rollout j - 1
+    for (;;) {
+        // ---- a lane that has used up its slice takes the item it holds in reserve and reserves another
+        if (act == 0u && j == jend && qnext != kExhausted) {
+            const uint32_t q = qnext;
+            if (q >= items) qnext = kExhausted;
+            else {
+                qnext = atomicAdd(a.queue, 1u);
+                const uint32_t r = q / slices, j0 = (q - r * slices) * grab;
+                if (r != root) {
+                    flush_tallies(a, root, games, a_is_p0 ? acc : games - acc, 0u);
+                    acc = games = 0;
+                    root = r;
+                }
+                rp = reinterpret_cast<const uint4 *>(a.roots + r);
+                const uint32_t flags = __ldg(&a.roots[r].flags);
+                a_is_p0 = (flags & 1u) == 0;
+                const uint32_t len = a.rollouts - j0 < grab ? a.rollouts - j0 : grab;
+                const uint32_t immediate = (flags >> QK_ROOT_IMMEDIATE_SHIFT) & 3u;
+                games += len;
+                j = j0; jend = j0 + len;
+                if (immediate) {            // decided at the root: that result for the whole slice, nothing to play
+                    acc += ((immediate == 1) == a_is_p0) ? len : 0u;
+                    j = jend;
+                }
+            }
+        }
+        // ---- 4-ply boundary: threads without a game in flight start their next one
+        asm volatile(
+            "{\n"
+            " .reg .pred pi, pr;\n"
+            " .reg .b32 fl;\n"
+            " setp.eq.u32 pi, %13, 0;\n"
+            " setp.lt.and.u32 pr, %11, %14, pi;\n"
+            " @pr ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%15];\n"
+            " @pr ld.global.nc.v4.u32 {%4, %5, %6, %7}, [%15+16];\n"
+            " @pr ld.global.nc.v4.u32 {%8, %9, %10, fl}, [%15+32];\n"
+            " @pr not.b32 %0, %0;\n"
+            " @pr add.u32 %11, %11, 1;\n"
+            " @pr mov.b32 %12, 0;\n"
+            " @pr mov.b32 %13, 0xFFFFFFFF;\n"
+            "}\n"
+            : "+r"(st.free2), "+r"(st.ra_lo), "+r"(st.ra_hi), "+r"(st.rb_lo), "+r"(st.rb_hi), "+r"(st.ta_lo), "+r"(st.ta_hi),
+              "+r"(st.tb_lo), "+r"(st.tb_hi), "+r"(st.lp_lo), "+r"(st.lp_hi), "+r"(j), "+r"(block), "+r"(act)
+            : "r"(jend), "l"(rp));
+        if (!__any_sync(kFull, act != 0u || qnext != kExhausted)) break;   // nobody plays, nobody can take another item
+
+        // ---- one Philox block = four plies, roles alternate A B A B
+        const Philox4 rnd = stream_block(a.seed, rollout_base + j, a.root_index_base + root, block);
+        ++block;
+        ply_pred<0>(st, rnd.v[0], pc, act, acc);
+        ply_pred<1>(st, rnd.v[1], pc, act, acc);
+        ply_pred<0>(st, rnd.v[2], pc, act, acc);
+        ply_pred<1>(st, rnd.v[3], pc, act, acc);
+    }
+    flush_tallies(a, root, games, a_is_p0 ? acc : games - acc, 0u);
+}
+
 size_t playout_scratch_bytes(size_t n_roots) { return n_roots * sizeof(RootRec) + 16; }   // + the work-queue counter
 
 int launch_playouts(const uint4 *roots, size_t n_roots, uint32_t rollouts, uint64_t seed, uint64_t first_rollout,
@@ -399,13 +491,25 @@ int launch_playouts(const uint4 *roots, size_t n_roots, uint32_t rollouts, uint6
     const bool cutoff = max_plies >= 0, pp = per_playout || per_plies;
     void (*kernel)(const PlayoutArgs) = cutoff ? (pp ? k_playout<true, true> : k_playout<true, false>)
                                                : (pp ? k_playout<false, true> : k_playout<false, false>);
-    if (n_roots == 1 && !cutoff && !pp && a.total <= 0xFFFFFFFFull - (1ull << 27)) {
-        const long long v = option(OPT_PLAYOUT_VARIANT);        // benchmarking aid: 0 fresh (default) / 1 hoist / 2 general
-        if (v == 0) kernel = k_playout_single<true>;
-        else if (v == 1) kernel = k_playout_single<false>;
+    // Tallies only, played to the end: the predicated kernels, which take their work from a queue (a 32-bit counter:
+    // every lane may over-shoot it once).  "playout_variant": 0 auto | 1, 6 the older single-root kernels (root record
+    // hoisted / re-read) | 2 the general kernel | 3, 4 the predicated kernels at 5 / 6 resident CTAs per SM instead of 4
+    const long long v = option(OPT_PLAYOUT_VARIANT);
+    const bool queue_fits = a.total <= 0xFFFFFFFFull - (1ull << 27);
+    bool pred = false, pred_roots = false;
+    if (n_roots == 1 && !cutoff && !pp && queue_fits) {
+        pred = true;
+        if (v == 0 || v == 5) kernel = k_playout_pred<4>;
         else if (v == 3) kernel = k_playout_pred<5>;
         else if (v == 4) kernel = k_playout_pred<6>;
-        else if (v == 5) kernel = k_playout_pred<4>;
+        else {
+            pred = false;
+            if (v == 1) kernel = k_playout_single<false>;
+            else if (v == 6) kernel = k_playout_single<true>;
+        }
+    } else if (!cutoff && !pp && queue_fits && v != 2 && rollouts >= 8) {
+        pred_roots = true;
+        kernel = v == 3 ? k_playout_pred_roots<5> : v == 4 ? k_playout_pred_roots<6> : k_playout_pred_roots<4>;
     }
     // persistent grid: exactly as many CTAs as are resident at once (no second wave), fewer only
     // when there are not enough playouts to give each thread one
@@ -417,12 +521,16 @@ int launch_playouts(const uint4 *roots, size_t n_roots, uint32_t rollouts, uint6
     unsigned grid = (unsigned)((threads + kBlock - 1) / kBlock);
     a.chunk = (a.total + (uint64_t)grid * kBlock - 1) / ((uint64_t)grid * kBlock);
     if (a.chunk >= (1ull << 32)) { set_error("qk_playouts: more than 2^32 playouts per thread"); return QK_E_BAD_ARG; }
-    if (kernel == k_playout_pred<4> || kernel == k_playout_pred<5> || kernel == k_playout_pred<6>) {
+    if (pred || pred_roots) {
         // lanes take their playouts from a queue, `grab` at a time: small enough that the lanes run dry together at the
         // end (about 1/16 of a lane's share), large enough that the counter is not a hot spot
         const long long g = option(OPT_PLAYOUT_GRAB);
         uint64_t share = a.total / ((uint64_t)grid * kBlock * 16);
         a.grab = g > 0 ? (uint32_t)(g < 256 ? g : 256) : (uint32_t)(share < 1 ? 1 : share > 64 ? 64 : share);
+        if (pred_roots) {                               // the queue's items are (root, slice of `grab` rollouts)
+            if (a.grab > rollouts) a.grab = rollouts;
+            a.total = (uint64_t)n_roots * ((rollouts + a.grab - 1) / a.grab);
+        }
         QK_CUDA(cudaMemsetAsync(a.queue, 0, 4, s));
     }
     kernel<<<grid, kBlock, 0, s>>>(a);

@@ -14,8 +14,8 @@ import quantik_b200 as Q  # noqa: E402
 import quantik_b200.batch as B  # noqa: E402
 from oracle import oracle as O  # noqa: E402
 
-VARIANTS = {"fresh": 0, "hoist": 1, "general": 2, "pred5": 3, "pred6": 4, "pred4": 5}
-names = [a for a in sys.argv[1:] if not a.startswith("grab=")] or ["fresh", "pred5", "pred6", "pred4"]
+VARIANTS = {"auto": 0, "hoist": 1, "general": 2, "pred5": 3, "pred6": 4, "pred4": 5, "fresh": 6}
+names = [a for a in sys.argv[1:] if not a.startswith("grab=")] or ["fresh", "pred5", "pred6", "auto"]
 grabs = [int(a[5:]) for a in sys.argv[1:] if a.startswith("grab=")] or [0]
 
 roots = [np.zeros((1, 8), np.uint16), O.make_roots(3, seed=5, min_plies=6, span=3)[1:2], O.make_roots(9, seed=7, min_plies=9, span=3)[4:5],
@@ -34,6 +34,21 @@ for ri, root in enumerate(roots):
                 bad += 1
                 print("MISMATCH root", ri, "n", n, "first", first, v, t, "general", want, flush=True)
 print("tally cross-check:", "OK" if not bad else f"{bad} mismatches", flush=True)
+
+# config 4: 65 536 mid-game roots x 1 024 rollouts
+roots4 = B.random_roots(65536, seed=4, min_plies=4, span=8, as_torch=True)
+if roots4 is not None:
+    for variant in ["general"] + [v for v in names if v != "fresh"]:
+        Q._native.set_option("playout_variant", VARIANTS[variant])
+        Q._native.set_option("playout_grab", 0)
+        B.playouts(roots4, 64)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(3):
+            r = B.playouts(roots4, 1024, first_rollout=i * 1024)
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / 3
+        print(f"config 4 {variant:8s} {65536 * 1024 / dt:.4e} playouts/s  p0 {float(r['wins_p0'].sum()) / (65536 * 1024):.5f}", flush=True)
 
 root = torch.zeros((1, 8), dtype=torch.int16, device="cuda:0")
 n = 1 << 30

@@ -815,13 +815,35 @@ def test_single_root_kernel_matches_general_kernel_and_oracle(options):
     for root in roots:
         for n, first in ((1, 0), (1000, 0), (300_001, 12345), (1 << 22, 1 << 40)):
             tallies = {}
-            for variant in ("fresh", "hoist", "general", "pred5", "pred6", "pred4"):
-                options("playout_variant", {"fresh": 0, "hoist": 1, "general": 2, "pred5": 3, "pred6": 4, "pred4": 5}[variant])
+            for variant in ("auto", "fresh", "hoist", "general", "pred5", "pred6"):
+                options("playout_variant", {"auto": 0, "hoist": 1, "general": 2, "pred5": 3, "pred6": 4, "fresh": 6}[variant])
                 r = B.playouts(root, n, SEED, first_rollout=first)
                 tallies[variant] = (int(r["wins_p0"][0]), int(r["wins_p1"][0]), int(r["draws"][0]))
                 assert sum(tallies[variant]) == n
             assert len(set(tallies.values())) == 1, (n, first, tallies)
             if n <= 300_001:
                 o = O.playouts(root, n, SEED, first)
-                assert tallies["fresh"] == (int(o["wins_p0"][0]), int(o["wins_p1"][0]), int(o["draws"][0]))
+                assert tallies["auto"] == (int(o["wins_p0"][0]), int(o["wins_p1"][0]), int(o["draws"][0]))
     options("playout_variant", 0)
+
+
+def test_many_roots_tally_kernel_matches_general_kernel_and_oracle(options):
+    """Tallies-only playouts of many roots run the predicated kernel with (root, slice) work items; every root's tallies
+    must equal the general kernel's and the oracle's -- odd slice sizes, decided roots, fewer items than lanes."""
+    roots = O.make_roots(3000, seed=11, min_plies=0, span=14)
+    roots[5] = np.array([1, 2, 4, 8, 0, 0, 0, 0], np.uint16)                  # already won
+    roots[6] = np.array([1, 0, 0, 0, 0, 0, 0, 0], np.uint16)                  # ordinary, P1 to move
+    for n_roots, rollouts, first, grab in ((3000, 100, 0, 0), (3000, 100, 7, 7), (37, 1000, 1 << 33, 0), (512, 16, 3, 64), (3000, 8, 0, 3)):
+        got = {}
+        for variant in ("general", "auto", "pred5", "pred6"):
+            options("playout_variant", {"auto": 0, "general": 2, "pred5": 3, "pred6": 4}[variant])
+            options("playout_grab", grab)
+            r = B.playouts(roots[:n_roots], rollouts, SEED, first_rollout=first, root_index_base=5)
+            got[variant] = np.stack([np.asarray(r[k].cpu() if hasattr(r[k], "cpu") else r[k]) for k in ("wins_p0", "wins_p1", "draws")])
+            assert (got[variant].sum(axis=0) == rollouts).all()
+        for variant in ("auto", "pred5", "pred6"):
+            assert np.array_equal(got[variant], got["general"]), (n_roots, rollouts, variant)
+        o = O.playouts(roots[:n_roots], rollouts, SEED, first, root_index_base=5)
+        assert np.array_equal(got["auto"], np.stack([o["wins_p0"], o["wins_p1"], o["draws"]]))
+    options("playout_variant", 0)
+    options("playout_grab", 0)

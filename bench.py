@@ -39,10 +39,11 @@ UNIT = "playouts/s"
 PLAYOUTS_PER_STEP = 1 << 30
 SEED = 0x5155414E54494B31
 # Integer-op model (which replaces the SURVEY 8d estimate made before the
-# incremental formulation existed): 60 lane-ops per ply, of which 36 issue to the 64-lane ALU pipe
-# and 24 to the FMA-heavy pipe (IMAD; IMAD.WIDE counts double); 11.08 plies per empty-board playout;
-# 118 per visited perft leaf parent = 4.4 per counted node at depth 6; 304 per canonical key.
-OPS_PER_PLY, ALU_OPS_PER_PLY, PLIES_PER_PLAYOUT, OPS_PER_NODE, OPS_PER_KEY = 60.0, 36.0, 11.08, 2.5, 304.0
+# incremental formulation existed): 56 lane-ops per ply in the predicated formulation of round 2 (60 in round 1's
+# multiply-add formulation: the fraction at that count is reported beside it), of which 27 issue to the 64-lane ALU
+# pipe; 11.08 plies per empty-board playout; 2.5 per counted perft node at depth 6; 304 per canonical key.
+OPS_PER_PLY, ALU_OPS_PER_PLY, PLIES_PER_PLAYOUT, OPS_PER_NODE, OPS_PER_KEY = 56.0, 27.0, 11.08, 2.5, 304.0
+OPS_PER_PLY_ROUND1 = 60.0
 OPS_PER_PLAYOUT = OPS_PER_PLY * PLIES_PER_PLAYOUT
 
 
@@ -423,13 +424,14 @@ def main():
     nominal_peak = info["sm_count"] * 128 * sm_mhz * 1e6          # 4 schedulers x 32 lanes per SM-clock
     achieved = value / world * OPS_PER_PLAYOUT                    # per GPU
     roofline = {
-        "bound": "int_issue", "kernel": "k_playout_single<true> (config 1: one root, tallies only; k_playout<false,false> for many roots)",
+        "bound": "int_issue", "kernel": "k_playout_pred<4> (config 1: one root, tallies only; k_playout_pred_roots<4> for many roots)",
         "achieved": achieved / 1e12, "peak": nominal_peak / 1e12, "unit": "Tlane-op/s", "frac": achieved / nominal_peak,
         "traffic": (ncu or {}).get("dram_bytes_per_launch"),   # ncu --set full, see "ncu" below
         "model": f"{OPS_PER_PLY:.0f} int ops/ply x {PLIES_PER_PLAYOUT} plies/playout (DESIGN.md section 5); peak = SMs x 4 "
                  f"schedulers x 32 lanes x SM clock under load ({sm_mhz:.0f} MHz)",
         "peak_measured_lop3": peak_issue["alu"] / 1e12, "peak_measured_lop3_imad_mix": peak_issue["mixed"] / 1e12,
         "frac_of_measured_mix": achieved / peak_issue["mixed"] if peak_issue["mixed"] else None,
+        "frac_at_round1_op_count": achieved * OPS_PER_PLY_ROUND1 / OPS_PER_PLY / nominal_peak,
         "alu_pipe": {"ops_per_ply": ALU_OPS_PER_PLY, "achieved": value / world * PLIES_PER_PLAYOUT * ALU_OPS_PER_PLY / 1e12,
                      "peak_measured": peak_issue["alu"] / 1e12,
                      "frac": value / world * PLIES_PER_PLAYOUT * ALU_OPS_PER_PLY / peak_issue["alu"] if peak_issue["alu"] else None,

@@ -21,7 +21,7 @@ struct Ctx {
 
 // Tuning / testing switches (qk_set_option in include/quantik_b200.h).  Process-wide, 0 = the default
 // behaviour; the library never reads the environment.
-enum Option { OPT_PERFT_KERNEL = 0, OPT_PERFT_MIN_ITEMS, OPT_PERFT_TILE_GENERIC, OPT_PLAYOUT_VARIANT, OPT_DEDUP_MODE, OPT_DEDUP_PART_MB, OPT_PLAYOUT_GRAB, OPT_COUNT };
+enum Option { OPT_PERFT_KERNEL = 0, OPT_PERFT_MIN_ITEMS, OPT_PERFT_TILE_GENERIC, OPT_PLAYOUT_VARIANT, OPT_DEDUP_MODE, OPT_DEDUP_PART_MB, OPT_PLAYOUT_GRAB, OPT_GRID_WAVES, OPT_COUNT };
 long long option(Option o);
 
 void set_error(const std::string &msg);
@@ -67,7 +67,8 @@ private:
 inline unsigned grid_for(size_t n, unsigned block, int sms, unsigned per_sm)
 {
     size_t want = (n + block - 1) / block;
-    size_t cap = (size_t)sms * per_sm;
+    const long long waves = option(OPT_GRID_WAVES);
+    size_t cap = (size_t)sms * per_sm * (size_t)(waves > 0 ? waves : 16);   // 16 waves: CTAs finish at different times (unfair warp scheduling), later waves fill the gaps
     if (want < 1) want = 1;
     return (unsigned)(want < cap ? want : cap);
 }

@@ -11,6 +11,9 @@ sys.path.insert(0, os.path.join(ROOT, "quantik-core-py_b200"))
 import quantik_b200 as Q  # noqa: E402
 from quantik_b200 import batch as B  # noqa: E402
 
+for a in sys.argv[1:]:
+    if a.startswith("waves="):
+        Q._native.set_option("grid_waves", int(a[6:]))
 base = B.random_roots(1 << 20, min_plies=0, span=13, as_torch=True)
 states = base.repeat(64, 1)
 for cs in (False, True):

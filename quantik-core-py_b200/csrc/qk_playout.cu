@@ -280,14 +280,15 @@ __global__ void __launch_bounds__(kBlock, MIN_CTAS) k_playout_pred(const Playout
     }
     const uint32_t lut_addr = smem_addr(s_lut), root_addr = smem_addr(s_root);
     for (uint32_t i = threadIdx.x; i < QK_MOVE_LUT_BYTES / 4; i += kBlock) s_lut[i] = move_lut_image_word(i);
-    for (uint32_t i = threadIdx.x; i < 2048; i += kBlock) s_sel16[i] = (uint16_t)sel16_entry(i, lut_addr);
+    for (uint32_t i = threadIdx.x; i < 2048; i += kBlock) s_sel16[i] = (uint16_t)sel16_entry(i, lut_addr & 0xFFFFu);
     __syncthreads();
 #ifdef QK_PLAYOUT_TIMELINE
     const unsigned long long t_begin = globaltimer();
 #endif
     PredConsts pc;
     pc.sel_addr = smem_addr(s_sel16);
-    pc.col_lo = (threadIdx.x & 7u) * 16u; pc.col_hi = pc.col_lo + 4096u;
+    // (the byte table holds the low 16 bits of the entries' shared-memory addresses; the rest rides on the column offset)
+    pc.col_lo = (threadIdx.x & 7u) * 16u + (lut_addr & 0xFFFF0000u); pc.col_hi = pc.col_lo + 4096u;
     pc.one = a.one; pc.zero = a.zero;
 
     // Work is not dealt out in advance: the warp scheduler favours some warps of an SM over others (with equal shares
@@ -386,13 +387,15 @@ __global__ void __launch_bounds__(kBlock, MIN_CTAS) k_playout_pred_roots(const P
 {
     __shared__ __align__(128) uint32_t s_lut[QK_MOVE_LUT_BYTES / 4];
     __shared__ __align__(16) uint16_t s_sel16[2048];
+    __shared__ __align__(16) uint4 s_rec[3][kBlock];   // every lane's copy of its current root's record (free squares first)
     const uint32_t lut_addr = smem_addr(s_lut);
     for (uint32_t i = threadIdx.x; i < QK_MOVE_LUT_BYTES / 4; i += kBlock) s_lut[i] = move_lut_image_word(i);
-    for (uint32_t i = threadIdx.x; i < 2048; i += kBlock) s_sel16[i] = (uint16_t)sel16_entry(i, lut_addr);
+    for (uint32_t i = threadIdx.x; i < 2048; i += kBlock) s_sel16[i] = (uint16_t)sel16_entry(i, lut_addr & 0xFFFFu);
     __syncthreads();
     PredConsts pc;
     pc.sel_addr = smem_addr(s_sel16);
-    pc.col_lo = (threadIdx.x & 7u) * 16u; pc.col_hi = pc.col_lo + 4096u;
+    // (the byte table holds the low 16 bits of the entries' shared-memory addresses; the rest rides on the column offset)
+    pc.col_lo = (threadIdx.x & 7u) * 16u + (lut_addr & 0xFFFF0000u); pc.col_hi = pc.col_lo + 4096u;
     pc.one = a.one; pc.zero = a.zero;
 
     const uint32_t grab = a.grab, slices = (a.rollouts + grab - 1) / grab;     // slices per root
@@ -407,7 +410,7 @@ __global__ void __launch_bounds__(kBlock, MIN_CTAS) k_playout_pred_roots(const P
     uint32_t j = 0, jend = 0;               // next rollout of the current root this lane starts, one past its slice
     uint32_t root = 0, acc = 0, games = 0;  // current root, games of it won by its mover, games of it played
     bool a_is_p0 = true;
-    const uint4 *rp = reinterpret_cast<const uint4 *>(a.roots);
+    const uint32_t rec_addr = smem_addr(&s_rec[0][threadIdx.x]);
 
     PlayState st = {};
     uint32_t act = 0, block = 0;
@@ -425,8 +428,14 @@ __global__ void __launch_bounds__(kBlock, MIN_CTAS) k_playout_pred_roots(const P
                     acc = games = 0;
                     root = r;
                 }
-                rp = reinterpret_cast<const uint4 *>(a.roots + r);
-                const uint32_t flags = __ldg(&a.roots[r].flags);
+                // the record moves into the lane's shared-memory slot: the refills below then cost what they cost
+                // in the single-root kernel instead of three global loads each
+                const uint4 *rp = reinterpret_cast<const uint4 *>(a.roots + r);
+                uint4 r0 = __ldg(rp);
+                const uint4 r1 = __ldg(rp + 1), r2 = __ldg(rp + 2);
+                r0.x = ~r0.x;
+                s_rec[0][threadIdx.x] = r0; s_rec[1][threadIdx.x] = r1; s_rec[2][threadIdx.x] = r2;
+                const uint32_t flags = r2.w;
                 a_is_p0 = (flags & 1u) == 0;
                 const uint32_t len = a.rollouts - j0 < grab ? a.rollouts - j0 : grab;
                 const uint32_t immediate = (flags >> QK_ROOT_IMMEDIATE_SHIFT) & 3u;
@@ -445,17 +454,18 @@ __global__ void __launch_bounds__(kBlock, MIN_CTAS) k_playout_pred_roots(const P
             " .reg .b32 fl;\n"
             " setp.eq.u32 pi, %13, 0;\n"
             " setp.lt.and.u32 pr, %11, %14, pi;\n"
-            " @pr ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%15];\n"
-            " @pr ld.global.nc.v4.u32 {%4, %5, %6, %7}, [%15+16];\n"
-            " @pr ld.global.nc.v4.u32 {%8, %9, %10, fl}, [%15+32];\n"
-            " @pr not.b32 %0, %0;\n"
+            " @pr ld.shared.v4.u32 {%0, %1, %2, %3}, [%15];\n"
+            " @pr ld.shared.v4.u32 {%4, %5, %6, %7}, [%15+4096];\n"
+            " @pr ld.shared.v4.u32 {%8, %9, %10, fl}, [%15+8192];\n"
             " @pr add.u32 %11, %11, 1;\n"
             " @pr mov.b32 %12, 0;\n"
             " @pr mov.b32 %13, 0xFFFFFFFF;\n"
             "}\n"
             : "+r"(st.free2), "+r"(st.ra_lo), "+r"(st.ra_hi), "+r"(st.rb_lo), "+r"(st.rb_hi), "+r"(st.ta_lo), "+r"(st.ta_hi),
               "+r"(st.tb_lo), "+r"(st.tb_hi), "+r"(st.lp_lo), "+r"(st.lp_hi), "+r"(j), "+r"(block), "+r"(act)
-            : "r"(jend), "l"(rp));
+            : "r"(jend), "r"(rec_addr)
+            : "memory");
+        static_assert(kBlock * 16 == 4096, "the record planes' stride is spelled out in the PTX above");
         if (!__any_sync(kFull, act != 0u || qnext != kExhausted)) break;   // nobody plays, nobody can take another item
 
         // ---- one Philox block = four plies, roles alternate A B A B

@@ -3,6 +3,7 @@
 // k_part_insert's 50 us go.   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o insert_rate insert_rate.cu
 #include <cstdio>
 #include <cstdint>
+#include <cstdlib>
 #include <cuda_runtime.h>
 typedef unsigned long long u64;
 struct __align__(32) TSlot { u64 hi, lo, count, pad; };
@@ -58,9 +59,11 @@ __global__ void k_fill_keys(Slot *keys, unsigned per_block, unsigned cap, unsign
 {
     for (unsigned i = threadIdx.x; i < per_block; i += blockDim.x) keys[(size_t)blockIdx.x * cap + i] = make_key((blockIdx.x * per_block + i) % uniq);
 }
-int main()
+int main(int argc, char **argv)
 {
-    const unsigned blocks = 592, per_block = 1350, cap = 1600, uniq = 270000;
+    // insert_rate [inserts per block]: 1350 = the size of one part of qk_canon_dedup's two-level merge; larger values show
+    // the rate the table sustains once the kernel is long enough to amortise its launch and its first probes
+    const unsigned blocks = 592, per_block = argc > 1 ? (unsigned)atoi(argv[1]) : 1350, cap = per_block + 250, uniq = 270000;
     const uint32_t slots = 1200128;
     TSlot *table; cudaMalloc(&table, (size_t)slots * 32);
     Slot *keys; cudaMalloc(&keys, (size_t)blocks * cap * 16);
@@ -85,7 +88,7 @@ int main()
             cudaMemcpy(&h, claims, 8, cudaMemcpyDeviceToHost);
         }
         const char *names[6] = { "computed keys, batch 4", "loaded keys, batch 4", "loaded, batch 1", "loaded, batch 2", "loaded, batch 6", "loaded, batch 4, 2x blocks of half size" };
-        printf("%-42s %8.1f us   claims %llu\n", names[variant], best * 1e3, h);
+        printf("%-42s %8.1f us   claims %llu   %.3e inserts/s\n", names[variant], best * 1e3, h, (double)blocks * per_block / (best * 1e-3));
     }
     return 0;
 }

@@ -185,6 +185,68 @@ QK_HD void ply_step(PlayState &st, uint32_t rnd, const SquareLut *lut, const uin
     if (action) *action = (int)(off >> 4) + (odd ? 16 : 0) + (up ? 32 : 0);
 }
 
+// ---------------------------------------------------------------- tables of the predicated ply (ply_pred, below)
+struct __attribute__((aligned(16))) MoveLut { uint32_t scope_lo, scope_hi, lines_lo, lines_hi, bit2, l_lo, l_hi, pad; };
+// Shared-memory layout: two planes (entry words 0-3, words 4-7), each entry replicated into the eight 16-byte columns
+// of a 128-byte row; a lane reads column lane % 8, so a 128-bit load of 32 different entries is conflict-free
+// (four wavefronts, the minimum for 512 bytes) whatever the entries are.
+enum { QK_MOVE_LUT_ENTRIES = 65, QK_MOVE_LUT_PLANE = QK_MOVE_LUT_ENTRIES * 128, QK_MOVE_LUT_BYTES = 2 * QK_MOVE_LUT_PLANE,
+       QK_MOVE_LUT_BLOCKED_ROW = 4 * 1792 };
+// word `wi` of entry `entry` = square | lane << 4 | half << 5; entry 64 = "the mover is blocked"
+QK_HD uint32_t move_lut_word(uint32_t entry, uint32_t wi)
+{
+    if (entry >= 64u) return (wi == 2u || wi == 3u) ? 0x80008000u : 0u;
+    const SquareLut q = square_lut((int)(entry & 15u));
+    const uint32_t lane = (entry & 16u) ? 0xFFFF0000u : 0x0000FFFFu, hi = (entry >> 5) & 1u;
+    const uint32_t v[8] = { hi ? 0u : q.scope2 & lane, hi ? q.scope2 & lane : 0u, hi ? 0u : q.lines2 & lane,
+                            hi ? q.lines2 & lane : 0u, q.bit2, hi ? 0u : lane, hi ? lane : 0u, 0u };
+    return v[wi & 7u];
+}
+// 16-bit byte table for the predicated ply: shared-memory address of the move-table entry of the k-th set bit of a
+// byte in row 0 (the row offset, QK_MOVE_LUT_BLOCKED_ROW for the empty byte, is added by the ply)
+QK_HD uint32_t sel16_entry(uint32_t index, uint32_t lut_addr)
+{
+    if ((index >> 3) == 0u) return lut_addr + 64u * 128u - QK_MOVE_LUT_BLOCKED_ROW;
+    return lut_addr + 128u * kth_in_byte(index >> 3, index & 7u);
+}
+// 32-bit word `w` of the shared-memory image of the move table
+QK_HD uint32_t move_lut_image_word(uint32_t w)
+{
+    const uint32_t plane = w / (QK_MOVE_LUT_PLANE / 4u), rem = w % (QK_MOVE_LUT_PLANE / 4u);
+    return move_lut_word(rem / 32u, (rem & 3u) + 4u * plane);
+}
+
+// C++ restatement of ply_pred (below): the same tables, the same three-level descent, the same sign test -- what the PTX
+// computes, for the CPU test tier (tests/hostsim) and as the readable version of it.  `lut` = the shared-memory image
+// of the move table (move_lut_image_word), `sel16` = the byte table built for a table at address 0, `col` = the lane's
+// column offset.  role 0: role A moves.
+QK_HD void ply_pred_model(PlayState &st, int role, uint32_t rnd, const uint32_t *lut, const uint16_t *sel16, uint32_t col,
+                          uint32_t &act, uint32_t &acc)
+{
+    uint32_t &rm_lo = role ? st.rb_lo : st.ra_lo, &rm_hi = role ? st.rb_hi : st.ra_hi;   // mover
+    uint32_t &ro_lo = role ? st.ra_lo : st.rb_lo, &ro_hi = role ? st.ra_hi : st.rb_hi;   // other
+    uint32_t &tm_lo = role ? st.tb_lo : st.ta_lo, &tm_hi = role ? st.tb_hi : st.ta_hi;
+    const uint32_t ll = st.free2 & ~rm_lo, lh = st.free2 & ~rm_hi;
+    const uint32_t nl = (uint32_t)popc(ll), n = nl + (uint32_t)popc(lh);
+    uint32_t k = mulhi(rnd, n), w = ll, row = col;
+    if (k >= nl) { w = lh; row += 4096u; k -= nl; }                    // 64 -> 32
+    uint32_t c = (uint32_t)popc(w << 16);
+    if (k >= c) { w >>= 16; k -= c; row += 2048u; }                    // 32 -> 16
+    c = (uint32_t)popc(w << 24);
+    if (k >= c) { w >>= 8; k -= c; row += 1024u; }                     // 16 -> 8
+    const uint32_t at = (uint32_t)sel16[(w & 0xFFu) * 8u + k] + row;   // byte offset of the entry's first plane
+    const uint32_t *e0 = lut + at / 4u, *e1 = lut + (at + QK_MOVE_LUT_PLANE) / 4u;
+    ro_lo |= e0[0];            ro_hi |= e0[1];
+    rm_lo |= tm_lo & e1[1];    rm_hi |= tm_hi & e1[2];
+    tm_lo |= e1[1];            tm_hi |= e1[2];
+    st.lp_lo |= e0[2];         st.lp_hi |= e0[3];
+    st.free2 -= e1[0];
+    const uint32_t a4 = st.lp_lo & st.lp_hi;
+    const int32_t t = (int32_t)(a4 & (a4 << 16) & act);                // > 0: a line is complete, < 0: the mover was blocked
+    if (role == 0 ? t > 0 : t < 0) ++acc;                              // role A wins
+    if (t != 0) act = 0;
+}
+
 #ifdef __CUDACC__
 // ---------------------------------------------------------------- one ply, pipe-balanced (device only)
 // Same function as ply_step, different instruction selection.  On sm_100 LOP3 / SEL / ISETP / SHF /
@@ -280,36 +342,6 @@ __device__ __forceinline__ void ply_step_fma(PlayState &st, uint32_t rnd, const 
 // line, the mover of an odd ply makes A win by being blocked (beam_search.py:633-635,641-642).
 // A lane whose game is over keeps executing plies on a meaningless state until the next 4-ply boundary:
 // every quantity stays in range (k < popcount of the word it indexes), nothing is tallied (act == 0).
-struct __attribute__((aligned(16))) MoveLut { uint32_t scope_lo, scope_hi, lines_lo, lines_hi, bit2, l_lo, l_hi, pad; };
-// Shared-memory layout: two planes (entry words 0-3, words 4-7), each entry replicated into the eight 16-byte columns
-// of a 128-byte row; a lane reads column lane % 8, so a 128-bit load of 32 different entries is conflict-free
-// (four wavefronts, the minimum for 512 bytes) whatever the entries are.
-enum { QK_MOVE_LUT_ENTRIES = 65, QK_MOVE_LUT_PLANE = QK_MOVE_LUT_ENTRIES * 128, QK_MOVE_LUT_BYTES = 2 * QK_MOVE_LUT_PLANE,
-       QK_MOVE_LUT_BLOCKED_ROW = 4 * 1792 };
-// word `wi` of entry `entry` = square | lane << 4 | half << 5; entry 64 = "the mover is blocked"
-QK_HD uint32_t move_lut_word(uint32_t entry, uint32_t wi)
-{
-    if (entry >= 64u) return (wi == 2u || wi == 3u) ? 0x80008000u : 0u;
-    const SquareLut q = square_lut((int)(entry & 15u));
-    const uint32_t lane = (entry & 16u) ? 0xFFFF0000u : 0x0000FFFFu, hi = (entry >> 5) & 1u;
-    const uint32_t v[8] = { hi ? 0u : q.scope2 & lane, hi ? q.scope2 & lane : 0u, hi ? 0u : q.lines2 & lane,
-                            hi ? q.lines2 & lane : 0u, q.bit2, hi ? 0u : lane, hi ? lane : 0u, 0u };
-    return v[wi & 7u];
-}
-// 16-bit byte table for the predicated ply: shared-memory address of the move-table entry of the k-th set bit of a
-// byte in row 0 (the row offset, QK_MOVE_LUT_BLOCKED_ROW for the empty byte, is added by the ply)
-QK_HD uint32_t sel16_entry(uint32_t index, uint32_t lut_addr)
-{
-    if ((index >> 3) == 0u) return lut_addr + 64u * 128u - QK_MOVE_LUT_BLOCKED_ROW;
-    return lut_addr + 128u * kth_in_byte(index >> 3, index & 7u);
-}
-// 32-bit word `w` of the shared-memory image of the move table
-QK_HD uint32_t move_lut_image_word(uint32_t w)
-{
-    const uint32_t plane = w / (QK_MOVE_LUT_PLANE / 4u), rem = w % (QK_MOVE_LUT_PLANE / 4u);
-    return move_lut_word(rem / 32u, (rem & 3u) + 4u * plane);
-}
-
 // shared-memory address of the 16-bit byte table, the lane's column in the move table (+ the row offset of shapes C,D),
 // and the opaque 1 and 0
 struct PredConsts { uint32_t sel_addr, col_lo, col_hi, one, zero; };

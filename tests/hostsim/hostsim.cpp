@@ -92,5 +92,38 @@ void hs_playouts(const uint16_t *roots, size_t n_roots, uint32_t rollouts, uint6
         }
     }
 }
+// the same playouts through the C++ model of the predicated ply (move table image, 16-bit byte table, blocked entry, sign
+// test) that k_playout_pred runs in PTX; outcome from player 0's point of view, no cut-off
+void hs_playouts_pred(const uint16_t *roots, size_t n_roots, uint32_t rollouts, uint64_t seed, uint64_t first, uint32_t root_base,
+                      int8_t *outcome, uint8_t *slots)
+{
+    static uint32_t lut[QK_MOVE_LUT_BYTES / 4];
+    static uint16_t sel16[2048];
+    for (uint32_t i = 0; i < QK_MOVE_LUT_BYTES / 4; ++i) lut[i] = move_lut_image_word(i);
+    for (uint32_t i = 0; i < 2048; ++i) sel16[i] = (uint16_t)sel16_entry(i, 0u);
+    for (size_t r = 0; r < n_roots; ++r) {
+        const RootRec rec = make_root(ld(roots + 8 * r));
+        const uint32_t immediate = (rec.flags >> QK_ROOT_IMMEDIATE_SHIFT) & 3u;
+        const bool a_is_p0 = (rec.flags & 1u) == 0;
+        for (uint32_t j = 0; j < rollouts; ++j) {
+            int res = 0, n_slots = 0;
+            if (immediate) res = immediate == 1 ? 1 : -1;
+            else {
+                PlayState st = load_play_state(rec);
+                uint32_t act = 0xFFFFFFFFu, acc = 0;
+                const uint32_t col = (uint32_t)((r + j) & 7u) * 16u;               // any column must do
+                Philox4 rnd = { { 0, 0, 0, 0 } };
+                for (int ply = 0; act; ++ply) {
+                    if ((ply & 3) == 0) rnd = stream_block(seed, first + j, root_base + (uint32_t)r, (uint32_t)(ply >> 2));
+                    ply_pred_model(st, ply & 1, rnd.v[ply & 3], lut, sel16, col, act, acc);
+                    ++n_slots;
+                }
+                res = (acc != 0) == a_is_p0 ? 1 : -1;
+            }
+            outcome[r * rollouts + j] = (int8_t)res;
+            slots[r * rollouts + j] = (uint8_t)n_slots;
+        }
+    }
+}
 #endif
 }

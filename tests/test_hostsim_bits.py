@@ -98,6 +98,29 @@ def test_playout_step_vs_reference_rules(hs):
         assert np.array_equal(oc[0], p[f"cut{mp}_outcome"]) and np.array_equal(pl[0], p[f"cut{mp}_plies"])
 
 
+def test_predicated_ply_model_vs_reference_rules(hs):
+    """The ply k_playout_pred runs in PTX, restated in C++ on the same tables (move-table image, 16-bit byte table, the
+    "blocked" 65th entry, the sign test): the reference's outcomes under the shared stream, playout for playout."""
+    p = np.load(os.path.join(G, "playouts_philox.npz"))
+    seed = int(p["seed"])
+
+    def run(roots, R, first, base):
+        oc, sl = np.zeros((len(roots), R), np.int8), np.zeros((len(roots), R), np.uint8)
+        hs.hs_playouts_pred(P(roots), ctypes.c_size_t(len(roots)), ctypes.c_uint32(R), ctypes.c_uint64(seed),
+                            ctypes.c_uint64(first), ctypes.c_uint32(base), P(oc), P(sl))
+        return oc, sl
+
+    oc, sl = run(np.zeros((1, 8), np.uint16), len(p["empty_outcome"]), 0, 0)
+    assert np.array_equal(oc[0], p["empty_outcome"])
+    extra = sl[0].astype(int) - p["empty_plies"].astype(int)            # a blocked mover takes a slot but makes no move
+    assert set(np.unique(extra)) <= {0, 1} and (extra == 1).any()
+    r = np.ascontiguousarray(p["roots"])
+    oc, sl = run(r, p["roots_outcome"].shape[1], int(p["roots_first_rollout"]), int(p["roots_index_base"]))
+    assert np.array_equal(oc, p["roots_outcome"])
+    extra = sl.astype(int) - p["roots_plies"].astype(int)
+    assert set(np.unique(extra)) <= {0, 1}
+
+
 def test_leaf_parent_bulk_counts(hs):
     d = np.load(os.path.join(G, "states_reference.npz"))
     nv = int(d["n_valid"])

@@ -382,7 +382,9 @@ namespace qk {
 // ply and the same queue, whose items are (root, slice of `grab` rollouts) -- a lane's range never straddles two roots,
 // so the root's record address, its index in the random stream and the tallies' destination change only in the
 // rarely taken range switch; a root that is already decided is accounted for there without being played.
-template <int MIN_CTAS>
+// GENERAL adds what only some callers need, at a few instructions per ply: the MCTS cut-off after max_plies moves (a draw,
+// tested before the win: mcts.py:412,436-437) and per-playout outcomes / lengths.
+template <int MIN_CTAS, bool GENERAL>
 __global__ void __launch_bounds__(kBlock, MIN_CTAS) k_playout_pred_roots(const PlayoutArgs a)
 {
     __shared__ __align__(128) uint32_t s_lut[QK_MOVE_LUT_BYTES / 4];
@@ -409,6 +411,8 @@ __global__ void __launch_bounds__(kBlock, MIN_CTAS) k_playout_pred_roots(const P
     }
     uint32_t j = 0, jend = 0;               // next rollout of the current root this lane starts, one past its slice
     uint32_t root = 0, acc = 0, games = 0;  // current root, games of it won by its mover, games of it played
+    uint32_t accd = 0, moves = 0;           // GENERAL: games of it cut off (draws); moves made in the game in flight
+    const bool cutoff = GENERAL && a.max_plies >= 0;
     bool a_is_p0 = true;
     const uint32_t rec_addr = smem_addr(&s_rec[0][threadIdx.x]);
 
@@ -424,8 +428,15 @@ __global__ void __launch_bounds__(kBlock, MIN_CTAS) k_playout_pred_roots(const P
                 qnext = atomicAdd(a.queue, 1u);
                 const uint32_t r = q / slices, j0 = (q - r * slices) * grab;
                 if (r != root) {
-                    flush_tallies(a, root, games, a_is_p0 ? acc : games - acc, 0u);
-                    acc = games = 0;
+                    if (slices == 1u) {     // this lane played every rollout of the root: plain stores, nobody else adds
+                        if (games) {
+                            const uint32_t p0 = a_is_p0 ? acc : games - acc - accd;
+                            if (a.wins_p0) a.wins_p0[root] = p0;
+                            if (a.wins_p1) a.wins_p1[root] = games - p0 - accd;
+                            if (a.draws) a.draws[root] = accd;
+                        }
+                    } else flush_tallies(a, root, games, a_is_p0 ? acc : games - acc - accd, accd);
+                    acc = games = accd = 0;
                     root = r;
                 }
                 // the record moves into the lane's shared-memory slot: the refills below then cost what they cost
@@ -441,8 +452,19 @@ __global__ void __launch_bounds__(kBlock, MIN_CTAS) k_playout_pred_roots(const P
                 const uint32_t immediate = (flags >> QK_ROOT_IMMEDIATE_SHIFT) & 3u;
                 games += len;
                 j = j0; jend = j0 + len;
-                if (immediate) {            // decided at the root: that result for the whole slice, nothing to play
+                if (cutoff && a.max_plies == 0) {           // nothing may be played: draws (the cut-off comes first)
+                    accd += len;
+                    if (GENERAL) for (uint32_t i = j0; i < j0 + len; ++i) {
+                        if (a.per_playout) a.per_playout[(size_t)r * a.rollouts + i] = 0;
+                        if (a.per_plies) a.per_plies[(size_t)r * a.rollouts + i] = 0;
+                    }
+                    j = jend;
+                } else if (immediate) {     // decided at the root: that result for the whole slice, nothing to play
                     acc += ((immediate == 1) == a_is_p0) ? len : 0u;
+                    if (GENERAL) for (uint32_t i = j0; i < j0 + len; ++i) {
+                        if (a.per_playout) a.per_playout[(size_t)r * a.rollouts + i] = immediate == 1 ? 1 : -1;
+                        if (a.per_plies) a.per_plies[(size_t)r * a.rollouts + i] = 0;
+                    }
                     j = jend;
                 }
             }
@@ -471,12 +493,40 @@ __global__ void __launch_bounds__(kBlock, MIN_CTAS) k_playout_pred_roots(const P
         // ---- one Philox block = four plies, roles alternate A B A B
         const Philox4 rnd = stream_block(a.seed, rollout_base + j, a.root_index_base + root, block);
         ++block;
-        ply_pred<0>(st, rnd.v[0], pc, act, acc);
-        ply_pred<1>(st, rnd.v[1], pc, act, acc);
-        ply_pred<0>(st, rnd.v[2], pc, act, acc);
-        ply_pred<1>(st, rnd.v[3], pc, act, acc);
+        if (!GENERAL) {
+            ply_pred<0>(st, rnd.v[0], pc, act, acc);
+            ply_pred<1>(st, rnd.v[1], pc, act, acc);
+            ply_pred<0>(st, rnd.v[2], pc, act, acc);
+            ply_pred<1>(st, rnd.v[3], pc, act, acc);
+        } else {
+            if (block == 1u) moves = 0;                   // (a game starts with its first block)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (q & 1) ply_pred_move<1>(st, rnd.v[q], pc); else ply_pred_move<0>(st, rnd.v[q], pc);
+                const int32_t t = ply_pred_outcome(st, act);
+                if (act) {
+                    moves += t >= 0;                       // a blocked mover makes no move
+                    const bool cut = cutoff && t >= 0 && moves >= (uint32_t)a.max_plies;
+                    if (cut || t != 0) {
+                        const bool a_wins = !cut && ((q & 1) ? t < 0 : t > 0);
+                        acc += a_wins; accd += cut;
+                        const size_t o = (size_t)root * a.rollouts + (j - 1);
+                        if (a.per_playout) a.per_playout[o] = (int8_t)(cut ? 0 : (a_wins == a_is_p0 ? 1 : -1));
+                        if (a.per_plies) a.per_plies[o] = (uint8_t)moves;
+                        act = 0;
+                    }
+                }
+            }
+        }
     }
-    flush_tallies(a, root, games, a_is_p0 ? acc : games - acc, 0u);
+    if (slices == 1u) {
+        if (games) {
+            const uint32_t p0 = a_is_p0 ? acc : games - acc - accd;
+            if (a.wins_p0) a.wins_p0[root] = p0;
+            if (a.wins_p1) a.wins_p1[root] = games - p0 - accd;
+            if (a.draws) a.draws[root] = accd;
+        }
+    } else flush_tallies(a, root, games, a_is_p0 ? acc : games - acc - accd, accd);
 }
 
 size_t playout_scratch_bytes(size_t n_roots) { return n_roots * sizeof(RootRec) + 16; }   // + the work-queue counter
@@ -507,7 +557,7 @@ int launch_playouts(const uint4 *roots, size_t n_roots, uint32_t rollouts, uint6
     const long long v = option(OPT_PLAYOUT_VARIANT);
     const bool queue_fits = a.total <= 0xFFFFFFFFull - (1ull << 27);
     bool pred = false, pred_roots = false;
-    if (n_roots == 1 && !cutoff && !pp && queue_fits) {
+    if (n_roots == 1 && !cutoff && !pp && queue_fits && v != 2) {
         pred = true;
         if (v == 0 || v == 5) kernel = k_playout_pred<4>;
         else if (v == 3) kernel = k_playout_pred<5>;
@@ -517,9 +567,13 @@ int launch_playouts(const uint4 *roots, size_t n_roots, uint32_t rollouts, uint6
             if (v == 1) kernel = k_playout_single<false>;
             else if (v == 6) kernel = k_playout_single<true>;
         }
-    } else if (!cutoff && !pp && queue_fits && v != 2 && rollouts >= 8) {
+    } else if (queue_fits && v != 2 && (rollouts < 4 || rollouts >= 32 || v != 0)) {
+        // (between 4 and 31 rollouts per root the range switch -- a divergent path with three global loads -- comes too
+        // often: 2^20 roots x 16: 2.7e10 playouts/s against 3.3e10 for round 1's kernel, which refills from global memory
+        // at every game anyway; x 1: 1.0e10 against 4.6e9, x 1024: 5.2e10 against 3.3e10)
         pred_roots = true;
-        kernel = v == 3 ? k_playout_pred_roots<5> : v == 4 ? k_playout_pred_roots<6> : k_playout_pred_roots<4>;
+        if (!cutoff && !pp) kernel = v == 3 ? k_playout_pred_roots<5, false> : v == 4 ? k_playout_pred_roots<6, false> : k_playout_pred_roots<4, false>;
+        else kernel = k_playout_pred_roots<4, true>;
     }
     // persistent grid: exactly as many CTAs as are resident at once (no second wave), fewer only
     // when there are not enough playouts to give each thread one

@@ -347,8 +347,9 @@ __device__ __forceinline__ void ply_step_fma(PlayState &st, uint32_t rnd, const 
 struct PredConsts { uint32_t sel_addr, col_lo, col_hi, one, zero; };
 
 // lut / sel16 live in shared memory; ROLE 0: role A moves
+// the move itself: pick + state update
 template <int ROLE>
-__device__ __forceinline__ void ply_pred(PlayState &st, uint32_t rnd, const PredConsts &pc, uint32_t &act, uint32_t &acc)
+__device__ __forceinline__ void ply_pred_move(PlayState &st, uint32_t rnd, const PredConsts &pc)
 {
     uint32_t &rm_lo = ROLE ? st.rb_lo : st.ra_lo, &rm_hi = ROLE ? st.rb_hi : st.ra_hi;   // mover
     uint32_t &ro_lo = ROLE ? st.ra_lo : st.rb_lo, &ro_hi = ROLE ? st.ra_hi : st.rb_hi;   // other
@@ -397,6 +398,18 @@ __device__ __forceinline__ void ply_pred(PlayState &st, uint32_t rnd, const Pred
     tm_lo |= e1y;              tm_hi |= e1z;
     st.lp_lo |= e0z;           st.lp_hi |= e0w;           // lines that now contain the shape
     st.free2 -= e1x;                                      // square no longer free
+}
+// > 0: the move completed a line (has_winning_line), < 0: there was no move, the mover is blocked; 0 otherwise and
+// whenever the lane has no game running
+__device__ __forceinline__ int32_t ply_pred_outcome(const PlayState &st, uint32_t act)
+{
+    const uint32_t a4 = st.lp_lo & st.lp_hi;
+    return (int32_t)(a4 & (a4 << 16) & act);
+}
+template <int ROLE>
+__device__ __forceinline__ void ply_pred(PlayState &st, uint32_t rnd, const PredConsts &pc, uint32_t &act, uint32_t &acc)
+{
+    ply_pred_move<ROLE>(st, rnd, pc);
     // has_winning_line (a line holding all four shapes) or blocked (the sign bit), while the game runs
     if (ROLE == 0)
         asm("{\n"

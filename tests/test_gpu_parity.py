@@ -845,5 +845,17 @@ def test_many_roots_tally_kernel_matches_general_kernel_and_oracle(options):
             assert np.array_equal(got[variant], got["general"]), (n_roots, rollouts, variant)
         o = O.playouts(roots[:n_roots], rollouts, SEED, first, root_index_base=5)
         assert np.array_equal(got["auto"], np.stack([o["wins_p0"], o["wins_p1"], o["draws"]]))
+    # the cut-off and the per-playout outputs run the same kernel with a few more instructions per ply
+    for n_roots, rollouts, mp, grab in ((300, 37, -1, 0), (300, 37, 0, 0), (300, 37, 3, 5), (300, 64, 7, 0), (40, 500, 16, 0), (300, 1, 9, 0)):
+        got = {}
+        for variant in ("general", "auto"):
+            options("playout_variant", {"auto": 0, "general": 2}[variant])
+            options("playout_grab", grab)
+            r = B.playouts(roots[:n_roots], rollouts, SEED, max_plies=mp, first_rollout=3, root_index_base=1, per_playout=True)
+            got[variant] = [np.asarray(r[k].cpu() if hasattr(r[k], "cpu") else r[k]) for k in ("wins_p0", "wins_p1", "draws", "outcome", "plies")]
+        o = O.playouts(roots[:n_roots], rollouts, SEED, 3, root_index_base=1, max_plies=mp, per_playout=True)
+        for i, k in enumerate(("wins_p0", "wins_p1", "draws", "outcome", "plies")):
+            assert np.array_equal(got["auto"][i], got["general"][i]), (n_roots, rollouts, mp, k)
+            assert np.array_equal(got["auto"][i].reshape(np.asarray(o[k]).shape), o[k]), (n_roots, rollouts, mp, k, "oracle")
     options("playout_variant", 0)
     options("playout_grab", 0)

@@ -256,6 +256,23 @@ __global__ void QK_PLAYOUT_BOUNDS k_playout_single(const PlayoutArgs a)
 // the all-ones / zero word `act`, and the tallies are one counter (games won by the root's mover; the number of
 // games a thread plays is known in advance).
 __device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// A value the compiler keeps in a register instead of recomputing it where it is used (shared-memory addresses cost
+// an S2R + LEA each time otherwise -- five instructions per loop iteration of the playout kernels): it comes back
+// from a volatile shared-memory load.
+// The queue's atomic in PTX: written as atomicAdd() the compiler aggregates it over the lanes of the warp that take a
+// range in the same iteration and then needs the result at once (a shuffle from the leader) -- the whole warp would
+// wait for the atomic's round trip, which taking a range one range ahead is meant to hide.
+__device__ __forceinline__ uint32_t queue_take(uint32_t *queue, uint32_t n)
+{
+    uint32_t old;
+    asm volatile("atom.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(queue), "r"(n) : "memory");
+    return old;
+}
+__device__ __forceinline__ uint32_t pinned_value(volatile uint32_t *slot, uint32_t v)
+{
+    *slot = v;
+    return *slot;
+}
 
 #ifdef QK_PLAYOUT_TIMELINE      // experiment build (scripts/playout_timeline.py): when does each warp start and finish?
 __device__ unsigned long long g_timeline[4 * 16384];
@@ -278,7 +295,8 @@ __global__ void __launch_bounds__(kBlock, MIN_CTAS) k_playout_pred(const Playout
         if (threadIdx.x == 0) v.x = ~v.x;          // occupied -> free squares
         s_root[threadIdx.x] = v;
     }
-    const uint32_t lut_addr = smem_addr(s_lut), root_addr = smem_addr(s_root);
+    __shared__ uint32_t s_pin[2 * kBlock];
+    const uint32_t lut_addr = smem_addr(s_lut), root_addr = pinned_value(&s_pin[threadIdx.x], smem_addr(s_root));
     for (uint32_t i = threadIdx.x; i < QK_MOVE_LUT_BYTES / 4; i += kBlock) s_lut[i] = move_lut_image_word(i);
     for (uint32_t i = threadIdx.x; i < 2048; i += kBlock) s_sel16[i] = (uint16_t)sel16_entry(i, lut_addr & 0xFFFFu);
     __syncthreads();
@@ -286,7 +304,7 @@ __global__ void __launch_bounds__(kBlock, MIN_CTAS) k_playout_pred(const Playout
     const unsigned long long t_begin = globaltimer();
 #endif
     PredConsts pc;
-    pc.sel_addr = smem_addr(s_sel16);
+    pc.sel_addr = pinned_value(&s_pin[kBlock + threadIdx.x], smem_addr(s_sel16));
     // (the byte table holds the low 16 bits of the entries' shared-memory addresses; the rest rides on the column offset)
     pc.col_lo = (threadIdx.x & 7u) * 16u + (lut_addr & 0xFFFF0000u); pc.col_hi = pc.col_lo + 4096u;
     pc.one = a.one; pc.zero = a.zero;
@@ -297,8 +315,8 @@ __global__ void __launch_bounds__(kBlock, MIN_CTAS) k_playout_pred(const Playout
     // holding its current range [jn, jend) and the start of its next one (taken ahead of time, so that the atomic's
     // latency is never waited for).
     const uint32_t total = (uint32_t)a.total, grab = a.grab;
-    constexpr uint32_t kExhausted = 0xFFFFFFFFu;
     uint32_t jn, jend, jnext;              // next playout this lane starts, one past its range, its next range
+                                           // (a lane that found the queue empty keeps jn > jend: nothing to start, nothing to take)
     {
         uint32_t base = 0;
         if ((threadIdx.x & 31u) == 0) base = atomicAdd(a.queue, 64u * grab);
@@ -306,16 +324,16 @@ __global__ void __launch_bounds__(kBlock, MIN_CTAS) k_playout_pred(const Playout
         jn = base + (threadIdx.x & 31u) * grab;
         jnext = jn + 32u * grab;
         jend = jn + grab < total ? jn + grab : total;
-        if (jn >= total) { jn = jend = 0; jnext = kExhausted; }
+        if (jn >= total) { jn = 1; jend = 0; }
     }
     const uint32_t flags = s_root[2].w;
     const bool a_is_p0 = (flags & 1u) == 0;
     const uint32_t immediate = (flags >> QK_ROOT_IMMEDIATE_SHIFT) & 3u;
-    uint32_t acc = 0, games = jend - jn;   // games won by role A, games played (every game that is started is finished)
+    uint32_t acc = 0, games = jn < jend ? jend - jn : 0u;   // games won by role A, games played (every game that is started is finished)
     if (immediate) {                       // the root is decided: every playout is that result (mcts.py:412 order)
         games = (blockIdx.x == 0 && threadIdx.x == 0) ? total : 0u;
         acc = ((immediate == 1) == a_is_p0) ? games : 0u;
-        jn = jend = 0; jnext = kExhausted;
+        jn = 1; jend = 0;
     }
 
     PlayState st = {};
@@ -323,12 +341,12 @@ __global__ void __launch_bounds__(kBlock, MIN_CTAS) k_playout_pred(const Playout
     const uint64_t rollout_base = a.first_rollout - 1;     // the game in flight is playout jn - 1
     for (;;) {
         // ---- a lane that has used up its range moves on to the one it holds in reserve and reserves another
-        if (act == 0u && jn == jend && jnext != kExhausted) {
+        if ((act | (jn ^ jend)) == 0u) {
             jn = jnext;
-            if (jn >= total) { jn = jend = 0; jnext = kExhausted; }
+            if (jn >= total) { jn = 1; jend = 0; }
             else {
                 jend = jn + grab < total ? jn + grab : total;
-                jnext = atomicAdd(a.queue, grab);
+                jnext = queue_take(a.queue, grab);
                 games += jend - jn;
             }
         }
@@ -395,7 +413,8 @@ __global__ void __launch_bounds__(kBlock, MIN_CTAS) k_playout_pred_roots(const P
     for (uint32_t i = threadIdx.x; i < 2048; i += kBlock) s_sel16[i] = (uint16_t)sel16_entry(i, lut_addr & 0xFFFFu);
     __syncthreads();
     PredConsts pc;
-    pc.sel_addr = smem_addr(s_sel16);
+    __shared__ uint32_t s_pin[2 * kBlock];
+    pc.sel_addr = pinned_value(&s_pin[threadIdx.x], smem_addr(s_sel16));
     // (the byte table holds the low 16 bits of the entries' shared-memory addresses; the rest rides on the column offset)
     pc.col_lo = (threadIdx.x & 7u) * 16u + (lut_addr & 0xFFFF0000u); pc.col_hi = pc.col_lo + 4096u;
     pc.one = a.one; pc.zero = a.zero;
@@ -414,7 +433,7 @@ __global__ void __launch_bounds__(kBlock, MIN_CTAS) k_playout_pred_roots(const P
     uint32_t accd = 0, moves = 0;           // GENERAL: games of it cut off (draws); moves made in the game in flight
     const bool cutoff = GENERAL && a.max_plies >= 0;
     bool a_is_p0 = true;
-    const uint32_t rec_addr = smem_addr(&s_rec[0][threadIdx.x]);
+    const uint32_t rec_addr = pinned_value(&s_pin[kBlock + threadIdx.x], smem_addr(&s_rec[0][threadIdx.x]));
 
     PlayState st = {};
     uint32_t act = 0, block = 0;
@@ -425,7 +444,7 @@ __global__ void __launch_bounds__(kBlock, MIN_CTAS) k_playout_pred_roots(const P
             const uint32_t q = qnext;
             if (q >= items) qnext = kExhausted;
             else {
-                qnext = atomicAdd(a.queue, 1u);
+                qnext = queue_take(a.queue, 1u);
                 const uint32_t r = q / slices, j0 = (q - r * slices) * grab;
                 if (r != root) {
                     if (slices == 1u) {     // this lane played every rollout of the root: plain stores, nobody else adds

@@ -375,9 +375,9 @@ def main():
         D.sharded_symmetry_table(16, device=dev)
         rows_n, t_nccl = timed_job(lambda: D.sharded_symmetry_table(16, device=dev))
         assert rows_n == one_rows, "NCCL partitioned BFS differs from the single-GPU table"
-        # (2) global canonical dedup: every rank holds 2^22 symmetric images of mid-game positions
+        # (2) global canonical dedup: every rank holds 2^24 symmetric images of mid-game positions
         import itertools
-        n_img = 1 << 22
+        n_img = 1 << 24                                   # the size of the single-GPU canon_dedup metric below
         pos = B.random_roots(n_img, first=rank * n_img, min_plies=3, span=6, device=dev)
         table = np.array([B.encode_transform(d4_, False, perm) for perm in itertools.permutations(range(4)) for d4_ in range(8)], np.uint16)
         codes = table[((np.arange(n_img, dtype=np.uint64) * np.uint64(2654435761) + np.uint64(rank)) % np.uint64(192)).astype(np.int64)]

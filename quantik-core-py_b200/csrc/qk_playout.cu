@@ -256,9 +256,6 @@ __global__ void QK_PLAYOUT_BOUNDS k_playout_single(const PlayoutArgs a)
 // the all-ones / zero word `act`, and the tallies are one counter (games won by the root's mover; the number of
 // games a thread plays is known in advance).
 __device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-// A value the compiler keeps in a register instead of recomputing it where it is used (shared-memory addresses cost
-// an S2R + LEA each time otherwise -- five instructions per loop iteration of the playout kernels): it comes back
-// from a volatile shared-memory load.
 // The queue's atomic in PTX: written as atomicAdd() the compiler aggregates it over the lanes of the warp that take a
 // range in the same iteration and then needs the result at once (a shuffle from the leader) -- the whole warp would
 // wait for the atomic's round trip, which taking a range one range ahead is meant to hide.
@@ -268,6 +265,9 @@ __device__ __forceinline__ uint32_t queue_take(uint32_t *queue, uint32_t n)
     asm volatile("atom.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(queue), "r"(n) : "memory");
     return old;
 }
+// A value the compiler keeps in a register instead of recomputing it where it is used (shared-memory addresses cost
+// an S2R + LEA each time otherwise -- five instructions per loop iteration of the playout kernels): it comes back
+// from a volatile shared-memory load.
 __device__ __forceinline__ uint32_t pinned_value(volatile uint32_t *slot, uint32_t v)
 {
     *slot = v;
@@ -329,7 +329,7 @@ __global__ void __launch_bounds__(kBlock, MIN_CTAS) k_playout_pred(const Playout
     const uint32_t flags = s_root[2].w;
     const bool a_is_p0 = (flags & 1u) == 0;
     const uint32_t immediate = (flags >> QK_ROOT_IMMEDIATE_SHIFT) & 3u;
-    uint32_t acc = 0, games = jn < jend ? jend - jn : 0u;   // games won by role A, games played (every game that is started is finished)
+    uint32_t acc = 0, games = jn < jend ? jend - jn : 0u;   // games won by role A; games played (each one started is finished)
     if (immediate) {                       // the root is decided: every playout is that result (mcts.py:412 order)
         games = (blockIdx.x == 0 && threadIdx.x == 0) ? total : 0u;
         acc = ((immediate == 1) == a_is_p0) ? games : 0u;

@@ -15,7 +15,7 @@ for label, kw in (("cut-off 16", dict(max_plies=16)), ("cut-off 6", dict(max_pli
         dt = (time.perf_counter() - t0) / 3
         print(f"{label:12s} variant {variant}: {65536 * 1024 / dt:.4e} playouts/s draws {float(r['draws'].sum()) / (65536 * 1024):.4f}", flush=True)
 small = B.random_roots(1 << 20, seed=5, min_plies=4, span=8, as_torch=True)
-for variant in (2, 0):
+for variant in (2, 0, 5):
     Q._native.set_option("playout_variant", variant)
     for rollouts in (1, 4, 16):
         B.playouts(small, rollouts)

@@ -439,8 +439,11 @@ __global__ void __launch_bounds__(kBlock, MIN_CTAS) k_playout_pred_roots(const P
     uint32_t act = 0, block = 0;
     const uint64_t rollout_base = a.first_rollout - 1;     // the game in flight is rollout j - 1
     for (;;) {
-        // ---- a lane that has used up its slice takes the item it holds in reserve and reserves another
-        if (act == 0u && j == jend && qnext != kExhausted) {
+        // ---- the lanes of a warp move on to their next items TOGETHER, when none of them has a game left to play or to
+        //      start: the switch is a long divergent path, and taken lane by lane -- 30 % of all iterations, with one or
+        //      two lanes in it -- it was 18 % of the executed instructions of config 4 (profiles/r02l_cfg4_playout_ncu);
+        //      a lane now waits for the slowest lane's slice instead, 0.41 / sqrt(slice length) of its time (5 % at 64)
+        if (!__any_sync(kFull, act != 0u || j != jend) && qnext != kExhausted) {
             const uint32_t q = qnext;
             if (q >= items) qnext = kExhausted;
             else {

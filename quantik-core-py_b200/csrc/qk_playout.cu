@@ -288,7 +288,7 @@ template <int MIN_CTAS>
 __global__ void __launch_bounds__(kBlock, MIN_CTAS) k_playout_pred(const PlayoutArgs a)
 {
     __shared__ __align__(128) uint32_t s_lut[QK_MOVE_LUT_BYTES / 4];
-    __shared__ __align__(16) uint16_t s_sel16[2048];
+    __shared__ uint8_t s_sel8r[4096];       // the byte table is the 2 KB-aligned half of it: the ply ORs (address / 8) into the index
     __shared__ __align__(16) uint4 s_root[3];
     if (threadIdx.x < 3) {
         uint4 v = __ldg(reinterpret_cast<const uint4 *>(a.roots) + threadIdx.x);
@@ -297,16 +297,16 @@ __global__ void __launch_bounds__(kBlock, MIN_CTAS) k_playout_pred(const Playout
     }
     __shared__ uint32_t s_pin[2 * kBlock];
     const uint32_t lut_addr = smem_addr(s_lut), root_addr = pinned_value(&s_pin[threadIdx.x], smem_addr(s_root));
+    const uint32_t sel_off = (0u - smem_addr(s_sel8r)) & 2047u;
     for (uint32_t i = threadIdx.x; i < QK_MOVE_LUT_BYTES / 4; i += kBlock) s_lut[i] = move_lut_image_word(i);
-    for (uint32_t i = threadIdx.x; i < 2048; i += kBlock) s_sel16[i] = (uint16_t)sel16_entry(i, lut_addr & 0xFFFFu);
+    for (uint32_t i = threadIdx.x; i < 2048; i += kBlock) s_sel8r[sel_off + i] = (uint8_t)sel8_row(i);
     __syncthreads();
 #ifdef QK_PLAYOUT_TIMELINE
     const unsigned long long t_begin = globaltimer();
 #endif
     PredConsts pc;
-    pc.sel_addr = pinned_value(&s_pin[kBlock + threadIdx.x], smem_addr(s_sel16));
-    // (the byte table holds the low 16 bits of the entries' shared-memory addresses; the rest rides on the column offset)
-    pc.col_lo = (threadIdx.x & 7u) * 16u + (lut_addr & 0xFFFF0000u); pc.col_hi = pc.col_lo + 4096u;
+    pc.sel_addr8 = pinned_value(&s_pin[kBlock + threadIdx.x], (smem_addr(s_sel8r) + sel_off) >> 3);
+    pc.col_lo = (threadIdx.x & 7u) * 16u + lut_addr; pc.col_hi = pc.col_lo + 4096u;
     pc.one = a.one; pc.zero = a.zero;
 
     // Work is not dealt out in advance: the warp scheduler favours some warps of an SM over others (with equal shares
@@ -406,17 +406,16 @@ template <int MIN_CTAS, bool GENERAL>
 __global__ void __launch_bounds__(kBlock, MIN_CTAS) k_playout_pred_roots(const PlayoutArgs a)
 {
     __shared__ __align__(128) uint32_t s_lut[QK_MOVE_LUT_BYTES / 4];
-    __shared__ __align__(16) uint16_t s_sel16[2048];
+    __shared__ uint8_t s_sel8r[4096];       // the byte table is the 2 KB-aligned half of it: the ply ORs (address / 8) into the index
     __shared__ __align__(16) uint4 s_rec[3][kBlock];   // every lane's copy of its current root's record (free squares first)
-    const uint32_t lut_addr = smem_addr(s_lut);
+    const uint32_t lut_addr = smem_addr(s_lut), sel_off = (0u - smem_addr(s_sel8r)) & 2047u;
     for (uint32_t i = threadIdx.x; i < QK_MOVE_LUT_BYTES / 4; i += kBlock) s_lut[i] = move_lut_image_word(i);
-    for (uint32_t i = threadIdx.x; i < 2048; i += kBlock) s_sel16[i] = (uint16_t)sel16_entry(i, lut_addr & 0xFFFFu);
+    for (uint32_t i = threadIdx.x; i < 2048; i += kBlock) s_sel8r[sel_off + i] = (uint8_t)sel8_row(i);
     __syncthreads();
     PredConsts pc;
     __shared__ uint32_t s_pin[2 * kBlock];
-    pc.sel_addr = pinned_value(&s_pin[threadIdx.x], smem_addr(s_sel16));
-    // (the byte table holds the low 16 bits of the entries' shared-memory addresses; the rest rides on the column offset)
-    pc.col_lo = (threadIdx.x & 7u) * 16u + (lut_addr & 0xFFFF0000u); pc.col_hi = pc.col_lo + 4096u;
+    pc.sel_addr8 = pinned_value(&s_pin[threadIdx.x], (smem_addr(s_sel8r) + sel_off) >> 3);
+    pc.col_lo = (threadIdx.x & 7u) * 16u + lut_addr; pc.col_hi = pc.col_lo + 4096u;
     pc.one = a.one; pc.zero = a.zero;
 
     const uint32_t grab = a.grab, slices = (a.rollouts + grab - 1) / grab;     // slices per root

@@ -202,12 +202,11 @@ QK_HD uint32_t move_lut_word(uint32_t entry, uint32_t wi)
                             hi ? q.lines2 & lane : 0u, q.bit2, hi ? 0u : lane, hi ? lane : 0u, 0u };
     return v[wi & 7u];
 }
-// 16-bit byte table for the predicated ply: shared-memory address of the move-table entry of the k-th set bit of a
-// byte in row 0 (the row offset, QK_MOVE_LUT_BLOCKED_ROW for the empty byte, is added by the ply)
-QK_HD uint32_t sel16_entry(uint32_t index, uint32_t lut_addr)
+// byte table of the predicated ply: row (= position) of the k-th set bit of a byte in the move table; the empty byte -- a
+// mover without a legal action -- leads to the "blocked" entry (row 8 on top of the row offset every predicate adds)
+QK_HD uint32_t sel8_row(uint32_t index)
 {
-    if ((index >> 3) == 0u) return lut_addr + 64u * 128u - QK_MOVE_LUT_BLOCKED_ROW;
-    return lut_addr + 128u * kth_in_byte(index >> 3, index & 7u);
+    return (index >> 3) == 0u ? (64u * 128u - QK_MOVE_LUT_BLOCKED_ROW) / 128u : kth_in_byte(index >> 3, index & 7u);
 }
 // 32-bit word `w` of the shared-memory image of the move table
 QK_HD uint32_t move_lut_image_word(uint32_t w)
@@ -218,9 +217,9 @@ QK_HD uint32_t move_lut_image_word(uint32_t w)
 
 // C++ restatement of ply_pred (below): the same tables, the same three-level descent, the same sign test -- what the PTX
 // computes, for the CPU test tier (tests/hostsim) and as the readable version of it.  `lut` = the shared-memory image
-// of the move table (move_lut_image_word), `sel16` = the byte table built for a table at address 0, `col` = the lane's
+// of the move table (move_lut_image_word), `sel8r` = the byte table (sel8_row), `col` = the lane's
 // column offset.  role 0: role A moves.
-QK_HD void ply_pred_model(PlayState &st, int role, uint32_t rnd, const uint32_t *lut, const uint16_t *sel16, uint32_t col,
+QK_HD void ply_pred_model(PlayState &st, int role, uint32_t rnd, const uint32_t *lut, const uint8_t *sel8r, uint32_t col,
                           uint32_t &act, uint32_t &acc)
 {
     uint32_t &rm_lo = role ? st.rb_lo : st.ra_lo, &rm_hi = role ? st.rb_hi : st.ra_hi;   // mover
@@ -234,7 +233,7 @@ QK_HD void ply_pred_model(PlayState &st, int role, uint32_t rnd, const uint32_t 
     if (k >= c) { w >>= 16; k -= c; row += 2048u; }                    // 32 -> 16
     c = (uint32_t)popc(w << 24);
     if (k >= c) { w >>= 8; k -= c; row += 1024u; }                     // 16 -> 8
-    const uint32_t at = (uint32_t)sel16[(w & 0xFFu) * 8u + k] + row;   // byte offset of the entry's first plane
+    const uint32_t at = (uint32_t)sel8r[(w & 0xFFu) * 8u + k] * 128u + row;   // byte offset of the entry's first plane
     const uint32_t *e0 = lut + at / 4u, *e1 = lut + (at + QK_MOVE_LUT_PLANE) / 4u;
     ro_lo |= e0[0];            ro_hi |= e0[1];
     rm_lo |= tm_lo & e1[1];    rm_hi |= tm_hi & e1[2];
@@ -342,11 +341,11 @@ __device__ __forceinline__ void ply_step_fma(PlayState &st, uint32_t rnd, const 
 // line, the mover of an odd ply makes A win by being blocked (beam_search.py:633-635,641-642).
 // A lane whose game is over keeps executing plies on a meaningless state until the next 4-ply boundary:
 // every quantity stays in range (k < popcount of the word it indexes), nothing is tallied (act == 0).
-// shared-memory address of the 16-bit byte table, the lane's column in the move table (+ the row offset of shapes C,D),
-// and the opaque 1 and 0
-struct PredConsts { uint32_t sel_addr, col_lo, col_hi, one, zero; };
+// (shared-memory address of the byte table, which is aligned to its 2 KB) / 8; the shared-memory address of the lane's
+// column of the move table, and the same + the row offset of shapes C,D; the opaque 1 and 0
+struct PredConsts { uint32_t sel_addr8, col_lo, col_hi, one, zero; };
 
-// lut / sel16 live in shared memory; ROLE 0: role A moves
+// the move table and the byte table live in shared memory; ROLE 0: role A moves
 // the move itself: pick + state update
 template <int ROLE>
 __device__ __forceinline__ void ply_pred_move(PlayState &st, uint32_t rnd, const PredConsts &pc)
@@ -358,7 +357,6 @@ __device__ __forceinline__ void ply_pred_move(PlayState &st, uint32_t rnd, const
     asm("{\n"
         " .reg .pred p0, p1, p2;\n"
         " .reg .b32 ll, lh, nl, nh, n, k, w, t, c, row, ad;\n"
-        " .reg .b16 eh;\n"
         " lop3.b32 ll, %8, %9, 0, 0x30;\n"              /* legal, shapes A,B: free & ~closed */
         " lop3.b32 lh, %8, %10, 0, 0x30;\n"             /* legal, shapes C,D */
         " popc.b32 nl, ll;\n"
@@ -381,17 +379,15 @@ __device__ __forceinline__ void ply_pred_move(PlayState &st, uint32_t rnd, const
         " @p2 shr.u32 w, w, 8;\n"
         " @p2 sub.u32 k, k, c;\n"
         " @p2 mad.lo.u32 row, %13, 1024, row;\n"
-        " and.b32 t, w, 0xFF;\n"                        /* 8 -> 1 from the byte table */
+        " lop3.b32 t, w, 0xFF, %12, 0xEA;\n"            /* 8 -> 1 from the byte table: (byte | table / 8) * 8 + k */
         " mad.lo.u32 ad, t, 8, k;\n"
-        " mad.lo.u32 ad, ad, 2, %12;\n"                 /* 16-bit entries */
-        " ld.shared.u16 eh, [ad];\n"
-        " cvt.u32.u16 ad, eh;\n"
-        " add.u32 ad, ad, row;\n"
+        " ld.shared.u8 ad, [ad];\n"
+        " mad.lo.u32 ad, ad, 128, row;\n"              /* the entry: table row (position) on top of the row offset */
         " ld.shared.v4.u32 {%0, %1, %2, %3}, [ad];\n"
         " ld.shared.v4.u32 {%4, %5, %6, %7}, [ad+8320];\n"
         "}\n"
         : "=r"(e0x), "=r"(e0y), "=r"(e0z), "=r"(e0w), "=r"(e1x), "=r"(e1y), "=r"(e1z), "=r"(e1w)
-        : "r"(st.free2), "r"(rm_lo), "r"(rm_hi), "r"(rnd), "r"(pc.sel_addr), "r"(pc.one), "r"(pc.col_lo), "r"(pc.col_hi));
+        : "r"(st.free2), "r"(rm_lo), "r"(rm_hi), "r"(rnd), "r"(pc.sel_addr8), "r"(pc.one), "r"(pc.col_lo), "r"(pc.col_hi));
     static_assert(QK_MOVE_LUT_PLANE == 8320, "the second plane's offset is spelled out in the PTX above");
     ro_lo |= e0x;              ro_hi |= e0y;              // opponent may no longer use this shape in my scope
     rm_lo |= tm_lo & e1y;      rm_hi |= tm_hi & e1z;      // second piece of the shape: lane exhausted for me

@@ -98,9 +98,9 @@ void hs_playouts_pred(const uint16_t *roots, size_t n_roots, uint32_t rollouts, 
                       int8_t *outcome, uint8_t *slots)
 {
     static uint32_t lut[QK_MOVE_LUT_BYTES / 4];
-    static uint16_t sel16[2048];
+    static uint8_t sel8r[2048];
     for (uint32_t i = 0; i < QK_MOVE_LUT_BYTES / 4; ++i) lut[i] = move_lut_image_word(i);
-    for (uint32_t i = 0; i < 2048; ++i) sel16[i] = (uint16_t)sel16_entry(i, 0u);
+    for (uint32_t i = 0; i < 2048; ++i) sel8r[i] = (uint8_t)sel8_row(i);
     for (size_t r = 0; r < n_roots; ++r) {
         const RootRec rec = make_root(ld(roots + 8 * r));
         const uint32_t immediate = (rec.flags >> QK_ROOT_IMMEDIATE_SHIFT) & 3u;
@@ -115,7 +115,7 @@ void hs_playouts_pred(const uint16_t *roots, size_t n_roots, uint32_t rollouts, 
                 Philox4 rnd = { { 0, 0, 0, 0 } };
                 for (int ply = 0; act; ++ply) {
                     if ((ply & 3) == 0) rnd = stream_block(seed, first + j, root_base + (uint32_t)r, (uint32_t)(ply >> 2));
-                    ply_pred_model(st, ply & 1, rnd.v[ply & 3], lut, sel16, col, act, acc);
+                    ply_pred_model(st, ply & 1, rnd.v[ply & 3], lut, sel8r, col, act, acc);
                     ++n_slots;
                 }
                 res = (acc != 0) == a_is_p0 ? 1 : -1;

@@ -442,7 +442,9 @@ __global__ void __launch_bounds__(kBlock, MIN_CTAS) k_playout_pred_roots(const P
         //      start: the switch is a long divergent path, and taken lane by lane -- 30 % of all iterations, with one or
         //      two lanes in it -- it was 18 % of the executed instructions of config 4 (profiles/r02l_cfg4_playout_ncu);
         //      a lane now waits for the slowest lane's slice instead, 0.41 / sqrt(slice length) of its time (5 % at 64)
-        if (!__any_sync(kFull, act != 0u || j != jend) && qnext != kExhausted) {
+        //      (a lane whose item needs no playing -- its root is decided -- takes the next one at once, so that decided
+        //      roots cost their lane a few dozen instructions each, not a round of waiting)
+        if (!__any_sync(kFull, act != 0u || j != jend)) while (j == jend && qnext != kExhausted) {
             const uint32_t q = qnext;
             if (q >= items) qnext = kExhausted;
             else {

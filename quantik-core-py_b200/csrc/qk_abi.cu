@@ -167,7 +167,7 @@ const char *qk_last_error(void) { return g_error.c_str(); }
 int qk_set_option(const char *name, long long value)
 {
     static const char *const names[OPT_COUNT] = { "perft_kernel", "perft_min_items", "perft_tile_generic", "playout_variant",
-                                                  "dedup_mode", "dedup_part_mb", "playout_grab", "grid_waves" };
+                                                  "dedup_mode", "dedup_part_mb", "playout_grab", "grid_waves", "dedup_streams", "table_slots_x10", "guided_scoring" };
     QK_REQUIRE(name, "qk_set_option: name is NULL");
     for (int i = 0; i < OPT_COUNT; ++i)
         if (strcmp(name, names[i]) == 0) { g_option[i].store(value, std::memory_order_relaxed); return QK_OK; }
@@ -219,6 +219,11 @@ int qk_shutdown(int dev)
     cudaGetDevice(&prev);
     cudaSetDevice(dev);
     cudaDeviceSynchronize();
+    for (int i = 0; i < Ctx::kAux; ++i) {
+        if (g_ctx[dev].aux[i]) cudaStreamDestroy(g_ctx[dev].aux[i]);
+        if (g_ctx[dev].join_ev[i]) cudaEventDestroy(g_ctx[dev].join_ev[i]);
+    }
+    if (g_ctx[dev].fork_ev) cudaEventDestroy(g_ctx[dev].fork_ev);
     cudaMemPoolTrimTo(g_ctx[dev].pool, 0);
     g_ctx[dev] = Ctx();
     cudaSetDevice(prev);

@@ -6,7 +6,7 @@
 //                    an open-addressing table keyed by the 16-byte payload with a single
 //                    128-bit compare-and-swap (atom.cas.b128, sm_90+), multiplicity added
 //                    with a 64-bit atomic.
-//   k_dedup_compact  table -> dense (key, multiplicity) arrays
+//   k_dedup_compact  table -> dense (key, multiplicity) arrays, one cursor atomic per 1 024 slots
 //   k_bitonic_step   sorts the distinct keys in payload byte order (deterministic output)
 #include "qk_common.cuh"
 #include <math.h>
@@ -122,43 +122,57 @@ __device__ __forceinline__ TSlot load_entry(const TSlot *table, size_t i)
     return t;
 }
 
-// position of this lane's entry in the dense output: one cursor atomic per warp (slots and the grid stride are
-// multiples of 32, so the warp is converged here)
-__device__ __forceinline__ u64 compact_slot(bool have, u64 *cursor)
+// table -> dense output.  A block takes runs of kBlock x kCompactItems slots, counts the run's entries and reserves
+// their place with ONE atomic.  (One reservation per warp made the single cursor the bottleneck -- 2.6 M atomics on
+// one address for the largest BFS level: 5.1 ms for a 2.6 GB table that is read in 0.5 ms.)  `slots` is a
+// multiple of 256.  EMIT: straight into the caller's payload / multiplicity arrays (unsorted output), else into
+// the (key, multiplicity) arrays the sort works on.
+static constexpr int kCompactItems = 4;
+template <bool EMIT>
+__global__ void __launch_bounds__(kBlock) k_dedup_compact(const TSlot *table, size_t slots, Slot *keys, u64 *mults,
+                                                           uint4 *uniq, u64 *uniq_mult, u64 *cursor)
 {
-    const unsigned lane = threadIdx.x & 31u;
-    const unsigned present = __ballot_sync(0xFFFFFFFFu, have);
-    u64 base = 0;
-    if (lane == 0 && present) base = atomicAdd(cursor, (u64)__popc(present));
-    base = __shfl_sync(0xFFFFFFFFu, base, 0);
-    return base + (u64)__popc(present & ((1u << lane) - 1u));
-}
-
-__global__ void __launch_bounds__(kBlock) k_dedup_compact(const TSlot *table, size_t slots, Slot *keys, u64 *mults, u64 *cursor)
-{
-    for (size_t i = blockIdx.x * (size_t)kBlock + threadIdx.x; i < slots; i += (size_t)gridDim.x * kBlock) {
-        const TSlot k = load_entry(table, i);
-        const bool have = !(k.hi == ~0ull && k.lo == ~0ull);
-        const u64 o = compact_slot(have, cursor);
-        if (have) { keys[o].hi = k.hi; keys[o].lo = k.lo; mults[o] = k.count; }
-    }
-}
-
-// unsorted path: table -> caller's payload / multiplicity arrays directly (no intermediate copy)
-__global__ void __launch_bounds__(kBlock) k_dedup_compact_emit(const TSlot *table, size_t slots,
-                                                                uint4 *uniq, u64 *uniq_mult, u64 *cursor)
-{
-    for (size_t i = blockIdx.x * (size_t)kBlock + threadIdx.x; i < slots; i += (size_t)gridDim.x * kBlock) {
-        const TSlot k = load_entry(table, i);
-        const bool have = !(k.hi == ~0ull && k.lo == ~0ull);
-        const u64 o = compact_slot(have, cursor);
-        if (have) {
-            uniq[o] = make_uint4(prmt((uint32_t)(k.hi >> 32), 0, 0x0123), prmt((uint32_t)k.hi, 0, 0x0123),
-                                 prmt((uint32_t)(k.lo >> 32), 0, 0x0123), prmt((uint32_t)k.lo, 0, 0x0123));
-            uniq_mult[o] = k.count;
+    __shared__ unsigned s_warp[kBlock / 32];
+    __shared__ u64 s_base;
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    for (size_t run = blockIdx.x * (size_t)(kBlock * kCompactItems); run < slots; run += (size_t)gridDim.x * kBlock * kCompactItems) {
+        TSlot e[kCompactItems];
+        unsigned mask[kCompactItems], mine = 0;
+#pragma unroll
+        for (int k = 0; k < kCompactItems; ++k) {
+            const size_t i = run + (size_t)k * kBlock + threadIdx.x;
+            e[k].hi = ~0ull; e[k].lo = ~0ull; e[k].count = 0;
+            if (i < slots) e[k] = load_entry(table, i);
+            mask[k] = __ballot_sync(0xFFFFFFFFu, !(e[k].hi == ~0ull && e[k].lo == ~0ull));
+            mine += (unsigned)__popc(mask[k]);
         }
+        if (lane == 0) s_warp[warp] = mine;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned total = 0;
+            for (unsigned w = 0; w < kBlock / 32; ++w) { const unsigned c = s_warp[w]; s_warp[w] = total; total += c; }
+            s_base = total ? atomicAdd(cursor, (u64)total) : 0ull;
+        }
+        __syncthreads();
+        u64 o = s_base + s_warp[warp];
+#pragma unroll
+        for (int k = 0; k < kCompactItems; ++k) {
+            if ((mask[k] >> lane) & 1u) {
+                const u64 at = o + (u64)__popc(mask[k] & ((1u << lane) - 1u));
+                if (EMIT) {
+                    uniq[at] = make_uint4(prmt((uint32_t)(e[k].hi >> 32), 0, 0x0123), prmt((uint32_t)e[k].hi, 0, 0x0123),
+                                          prmt((uint32_t)(e[k].lo >> 32), 0, 0x0123), prmt((uint32_t)e[k].lo, 0, 0x0123));
+                    uniq_mult[at] = e[k].count;
+                } else {
+                    keys[at].hi = e[k].hi; keys[at].lo = e[k].lo; mults[at] = e[k].count;
+                }
+            }
+            o += (u64)__popc(mask[k]);
+        }
+        __syncthreads();
     }
 }
+static unsigned compact_grid(size_t slots, int sms) { return grid_for((slots + kCompactItems - 1) / kCompactItems, kBlock, sms, 8); }
 
 __global__ void __launch_bounds__(kBlock) k_pad(Slot *keys, u64 *mults, size_t from, size_t to)
 {
@@ -566,7 +580,8 @@ static int dedup_begin(Call &call, size_t expected_unique, DedupTable &t)
     cudaStream_t s = call.stream();
     // 1.5 slots per expected key (linear probing stays short up to ~2/3 full), a multiple of 256 so that warps
     // scan it converged
-    t.slots = expected_unique + expected_unique / 2 + 2;
+    const long long x10 = option(OPT_TABLE_SLOTS_X10);
+    t.slots = x10 >= 11 ? (size_t)((double)expected_unique * (double)x10 / 10.0) + 2 : expected_unique + expected_unique / 2 + 2;
     if (t.slots < 1024) t.slots = 1024;
     t.slots = (t.slots + 255) / 256 * 256;
     t.table = (TSlot *)call.temp(t.slots * sizeof(TSlot));
@@ -636,7 +651,7 @@ static int dedup_finish(Call &call, DedupTable &t, uint16_t *uniq, uint64_t *uni
         uint4 *d_uniq = (uint4 *)call.out(uniq, (nu + 1) * 16);
         u64 *d_um = (u64 *)call.out(uniq_mult, (nu + 1) * 8);
         if (call.status() != QK_OK) return call.status();
-        k_dedup_compact_emit<<<grid_for(t.slots, kBlock, c->sms, 8), kBlock, 0, s>>>(t.table, t.slots, d_uniq, d_um, t.meta + 2);
+        k_dedup_compact<true><<<compact_grid(t.slots, c->sms), kBlock, 0, s>>>(t.table, t.slots, nullptr, nullptr, d_uniq, d_um, t.meta + 2);
         QK_CUDA(cudaGetLastError());
         if (special) {
             const uint32_t ones[4] = { ~0u, ~0u, ~0u, ~0u };
@@ -653,16 +668,17 @@ static int dedup_finish(Call &call, DedupTable &t, uint16_t *uniq, uint64_t *uni
     Slot *keys = (Slot *)call.temp((padded + 1) * sizeof(Slot));
     u64 *mults = (u64 *)call.temp((padded + 1) * sizeof(u64));
     if (!keys || !mults) return call.status();
-    k_dedup_compact<<<grid_for(t.slots, kBlock, c->sms, 8), kBlock, 0, s>>>(t.table, t.slots, keys, mults, t.meta + 2);
+    k_dedup_compact<false><<<compact_grid(t.slots, c->sms), kBlock, 0, s>>>(t.table, t.slots, keys, mults, nullptr, nullptr, t.meta + 2);
     QK_CUDA(cudaGetLastError());
     return dedup_emit_dense(call, keys, mults, padded, nu, special, h_meta[1], uniq, uniq_mult, n_uniq, true);
 }
 
 // Plan of a two-level merge of `n_keys` keys with at most `expected_unique` classes (see the kernels above).
-static bool plan_two_level(size_t n_keys, size_t expected_unique, int sms, Buckets &b, size_t &per_block)
+static bool plan_two_level(size_t n_keys, size_t expected_unique, int sms, int streams, Buckets &b, size_t &per_block)
 {
     const size_t slots = expected_unique + expected_unique / 2 + 2;
-    size_t parts = (slots * sizeof(TSlot) + l2_table_bytes() - 1) / l2_table_bytes();
+    const size_t part_bytes = l2_table_bytes() / (size_t)streams;       // `streams` part tables share the L2 budget
+    size_t parts = (slots * sizeof(TSlot) + part_bytes - 1) / part_bytes;
     if (parts < 2) parts = 2;
     if (parts > (size_t)kMaxParts) return false;
     // hash-uniform shares: mean + 6 sigma of the classes of one part, 1.5 slots per class, a multiple of 256
@@ -680,28 +696,65 @@ static bool plan_two_level(size_t n_keys, size_t expected_unique, int sms, Bucke
     return true;
 }
 
-// pass B for every part + the tail.  meta = n_unique, all-ones mult, cursor, overflow (as DedupTable::meta)
-static int merge_buckets(Call &call, const Buckets &b, u64 *meta, size_t expected_unique, uint16_t *uniq, uint64_t *uniq_mult,
-                         size_t cap, size_t *n_uniq, bool sort_output, const char *who, bool *fallback)
+// side streams of the merge: created once per device, non-blocking (they are ordered against the caller's stream
+// by events only, whatever kind of stream that is)
+static int merge_streams(Ctx *c, int n_aux)
+{
+    if (!c->fork_ev) QK_CUDA(cudaEventCreateWithFlags(&c->fork_ev, cudaEventDisableTiming));
+    for (int i = 0; i < n_aux; ++i) {
+        if (!c->aux[i]) QK_CUDA(cudaStreamCreateWithFlags(&c->aux[i], cudaStreamNonBlocking));
+        if (!c->join_ev[i]) QK_CUDA(cudaEventCreateWithFlags(&c->join_ev[i], cudaEventDisableTiming));
+    }
+    return QK_OK;
+}
+static int dedup_streams()
+{
+    const long long v = option(OPT_DEDUP_STREAMS);
+    return v <= 0 ? 1 : (v > Ctx::kAux + 1 ? Ctx::kAux + 1 : (int)v);
+}
+
+// pass B for every part + the tail.  meta = n_unique, all-ones mult, cursor, overflow (as DedupTable::meta).
+// One part's kernels are short (about 75 + 19 us at 2^24 keys, a fifth of it ramp-up and tail), so `streams` parts
+// are merged at the same time, each in its own table (together they take the L2 budget) on its own stream: part
+// k + 1 fills the SMs that part k's tail and drain leave idle.  The parts are independent -- different keys,
+// different tables; they share only the append cursor and the counters, which are atomics.
+static int merge_buckets(Call &call, const Buckets &b, int streams, u64 *meta, size_t expected_unique, uint16_t *uniq,
+                         uint64_t *uniq_mult, size_t cap, size_t *n_uniq, bool sort_output, const char *who, bool *fallback)
 {
     cudaStream_t s = call.stream();
     Ctx *c = call.ctx();
     *fallback = false;
-    TSlot *table = (TSlot *)call.temp((size_t)b.part_slots * sizeof(TSlot));
+    if (streams > b.parts) streams = b.parts;
+    int rc = merge_streams(c, streams - 1);
+    if (rc != QK_OK) return rc;
+    TSlot *table = (TSlot *)call.temp((size_t)streams * b.part_slots * sizeof(TSlot));
     size_t padded = kTile;
     while (padded < expected_unique) padded <<= 1;
     if (!sort_output) padded = expected_unique;
     Slot *keys = (Slot *)call.temp((padded + 1) * sizeof(Slot));
     u64 *mults = (u64 *)call.temp((padded + 1) * sizeof(u64));
     if (!table || !keys || !mults) return call.status();
-    k_dedup_fill<<<grid_for(b.part_slots, kBlock, c->sms, 8), kBlock, 0, s>>>(table, b.part_slots);
+    k_dedup_fill<<<grid_for((size_t)streams * b.part_slots, kBlock, c->sms, 8), kBlock, 0, s>>>(table, (size_t)streams * b.part_slots);
     const u64 max_unique = (u64)(expected_unique < 512 ? 512 : expected_unique);
     const unsigned insert_grid = b.blocks < (unsigned)c->sms * 8 ? b.blocks : (unsigned)c->sms * 8;
-    for (int part = 0; part < b.parts; ++part) {
-        k_part_insert<<<insert_grid, kBlock, 0, s>>>(b, part, table, meta, (int *)(meta + 3), max_unique);
-        k_part_drain<<<grid_for((b.part_slots + kDrainItems - 1) / kDrainItems, kBlock, c->sms, 8), kBlock, 0, s>>>(table, b.part_slots, keys, mults,
-                                                                                                                  meta + 2, (u64)padded);
+    const unsigned drain_grid = grid_for((b.part_slots + kDrainItems - 1) / kDrainItems, kBlock, c->sms, 8);
+    if (streams > 1) {
+        QK_CUDA(cudaEventRecord(c->fork_ev, s));
+        for (int i = 0; i + 1 < streams; ++i) QK_CUDA(cudaStreamWaitEvent(c->aux[i], c->fork_ev, 0));
     }
+    for (int part = 0; part < b.parts; ++part) {
+        const int lane = part % streams;
+        cudaStream_t st = lane == 0 ? s : c->aux[lane - 1];
+        TSlot *t = table + (size_t)lane * b.part_slots;
+        k_part_insert<<<insert_grid, kBlock, 0, st>>>(b, part, t, meta, (int *)(meta + 3), max_unique);
+        k_part_drain<<<drain_grid, kBlock, 0, st>>>(t, b.part_slots, keys, mults, meta + 2, (u64)padded);
+    }
+    const cudaError_t launch_err = cudaGetLastError();
+    for (int i = 0; i + 1 < streams; ++i) {             // join even after a failed launch: `s` frees the tables
+        cudaEventRecord(c->join_ev[i], c->aux[i]);
+        cudaStreamWaitEvent(s, c->join_ev[i], 0);
+    }
+    QK_CUDA(launch_err);
     QK_CUDA(cudaGetLastError());
     u64 h_meta[4];
     QK_CUDA(cudaMemcpyAsync(h_meta, meta, sizeof h_meta, cudaMemcpyDeviceToHost, s));
@@ -738,7 +791,7 @@ int run_dedup(Call &call, const uint4 *states, const uint64_t *mult, size_t n, i
     Buckets b;
     size_t per_block = 0;
     if (mode != 1 && (mode == 2 || (expected + expected / 2) * sizeof(TSlot) > 2 * l2_table_bytes()) &&
-        plan_two_level(n, expected, c->sms, b, per_block)) {
+        plan_two_level(n, expected, c->sms, dedup_streams(), b, per_block)) {
         int rc = alloc_buckets(call, b, mult != nullptr);
         if (rc != QK_OK) return rc;
         u64 *meta = (u64 *)call.temp(10 * sizeof(u64), true);
@@ -750,7 +803,7 @@ int run_dedup(Call &call, const uint4 *states, const uint64_t *mult, size_t n, i
             k_bucket_states<false><<<b.blocks, kBlock, smem, s>>>(states, (const u64 *)mult, n, per_block, b, meta + 1, (int *)(meta + 3));
         QK_CUDA(cudaGetLastError());
         bool fallback = false;
-        rc = merge_buckets(call, b, meta, expected, uniq, uniq_mult, cap, n_uniq, !unsorted, "qk_canon_dedup", &fallback);
+        rc = merge_buckets(call, b, dedup_streams(), meta, expected, uniq, uniq_mult, cap, n_uniq, !unsorted, "qk_canon_dedup", &fallback);
         if (rc != QK_OK || !fallback) return rc;
         call.release(b.keys); call.release(b.counts);
         if (b.mults) call.release(b.mults);

@@ -38,72 +38,98 @@ __global__ void __launch_bounds__(kBlock) k_guided_lines(const uint4 *__restrict
 
 // ---- the playout kernel: 32 playouts per warp, one ply per iteration for all of them.
 // A lane whose playout is still on its root's greedy line takes the line's move; a lane that needs a greedy move of
-// its own has to score every child of its position.  When only a few lanes of the warp are in that situation -- the
-// first plies, where positions have 40-64 children and most playouts are still on the line -- the warp scores THEIR
-// children together, one child per lane (a lane-serial scan would keep 32 lanes waiting for the few); when most lanes
-// need one, every lane scans its own children.  Same moves either way (first decisive child, else first maximum).
+// its own has to score every child of its position.  Unless nearly all lanes are in that situation with about the
+// same number of children, the warp scores the children of all of them together, dealt out one per lane
+// (dealt_greedy_actions; a lane-serial scan keeps the other lanes waiting for the longest one); otherwise every
+// lane scans its own children.  Same moves either way (first decisive child, else first maximum).
 static constexpr unsigned kFull = 0xFFFFFFFFu;
 __device__ __forceinline__ uint64_t sortable(double d)      // order-preserving map double -> u64 (no NaNs, no -0.0 here)
 {
     const long long bits = __double_as_longlong(d);
     return (uint64_t)(bits ^ ((bits >> 63) | (long long)0x8000000000000000ull));
 }
-__device__ __forceinline__ uint64_t shfl64(uint64_t v, int src)
-{
-    return ((uint64_t)__shfl_sync(kFull, (uint32_t)(v >> 32), src) << 32) | __shfl_sync(kFull, (uint32_t)v, src);
-}
+// What a lane in need of a greedy move publishes for the warp: its position, the packed line fields, its legal
+// moves and what the opponent could play now (the starting point of every child's reply count).
+struct __align__(16) GuidedSlot { uint4 cur, ev0, ev1, misc; };     // 64 bytes
 
-// the greedy move of lane `src`'s position, worked out by the whole warp; every lane returns it
-__device__ __forceinline__ int warp_greedy_action(int src, const State4 &cur, const EvalPos &ev, int player, uint64_t mask, const double *tab)
+// The greedy moves of ALL lanes in need, worked out by the whole warp: their children -- n_mine each, `total` together
+// -- are dealt out 32 per round, one per lane, whoever they belong to, so the scoring (about 115 instructions per
+// child) runs with full warps however few lanes need a move and however different their child counts are.  Children
+// of one lane are consecutive and in ascending order; the arg-max of each lane's children inside a round is a
+// two-stage REDUX over the lanes holding them (first maximum: highest key, lowest lane among equals), a decisive
+// child counts as the largest key of all (first decisive child, else first best child -- mcts.py:362-383), and a
+// lane whose children span two rounds keeps the earlier round's winner unless the later one is strictly better.
+__device__ __forceinline__ int dealt_greedy_actions(bool need, const State4 &cur, const EvalPos &ev, int player, uint64_t mask,
+                                                    uint32_t n_mine, GuidedSlot *slots, const double *tab)
 {
     const unsigned lane = threadIdx.x & 31u;
-    State4 c;
-    c.x = __shfl_sync(kFull, cur.x, src); c.y = __shfl_sync(kFull, cur.y, src);
-    c.z = __shfl_sync(kFull, cur.z, src); c.w = __shfl_sync(kFull, cur.w, src);
-    EvalPos e;
-    e.occ = shfl64(ev.occ, src); e.np = shfl64(ev.np, src); e.pres = shfl64(ev.pres, src);
-    const int pl = __shfl_sync(kFull, player, src);
-    const uint64_t mk = shfl64(mask, src);
-    const uint32_t lo = (uint32_t)mk, hi = (uint32_t)(mk >> 32);
-    const int nlo = __popc(lo), n = nlo + __popc(hi);
-    uint32_t opp_lo, opp_hi;
-    legal_masks(c, 1 - pl, opp_lo, opp_hi);
+    if (need) {
+        uint32_t opp_lo, opp_hi;
+        legal_masks(cur, 1 - player, opp_lo, opp_hi);
+        GuidedSlot &g = slots[lane];
+        g.cur = make_uint4(cur.x, cur.y, cur.z, cur.w);
+        g.ev0 = make_uint4((uint32_t)ev.occ, (uint32_t)(ev.occ >> 32), (uint32_t)ev.np, (uint32_t)(ev.np >> 32));
+        g.ev1 = make_uint4((uint32_t)ev.pres, (uint32_t)(ev.pres >> 32), (uint32_t)mask, (uint32_t)(mask >> 32));
+        g.misc = make_uint4(opp_lo, opp_hi, (uint32_t)player, 0u);
+    }
+    uint32_t incl = n_mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(kFull, incl, o); if (lane >= (unsigned)o) incl += t; }
+    const uint32_t total = __shfl_sync(kFull, incl, 31), start = incl - n_mine;
+    __syncwarp();
     uint64_t best_key = 0;
     int best_a = -1;
-    for (int k0 = 0; k0 < n; k0 += 32) {
-        const int k = k0 + (int)lane;
-        const bool have = k < n;
-        const int a = select_bit64(lo, hi, nlo, have ? k : 0);
-        EvalPos ce = e;
+    for (uint32_t base = 0; base < total; base += 32) {
+        const uint32_t idx = base + lane;
+        const bool have = idx < total;
+        // owner of child idx: the first lane whose range ends beyond it = the number of lanes with incl <= idx
+        int src = 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { const uint32_t v = __shfl_sync(kFull, incl, src + o - 1); if (v <= idx) src += o; }
+        const uint32_t first = __shfl_sync(kFull, start, src);
+        const GuidedSlot &g = slots[src];
+        const uint4 gc = g.cur, e0 = g.ev0, e1 = g.ev1, gm = g.misc;
+        const State4 c = { gc.x, gc.y, gc.z, gc.w };
+        const uint32_t lo = e1.z, hi = e1.w;
+        const int pl = (int)gm.z;
+        const int a = select_bit64(lo, hi, __popc(lo), have ? (int)(idx - first) : 0);
+        EvalPos ce = { ((uint64_t)e0.y << 32) | e0.x, ((uint64_t)e0.w << 32) | e0.z, ((uint64_t)e1.y << 32) | e1.x };
         eval_pos_place(ce, a >> 4, a & 15);
         uint32_t clo, chi;
-        child_reply_masks(opp_lo, opp_hi, a, clo, chi);
-        const bool decisive = have && ((ce.np & (kLineLsb << 2)) != 0 || (clo | chi) == 0);
-        const unsigned dmask = __ballot_sync(kFull, decisive);
-        if (dmask) return __shfl_sync(kFull, a, __ffs((int)dmask) - 1);      // children are in ascending order: the first one
-        int f[6];
-        eval_features_pos(apply_action(c, pl, a), ce, pl, 1 - pl, __popc(clo) + __popc(chi), f);
-        const uint64_t key = sortable(eval_dot_tab(f, tab));
-        // first maximum of the round: highest key, lowest lane among equals
-        const uint32_t kh = have ? (uint32_t)(key >> 32) : 0u, mh = __reduce_max_sync(kFull, kh);
-        const bool cand = have && kh == mh;
-        const uint32_t kl = cand ? (uint32_t)key : 0u, ml = __reduce_max_sync(kFull, kl);
-        const int wl = __ffs((int)__ballot_sync(kFull, cand && kl == ml)) - 1;
-        const uint64_t round_key = ((uint64_t)mh << 32) | ml;
+        child_reply_masks(gm.x, gm.y, a, clo, chi);
+        uint64_t key = ~0ull;                                            // decisive: a fourth shape on a line, or no reply
+        if (!((ce.np & (kLineLsb << 2)) != 0 || (clo | chi) == 0)) {
+            int f[6];
+            eval_features_pos(apply_action(c, pl, a), ce, pl, 1 - pl, __popc(clo) + __popc(chi), f);
+            key = sortable(eval_dot_tab(f, tab));
+        }
+        const unsigned seg = __match_any_sync(kFull, have ? src : 64);
+        const uint32_t kh = (uint32_t)(key >> 32), mh = __reduce_max_sync(seg, kh);
+        const bool cand = kh == mh;
+        const uint32_t kl = cand ? (uint32_t)key : 0u, ml = __reduce_max_sync(seg, kl);
+        const int wl = __ffs((int)(__ballot_sync(kFull, cand && kl == ml) & seg)) - 1;
         const int round_a = __shfl_sync(kFull, a, wl);
-        if (best_a < 0 || round_key > best_key) { best_key = round_key; best_a = round_a; }
+        // back to the owners: any lane that holds one of my children knows my round's winner
+        const bool mine = need && start < base + 32 && incl > base;
+        const int at = mine ? (int)((start > base ? start : base) - base) : 0;
+        const uint32_t rh = __shfl_sync(kFull, mh, at), rl = __shfl_sync(kFull, ml, at);
+        const int ra = __shfl_sync(kFull, round_a, at);
+        const uint64_t rk = ((uint64_t)rh << 32) | rl;
+        if (mine && (best_a < 0 || rk > best_key)) { best_key = rk; best_a = ra; }
     }
+    __syncwarp();
     return best_a;
 }
 
 __global__ void __launch_bounds__(kBlock) k_playout_guided(const uint4 *__restrict__ roots, uint64_t n_roots, uint32_t rollouts,
                                                             uint64_t seed, uint64_t first_rollout, uint32_t root_index_base,
                                                             int max_plies, double epsilon, const EvalWeights weights,
-                                                            const GuidedLine *__restrict__ lines,
+                                                            const GuidedLine *__restrict__ lines, int scoring,
                                                             uint32_t *wins_p0, uint32_t *wins_p1, uint32_t *draws,
                                                             int8_t *per_playout, uint8_t *per_plies)
 {
     __shared__ double s_tab[6 * kEvalTabStride];
+    __shared__ GuidedSlot s_slots[kBlock / 32][32];
 #pragma unroll
     for (int i = 0; i < 6; ++i)
         for (int v = threadIdx.x; v < kEvalTabStride; v += kBlock) s_tab[i * kEvalTabStride + v] = __dmul_rn(weights.w[i], (double)(v - 64));
@@ -160,18 +186,14 @@ __global__ void __launch_bounds__(kBlock) k_playout_guided(const uint4 *__restri
                 } else if (on_line) action = line->action[ply];
                 else need = true;
             }
-            unsigned need_mask = __ballot_sync(kFull, need);
-            if (need_mask) {
-                const int n_mine = need ? __popc((uint32_t)mask) + __popc((uint32_t)(mask >> 32)) : 0;
-                const int n_max = __reduce_max_sync(kFull, n_mine);
-                // together: one round of ~160 instructions per 32 children of every lane in need; each on its own: the
-                // longest scan, ~115 instructions per child
-                if (__popc(need_mask) * ((n_max + 31) / 32) * 160 < n_max * 115) {
-                    for (; need_mask; need_mask &= need_mask - 1) {
-                        const int src = __ffs((int)need_mask) - 1;
-                        const int a = warp_greedy_action(src, cur, ev, player, mask, s_tab);
-                        if ((int)lane == src) action = a;
-                    }
+            if (__any_sync(kFull, need)) {
+                const uint32_t n_mine = need ? (uint32_t)(__popc((uint32_t)mask) + __popc((uint32_t)(mask >> 32))) : 0u;
+                const uint32_t n_max = __reduce_max_sync(kFull, n_mine), n_all = __reduce_add_sync(kFull, n_mine);
+                // dealt: one round of ~160 instructions per 32 children of the warp; each lane on its own: the longest
+                // scan, ~115 instructions per child
+                if (scoring == 2 || (scoring == 0 && ((n_all + 31u) >> 5) * 160u < n_max * 115u)) {
+                    const int a = dealt_greedy_actions(need, cur, ev, player, mask, n_mine, s_slots[threadIdx.x >> 5], s_tab);
+                    if (need) action = a;
                 } else if (need) action = guided_greedy_action(cur, ev, player, mask, weights.w, s_tab);
             }
             if (!done) {
@@ -223,7 +245,8 @@ int launch_playouts_guided(const uint4 *roots, size_t n_roots, uint32_t rollouts
         QK_CUDA(cudaGetLastError());
     }
     k_playout_guided<<<grid_for(total, kBlock, c->sms, 16), kBlock, 0, s>>>(roots, n_roots, rollouts, seed, first_rollout,
-                                                                            root_index_base, max_plies, epsilon, w, lines, wins_p0,
+                                                                            root_index_base, max_plies, epsilon, w, lines,
+                                                                            (int)option(OPT_GUIDED_SCORING), wins_p0,
                                                                             wins_p1, draws, per_playout, per_plies);
     QK_CUDA(cudaGetLastError());
     return QK_OK;

@@ -11,6 +11,12 @@ for waves in (1, 2, 4, 8, 32):
         t0 = time.perf_counter(); r = Q.guided_playouts(e, 1 << 24); ts.append(time.perf_counter() - t0)
     print("grid_waves", waves, f"{(1 << 24) / min(ts):.4e}")
 Q._native.set_option("grid_waves", 0)
+for scoring in (1, 2, 0):
+    Q._native.set_option("guided_scoring", scoring)
+    ts = []
+    for _ in range(3):
+        t0 = time.perf_counter(); r = Q.guided_playouts(e, 1 << 24); ts.append(time.perf_counter() - t0)
+    print("guided_scoring", scoring, f"{(1 << 24) / min(ts):.4e}")
 for n in (1 << 22, 1 << 24):
     ts = []
     for _ in range(3):

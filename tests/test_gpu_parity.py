@@ -598,21 +598,27 @@ def test_evaluation_and_guided_rollouts():
     big = O.make_roots(20000, seed=123, min_plies=1, span=13)
     pl = (np.arange(len(big)) % 2).astype(np.uint8)
     assert np.array_equal(B.eval_features(big, pl), O.features(big, pl))
-    e = np.zeros((1, 8), np.uint16)
-    for name, wkey, eps in (("seeded_eps02", "seeded_weights", 0.2), ("fitted_eps02", "fitted_weights", 0.2),
-                            ("fitted_eps0", "fitted_weights", 0.0), ("seeded_eps1", "seeded_weights", 1.0)):
-        r = B.guided_playouts(e, len(g[name + "_outcome"]), SEED, eps, g[wkey], root_index_base=3, per_playout=True)
-        assert np.array_equal(r["outcome"][0], g[name + "_outcome"]) and np.array_equal(r["plies"][0], g[name + "_plies"]), name
-    r = B.guided_playouts(g["roots"], 24, SEED, 0.2, g["fitted_weights"], first_rollout=500, root_index_base=40, per_playout=True)
-    assert np.array_equal(r["outcome"], g["roots_outcome"]) and np.array_equal(r["plies"], g["roots_plies"])
-    r = B.guided_playouts(e, 80, SEED, 0.2, g["fitted_weights"], root_index_base=3, max_plies=9, per_playout=True)
-    assert np.array_equal(r["outcome"][0], g["cut9_outcome"]) and np.array_equal(r["plies"][0], g["cut9_plies"])
-    # larger sample against the oracle, both weight sets, per playout
-    roots = O.make_roots(64, seed=9)
-    for w, eps in ((g["fitted_weights"], 0.2), (g["seeded_weights"], 0.05)):
-        a, b = B.guided_playouts(roots, 128, SEED, eps, w, per_playout=True), O.guided_playouts(roots, 128, SEED, eps, w, per_playout=True)
-        assert np.array_equal(a["outcome"], b["outcome"]) and np.array_equal(a["plies"], b["plies"])
-        assert np.array_equal(a["wins_p0"], b["wins_p0"]) and np.array_equal(a["wins_p1"], b["wins_p1"])
+    from quantik_b200 import _native as N
+    # every scoring mode of the kernel (0 = its own choice per ply, 1 = each lane scans its own children, 2 = the
+    # children of all lanes dealt out over the warp) must play the same games
+    for scoring in (0, 1, 2):
+        N.set_option("guided_scoring", scoring)
+        e = np.zeros((1, 8), np.uint16)
+        for name, wkey, eps in (("seeded_eps02", "seeded_weights", 0.2), ("fitted_eps02", "fitted_weights", 0.2),
+                                ("fitted_eps0", "fitted_weights", 0.0), ("seeded_eps1", "seeded_weights", 1.0)):
+            r = B.guided_playouts(e, len(g[name + "_outcome"]), SEED, eps, g[wkey], root_index_base=3, per_playout=True)
+            assert np.array_equal(r["outcome"][0], g[name + "_outcome"]) and np.array_equal(r["plies"][0], g[name + "_plies"]), name
+        r = B.guided_playouts(g["roots"], 24, SEED, 0.2, g["fitted_weights"], first_rollout=500, root_index_base=40, per_playout=True)
+        assert np.array_equal(r["outcome"], g["roots_outcome"]) and np.array_equal(r["plies"], g["roots_plies"])
+        r = B.guided_playouts(e, 80, SEED, 0.2, g["fitted_weights"], root_index_base=3, max_plies=9, per_playout=True)
+        assert np.array_equal(r["outcome"][0], g["cut9_outcome"]) and np.array_equal(r["plies"][0], g["cut9_plies"])
+        # larger sample against the oracle, both weight sets, per playout
+        roots = O.make_roots(64, seed=9)
+        for w, eps in ((g["fitted_weights"], 0.2), (g["seeded_weights"], 0.05)):
+            a, b = B.guided_playouts(roots, 128, SEED, eps, w, per_playout=True), O.guided_playouts(roots, 128, SEED, eps, w, per_playout=True)
+            assert np.array_equal(a["outcome"], b["outcome"]) and np.array_equal(a["plies"], b["plies"])
+            assert np.array_equal(a["wins_p0"], b["wins_p0"]) and np.array_equal(a["wins_p1"], b["wins_p1"])
+    N.set_option("guided_scoring", 0)
     with pytest.raises(ValueError):
         B.guided_playouts(e, 4, epsilon=1.5)                                                    # mcts.py:70-76
 

@@ -81,10 +81,10 @@ QK_API const char *qk_last_error(void);
  *   "playout_variant"     0 auto | 2 the general kernel for every case | 3 / 4 the predicated tallies-only kernels at
  *                         5 / 6 resident CTAs per SM instead of 4 | 1 / 6 the older single-root kernels
  *   "dedup_mode"          0 auto | 1 one-level table insert | 2 partitioned (two-level) insert
- *   "dedup_part_mb"       > 0: MiB of L2 the part tables of the two-level insert may take together
- *   "dedup_streams"       1..4: parts merged at the same time, each in its own table on its own stream (0 = 2)
+ *   "dedup_part_mb"       > 0: size in MiB of the table one part of the two-level insert is merged in (0 = 112)
+ *   "dedup_streams"       1..4: part tables in use at a time, each on its own stream (0 = 2)
  *   "table_slots_x10"     >= 11: slots of the one-level merge table per expected class, times ten (0 = 15)
- *   "guided_scoring"      0 auto | 1 every lane scores its own children | 2 children dealt out over the warp
+ *   "guided_scoring"      0 children dealt out over the warp | 1 every lane scores its own children
  *   "grid_waves"          > 0: waves of CTAs a grid-stride kernel is launched with (0 = 16)
  *   "playout_grab"        > 0: playouts a lane of the single-root playout kernel takes from the work queue at a time  */
 QK_API int qk_set_option(const char *name, long long value);

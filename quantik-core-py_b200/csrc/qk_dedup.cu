@@ -411,9 +411,9 @@ __global__ void __launch_bounds__(kBlock) k_book_expand_insert(const uint4 *__re
 // one-level one on 2^24 keys, and is NOT used for the BFS expansion, whose 2.7 x 10^10 children/s already equal it.
 static constexpr int kMaxParts = 1024;
 // one part's table.  Measured on 2^24 keys (scripts/dedup_case.py, whole call): 24 MiB parts 2.01 ms, 40 MiB 1.64 ms,
-// 64 MiB 1.36 ms, 96 MiB 1.23 ms (one-level table: 1.85 ms) -- fewer, larger parts win as long as the table still
-// fits the 126 MB L2 next to the bucket streams.
-static constexpr size_t kL2TableBytes = 96u << 20;
+// 64 MiB 1.36 ms, 96 MiB 1.23 ms, 112 MiB 1.15 ms, 120-128 MiB 1.14 ms (one-level table: 1.85 ms) -- fewer, larger parts
+// win as long as the table still fits the 126 MB L2 next to the bucket streams.
+static constexpr size_t kL2TableBytes = 112u << 20;
 static size_t l2_table_bytes() { const long long mb = option(OPT_DEDUP_PART_MB); return mb > 0 ? (size_t)mb << 20 : kL2TableBytes; }
 
 __device__ __forceinline__ void route(u64 hi, u64 lo, int parts, uint32_t part_slots, int &part, uint32_t &slot)
@@ -677,7 +677,8 @@ static int dedup_finish(Call &call, DedupTable &t, uint16_t *uniq, uint64_t *uni
 static bool plan_two_level(size_t n_keys, size_t expected_unique, int sms, int streams, Buckets &b, size_t &per_block)
 {
     const size_t slots = expected_unique + expected_unique / 2 + 2;
-    const size_t part_bytes = l2_table_bytes() / (size_t)streams;       // `streams` part tables share the L2 budget
+    (void)streams;
+    const size_t part_bytes = l2_table_bytes();
     size_t parts = (slots * sizeof(TSlot) + part_bytes - 1) / part_bytes;
     if (parts < 2) parts = 2;
     if (parts > (size_t)kMaxParts) return false;
@@ -710,14 +711,17 @@ static int merge_streams(Ctx *c, int n_aux)
 static int dedup_streams()
 {
     const long long v = option(OPT_DEDUP_STREAMS);
-    return v <= 0 ? 1 : (v > Ctx::kAux + 1 ? Ctx::kAux + 1 : (int)v);
+    return v <= 0 ? 2 : (v > Ctx::kAux + 1 ? Ctx::kAux + 1 : (int)v);
 }
 
 // pass B for every part + the tail.  meta = n_unique, all-ones mult, cursor, overflow (as DedupTable::meta).
 // One part's kernels are short (about 75 + 19 us at 2^24 keys, a fifth of it ramp-up and tail), so `streams` parts
-// are merged at the same time, each in its own table (together they take the L2 budget) on its own stream: part
-// k + 1 fills the SMs that part k's tail and drain leave idle.  The parts are independent -- different keys,
-// different tables; they share only the append cursor and the counters, which are atomics.
+// are in flight at a time, each in its own full-size table on its own stream: part k + 1 starts on the SMs that part
+// k's tail and drain leave idle.  An insert kernel fills the machine, so the parts mostly run one after the other and
+// the L2 holds the table that is being filled.  Measured (2^24 keys, whole call): one stream 1.15 ms, two 1.07 ms;
+// splitting the L2 between the tables instead (2 x 48 MiB: 1.31 ms, 4 x 24 MiB: 1.55 ms) loses -- twice the parts,
+// twice the launches.  The parts are independent -- different keys, different tables; they share only the append
+// cursor and the counters, which are atomics.
 static int merge_buckets(Call &call, const Buckets &b, int streams, u64 *meta, size_t expected_unique, uint16_t *uniq,
                          uint64_t *uniq_mult, size_t cap, size_t *n_uniq, bool sort_output, const char *who, bool *fallback)
 {

@@ -38,87 +38,114 @@ __global__ void __launch_bounds__(kBlock) k_guided_lines(const uint4 *__restrict
 
 // ---- the playout kernel: 32 playouts per warp, one ply per iteration for all of them.
 // A lane whose playout is still on its root's greedy line takes the line's move; a lane that needs a greedy move of
-// its own has to score every child of its position.  Unless nearly all lanes are in that situation with about the
-// same number of children, the warp scores the children of all of them together, dealt out one per lane
-// (dealt_greedy_actions; a lane-serial scan keeps the other lanes waiting for the longest one); otherwise every
-// lane scans its own children.  Same moves either way (first decisive child, else first maximum).
+// its own has to score every child of its position.  The warp scores the children of all such lanes together, dealt
+// out one per lane (dealt_greedy_actions; a lane-serial scan keeps the other lanes waiting for the longest one and
+// is kept as the second implementation the parity tests compare with: qk_set_option("guided_scoring", 1)).  Same
+// moves either way (first decisive child, else first maximum).
 static constexpr unsigned kFull = 0xFFFFFFFFu;
 __device__ __forceinline__ uint64_t sortable(double d)      // order-preserving map double -> u64 (no NaNs, no -0.0 here)
 {
     const long long bits = __double_as_longlong(d);
     return (uint64_t)(bits ^ ((bits >> 63) | (long long)0x8000000000000000ull));
 }
-// What a lane in need of a greedy move publishes for the warp: its position, the packed line fields, its legal
-// moves and what the opponent could play now (the starting point of every child's reply count).
-struct __align__(16) GuidedSlot { uint4 cur, ev0, ev1, misc; };     // 64 bytes
+// What a lane in need of a greedy move publishes for the warp: the packed line fields of its position, its legal
+// moves, what the opponent could play now (the starting point of every child's reply count), and in `info` the
+// occupied squares (bits 0-15), the mover's shapes with exactly one piece placed (16-19) and the mover (20).
+struct __align__(16) GuidedSlot { uint32_t occ_lo, occ_hi, np_lo, np_hi, pres_lo, pres_hi, mask_lo, mask_hi, opp_lo, opp_hi, info, pad; };
+struct GuidedWarp {
+    GuidedSlot slot[32];
+    uint64_t best_key[32];              // per owner lane: the best child so far, 0 = none yet (a key is never 0)
+    unsigned short queue[2048];         // (owner lane << 6 | action) of every child to score, owner by owner, ascending actions
+    unsigned char best_a[32];
+};
 
-// The greedy moves of ALL lanes in need, worked out by the whole warp: their children -- n_mine each, `total` together
-// -- are dealt out 32 per round, one per lane, whoever they belong to, so the scoring (about 115 instructions per
-// child) runs with full warps however few lanes need a move and however different their child counts are.  Children
-// of one lane are consecutive and in ascending order; the arg-max of each lane's children inside a round is a
-// two-stage REDUX over the lanes holding them (first maximum: highest key, lowest lane among equals), a decisive
-// child counts as the largest key of all (first decisive child, else first best child -- mcts.py:362-383), and a
-// lane whose children span two rounds keeps the earlier round's winner unless the later one is strictly better.
+// sortable evaluation (from the mover's point of view, evaluation.py:130-212) of the child reached by `a`, from the
+// PARENT's data: the child's line fields `ce`, what its mover (own64) and the player to move in it (opp64) may still
+// play there as 64-bit action masks, and the squares of each line (s_line).  The child itself is never built.
+// A threat line -- three pieces, three shapes -- has one empty square and one missing shape, and a player "can
+// complete" it (evaluation.py:99-112, :170-175) exactly when that placement is among his legal moves.
+__device__ __forceinline__ uint64_t dealt_child_key(const EvalPos &ce, uint64_t own64, uint64_t opp64, int n_reply,
+                                                    const uint32_t *s_line, const double *tab)
+{
+    const uint64_t diff = ce.occ - ce.np;
+    const uint64_t live = ~(diff | (diff >> 1)) & kLineLsb;
+    const uint64_t b0 = ce.occ, b1 = ce.occ >> 1;
+    int f[6];
+    f[5] = -popc64(b0 & ~b1 & live); f[4] = -popc64(b1 & ~b0 & live);        // build_one, build_two; the side to move is the opponent
+    int t_own = 0, t_opp = 0, t_both = 0;
+    for (uint64_t threats = b0 & b1 & live; threats; threats &= threats - 1) {
+        const uint32_t tlo = (uint32_t)threats;
+        const int bit = tlo ? __ffs((int)tlo) - 1 : 32 + __ffs((int)(uint32_t)(threats >> 32)) - 1;
+        const uint32_t absent = ~(uint32_t)(ce.pres >> bit) & 0xFu;          // exactly one bit: the missing shape
+        const int lane16 = (int)(((absent >> 1) - (absent >> 3)) << 4);       // 1,2,4,8 -> 0,16,32,48
+        const uint32_t line = s_line[bit >> 2];
+        const uint32_t o = ((uint32_t)(own64 >> lane16) & line) ? 1u : 0u, q = ((uint32_t)(opp64 >> lane16) & line) ? 1u : 0u;
+        t_own += (int)o; t_opp += (int)q; t_both += (int)(o & q);
+    }
+    f[0] = t_own; f[1] = t_opp; f[2] = -t_both; f[3] = -n_reply;
+    return sortable(eval_dot_tab(f, tab));
+}
+
+// The greedy moves of ALL lanes in need, worked out by the whole warp: every such lane lists its children in the
+// warp's queue, and the queue is scored 32 children per round, one per lane, whoever they belong to -- full warps
+// however few lanes need a move and however different their child counts are.  Children of one lane are consecutive
+// and in ascending order; the arg-max of each lane's children inside a round is a two-stage REDUX over the lanes
+// holding them (first maximum: highest key, lowest lane among equals), a decisive child counts as the largest key
+// of all (first decisive child, else first best child -- mcts.py:362-383), and across rounds an owner keeps the
+// earlier winner unless a later one is strictly better.
 __device__ __forceinline__ int dealt_greedy_actions(bool need, const State4 &cur, const EvalPos &ev, int player, uint64_t mask,
-                                                    uint32_t n_mine, GuidedSlot *slots, const double *tab)
+                                                    uint32_t n_mine, GuidedWarp &w, const uint32_t *s_line, const double *tab)
 {
     const unsigned lane = threadIdx.x & 31u;
-    if (need) {
-        uint32_t opp_lo, opp_hi;
-        legal_masks(cur, 1 - player, opp_lo, opp_hi);
-        GuidedSlot &g = slots[lane];
-        g.cur = make_uint4(cur.x, cur.y, cur.z, cur.w);
-        g.ev0 = make_uint4((uint32_t)ev.occ, (uint32_t)(ev.occ >> 32), (uint32_t)ev.np, (uint32_t)(ev.np >> 32));
-        g.ev1 = make_uint4((uint32_t)ev.pres, (uint32_t)(ev.pres >> 32), (uint32_t)mask, (uint32_t)(mask >> 32));
-        g.misc = make_uint4(opp_lo, opp_hi, (uint32_t)player, 0u);
-    }
     uint32_t incl = n_mine;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(kFull, incl, o); if (lane >= (unsigned)o) incl += t; }
-    const uint32_t total = __shfl_sync(kFull, incl, 31), start = incl - n_mine;
+    const uint32_t total = __shfl_sync(kFull, incl, 31);
+    if (need) {
+        uint32_t opp_lo, opp_hi;
+        legal_masks(cur, 1 - player, opp_lo, opp_hi);
+        const uint32_t all = cur.x | cur.y | cur.z | cur.w, m01 = player ? cur.z : cur.x, m23 = player ? cur.w : cur.y;
+        const uint32_t once = (__popc(m01 & 0xFFFFu) == 1 ? 1u : 0u) | (__popc(m01 >> 16) == 1 ? 2u : 0u) |
+                              (__popc(m23 & 0xFFFFu) == 1 ? 4u : 0u) | (__popc(m23 >> 16) == 1 ? 8u : 0u);
+        GuidedSlot &g = w.slot[lane];
+        g.occ_lo = (uint32_t)ev.occ; g.occ_hi = (uint32_t)(ev.occ >> 32); g.np_lo = (uint32_t)ev.np; g.np_hi = (uint32_t)(ev.np >> 32);
+        g.pres_lo = (uint32_t)ev.pres; g.pres_hi = (uint32_t)(ev.pres >> 32); g.mask_lo = (uint32_t)mask; g.mask_hi = (uint32_t)(mask >> 32);
+        g.opp_lo = opp_lo; g.opp_hi = opp_hi;
+        g.info = ((all | (all >> 16)) & 0xFFFFu) | (once << 16) | ((uint32_t)player << 20);
+        w.best_key[lane] = 0ull;
+        uint32_t at = incl - n_mine;
+        for (uint32_t v = (uint32_t)mask; v; v &= v - 1) w.queue[at++] = (unsigned short)((lane << 6) | (uint32_t)(__ffs((int)v) - 1));
+        for (uint32_t v = (uint32_t)(mask >> 32); v; v &= v - 1) w.queue[at++] = (unsigned short)((lane << 6) | (uint32_t)(32 + __ffs((int)v) - 1));
+    }
     __syncwarp();
-    uint64_t best_key = 0;
-    int best_a = -1;
     for (uint32_t base = 0; base < total; base += 32) {
         const uint32_t idx = base + lane;
         const bool have = idx < total;
-        // owner of child idx: the first lane whose range ends beyond it = the number of lanes with incl <= idx
-        int src = 0;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) { const uint32_t v = __shfl_sync(kFull, incl, src + o - 1); if (v <= idx) src += o; }
-        const uint32_t first = __shfl_sync(kFull, start, src);
-        const GuidedSlot &g = slots[src];
-        const uint4 gc = g.cur, e0 = g.ev0, e1 = g.ev1, gm = g.misc;
-        const State4 c = { gc.x, gc.y, gc.z, gc.w };
-        const uint32_t lo = e1.z, hi = e1.w;
-        const int pl = (int)gm.z;
-        const int a = select_bit64(lo, hi, __popc(lo), have ? (int)(idx - first) : 0);
-        EvalPos ce = { ((uint64_t)e0.y << 32) | e0.x, ((uint64_t)e0.w << 32) | e0.z, ((uint64_t)e1.y << 32) | e1.x };
-        eval_pos_place(ce, a >> 4, a & 15);
+        const uint32_t e = have ? w.queue[idx] : 0u;
+        const int src = (int)(e >> 6), a = (int)(e & 63u), shape = a >> 4, sq = a & 15;
+        const uint4 g0 = *reinterpret_cast<const uint4 *>(&w.slot[src].occ_lo), g1 = *reinterpret_cast<const uint4 *>(&w.slot[src].pres_lo),
+                    g2 = *reinterpret_cast<const uint4 *>(&w.slot[src].opp_lo);
+        EvalPos ce = { ((uint64_t)g0.y << 32) | g0.x, ((uint64_t)g0.w << 32) | g0.z, ((uint64_t)g1.y << 32) | g1.x };
+        eval_pos_place(ce, shape, sq);
         uint32_t clo, chi;
-        child_reply_masks(gm.x, gm.y, a, clo, chi);
-        uint64_t key = ~0ull;                                            // decisive: a fourth shape on a line, or no reply
-        if (!((ce.np & (kLineLsb << 2)) != 0 || (clo | chi) == 0)) {
-            int f[6];
-            eval_features_pos(apply_action(c, pl, a), ce, pl, 1 - pl, __popc(clo) + __popc(chi), f);
-            key = sortable(eval_dot_tab(f, tab));
+        child_reply_masks(g2.x, g2.y, a, clo, chi);
+        uint64_t key = have ? ~0ull : 0ull;                              // decisive: a fourth shape on a line, or no reply
+        if (have && !((ce.np & (kLineLsb << 2)) != 0 || (clo | chi) == 0)) {
+            // the mover's own options in the child: the parent's, without the square just taken and without the
+            // shape just played if that was its second piece
+            uint64_t own64 = (((uint64_t)g1.w << 32) | g1.z) & ~(0x0001000100010001ull << sq);
+            if ((g2.z >> (16 + shape)) & 1u) own64 &= ~(0xFFFFull << (shape << 4));
+            key = dealt_child_key(ce, own64, ((uint64_t)chi << 32) | clo, __popc(clo) + __popc(chi), s_line, tab);
         }
         const unsigned seg = __match_any_sync(kFull, have ? src : 64);
         const uint32_t kh = (uint32_t)(key >> 32), mh = __reduce_max_sync(seg, kh);
         const bool cand = kh == mh;
         const uint32_t kl = cand ? (uint32_t)key : 0u, ml = __reduce_max_sync(seg, kl);
         const int wl = __ffs((int)(__ballot_sync(kFull, cand && kl == ml) & seg)) - 1;
-        const int round_a = __shfl_sync(kFull, a, wl);
-        // back to the owners: any lane that holds one of my children knows my round's winner
-        const bool mine = need && start < base + 32 && incl > base;
-        const int at = mine ? (int)((start > base ? start : base) - base) : 0;
-        const uint32_t rh = __shfl_sync(kFull, mh, at), rl = __shfl_sync(kFull, ml, at);
-        const int ra = __shfl_sync(kFull, round_a, at);
-        const uint64_t rk = ((uint64_t)rh << 32) | rl;
-        if (mine && (best_a < 0 || rk > best_key)) { best_key = rk; best_a = ra; }
+        if (have && (int)lane == wl && key > w.best_key[src]) { w.best_key[src] = key; w.best_a[src] = (unsigned char)a; }
+        __syncwarp();
     }
-    __syncwarp();
-    return best_a;
+    return need ? (int)w.best_a[lane] : 0;
 }
 
 __global__ void __launch_bounds__(kBlock) k_playout_guided(const uint4 *__restrict__ roots, uint64_t n_roots, uint32_t rollouts,
@@ -129,7 +156,9 @@ __global__ void __launch_bounds__(kBlock) k_playout_guided(const uint4 *__restri
                                                             int8_t *per_playout, uint8_t *per_plies)
 {
     __shared__ double s_tab[6 * kEvalTabStride];
-    __shared__ GuidedSlot s_slots[kBlock / 32][32];
+    __shared__ GuidedWarp s_warp[kBlock / 32];
+    __shared__ uint32_t s_line[12];
+    if (threadIdx.x < 12) s_line[threadIdx.x] = line_squares((int)threadIdx.x);
 #pragma unroll
     for (int i = 0; i < 6; ++i)
         for (int v = threadIdx.x; v < kEvalTabStride; v += kBlock) s_tab[i * kEvalTabStride + v] = __dmul_rn(weights.w[i], (double)(v - 64));
@@ -188,11 +217,11 @@ __global__ void __launch_bounds__(kBlock) k_playout_guided(const uint4 *__restri
             }
             if (__any_sync(kFull, need)) {
                 const uint32_t n_mine = need ? (uint32_t)(__popc((uint32_t)mask) + __popc((uint32_t)(mask >> 32))) : 0u;
-                const uint32_t n_max = __reduce_max_sync(kFull, n_mine), n_all = __reduce_add_sync(kFull, n_mine);
-                // dealt: one round of ~160 instructions per 32 children of the warp; each lane on its own: the longest
-                // scan, ~115 instructions per child
-                if (scoring == 2 || (scoring == 0 && ((n_all + 31u) >> 5) * 160u < n_max * 115u)) {
-                    const int a = dealt_greedy_actions(need, cur, ev, player, mask, n_mine, s_slots[threadIdx.x >> 5], s_tab);
+                // dealt out over the warp (measured faster for every mix of lanes in need, 7.0e8 against 6.5e8 playouts/s
+                // with a per-ply choice and 3.3e8 with every lane scanning its own children: the dealt child is also
+                // the cheaper one to score); the lane-serial scan is kept for the parity tests
+                if (scoring != 1) {
+                    const int a = dealt_greedy_actions(need, cur, ev, player, mask, n_mine, s_warp[threadIdx.x >> 5], s_line, s_tab);
                     if (need) action = a;
                 } else if (need) action = guided_greedy_action(cur, ev, player, mask, weights.w, s_tab);
             }

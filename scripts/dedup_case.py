@@ -22,7 +22,7 @@ for mode in (1, 2):
         torch.cuda.synchronize()
         print(f"mode {mode} rep {rep}: {1e3 * (time.perf_counter() - t0):.3f} ms, {int(u.shape[0])} classes")
 N.set_option("dedup_mode", 2)
-for streams, budgets in ((1, (64, 96, 112, 120, 128)), (2, (96, 192, 224)), (3, (288,))):
+for streams, budgets in ((1, (96, 112)), (2, (96, 112, 128, 160, 200)), (3, (112,))):
     N.set_option("dedup_streams", streams)
     for mb in budgets:
         N.set_option("dedup_part_mb", mb)
@@ -32,4 +32,4 @@ for streams, budgets in ((1, (64, 96, 112, 120, 128)), (2, (96, 192, 224)), (3, 
         for _ in range(5):
             u, m = Q.canon_dedup(pos, None, sort_output=False)
         torch.cuda.synchronize()
-        print(f"streams {streams}, L2 budget {mb} MiB: {1e3 * (time.perf_counter() - t0) / 5:.3f} ms per call, {int(u.shape[0])} classes")
+        print(f"streams {streams}, part table {mb} MiB: {1e3 * (time.perf_counter() - t0) / 5:.3f} ms per call, {int(u.shape[0])} classes")

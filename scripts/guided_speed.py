@@ -11,7 +11,7 @@ for waves in (1, 2, 4, 8, 32):
         t0 = time.perf_counter(); r = Q.guided_playouts(e, 1 << 24); ts.append(time.perf_counter() - t0)
     print("grid_waves", waves, f"{(1 << 24) / min(ts):.4e}")
 Q._native.set_option("grid_waves", 0)
-for scoring in (1, 2, 0):
+for scoring in (1, 0):
     Q._native.set_option("guided_scoring", scoring)
     ts = []
     for _ in range(3):
@@ -24,5 +24,7 @@ for n in (1 << 22, 1 << 24):
     print("empty board", n, f"{n / min(ts):.4e}", int(r["wins_p0"][0]), int(r["wins_p1"][0]))
 roots = B.random_roots(4096, seed=4, min_plies=4, span=8)
 Q.guided_playouts(roots, 64)
-t0 = time.perf_counter(); r = Q.guided_playouts(roots, 4096); dt = time.perf_counter() - t0
-print("mid-game roots", f"{4096 * 4096 / dt:.4e}")
+for scoring in (1, 0):
+    Q._native.set_option("guided_scoring", scoring)
+    t0 = time.perf_counter(); r = Q.guided_playouts(roots, 4096); dt = time.perf_counter() - t0
+    print("mid-game roots, guided_scoring", scoring, f"{4096 * 4096 / dt:.4e}")

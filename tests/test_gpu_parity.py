@@ -599,9 +599,9 @@ def test_evaluation_and_guided_rollouts():
     pl = (np.arange(len(big)) % 2).astype(np.uint8)
     assert np.array_equal(B.eval_features(big, pl), O.features(big, pl))
     from quantik_b200 import _native as N
-    # every scoring mode of the kernel (0 = its own choice per ply, 1 = each lane scans its own children, 2 = the
-    # children of all lanes dealt out over the warp) must play the same games
-    for scoring in (0, 1, 2):
+    # both scoring modes of the kernel (0 = the children of all lanes dealt out over the warp, 1 = each lane scans
+    # its own children) must play the same games
+    for scoring in (0, 1):
         N.set_option("guided_scoring", scoring)
         e = np.zeros((1, 8), np.uint16)
         for name, wkey, eps in (("seeded_eps02", "seeded_weights", 0.2), ("fitted_eps02", "fitted_weights", 0.2),

@@ -465,6 +465,104 @@ __global__ void __launch_bounds__(kBlock) k_bucket_states(const uint4 *__restric
         b.counts[(size_t)k * b.blocks + blockIdx.x] = s_cur[k] < b.sub_cap ? s_cur[k] : b.sub_cap;
 }
 
+// ---- the BFS level in two-level form (k_bfs_expand_insert's table is DRAM-sized at the large levels -- 2.6 GB for 55 M
+// classes -- and every child is a random DRAM sector there: 3.7 x 10^10 random reads per second on this machine,
+// profiles/r02n_atomics_sweep.txt, against 2 x 10^11 on an L2-resident table).  Same plan as the dedup above: a
+// count pass (how many children each block of parents will emit: the sub-bucket ranges are sized from it), the
+// expansion with the children ROUTED into (part, block) ranges instead of inserted, then merge_buckets.
+__global__ void __launch_bounds__(kBlock) k_bfs_count_children(const uint4 *__restrict__ parents, size_t n, size_t per_block,
+                                                                unsigned *__restrict__ block_children)
+{
+    const size_t begin = blockIdx.x * per_block, end = begin + per_block < n ? begin + per_block : n;
+    unsigned cnt = 0;
+    for (size_t i = begin + threadIdx.x; i < end; i += kBlock) {
+        const uint4 v = __ldg(parents + i);
+        const State4 parent = { v.x, v.y, v.z, v.w };
+        uint32_t lo, hi, wab, wcd;
+        legal_masks(parent, piece_balance(parent), lo, hi);
+        winning_squares(parent, wab, wcd);
+        cnt += (unsigned)(popc(lo & ~wab) + popc(hi & ~wcd));
+    }
+    cnt = __reduce_add_sync(0xFFFFFFFFu, cnt);
+    if ((threadIdx.x & 31u) == 0 && cnt) atomicAdd(block_children + blockIdx.x, cnt);
+}
+
+template <bool COLOR_SWAP>
+__global__ void __launch_bounds__(kBlock) k_bfs_expand_bucket(const uint4 *__restrict__ parents, const u64 *__restrict__ mult,
+                                                               size_t n, size_t per_block, Buckets b, u64 *all_ones_count,
+                                                               int *overflow, u64 *stats)
+{
+    __shared__ BfsWarpScratch s_scratch[kBlock / 32];
+    extern __shared__ unsigned s_cur[];
+    for (int k = threadIdx.x; k < b.parts; k += kBlock) s_cur[k] = 0;
+    __syncthreads();
+    BfsWarpScratch &ws = s_scratch[threadIdx.x >> 5];
+    const unsigned lane = threadIdx.x & 31u;
+    const size_t begin = blockIdx.x * per_block, end = begin + per_block < n ? begin + per_block : n;
+    u64 s_moves = 0, s_w0 = 0, s_w1 = 0, s_b0 = 0, s_b1 = 0;      // per lane
+    for (size_t tile = begin + (threadIdx.x >> 5) * 32; tile < end; tile += kBlock) {
+        // ---- one parent per lane: moves, winning moves, the children worth keeping (as k_bfs_expand_insert)
+        uint32_t nl = 0, nh = 0;
+        const size_t i = tile + lane;
+        if (i < end) {
+            const uint4 v = __ldg(parents + i);
+            const State4 parent = { v.x, v.y, v.z, v.w };
+            const u64 m = mult ? mult[i] : 1ull;
+            const int mover = piece_balance(parent);
+            uint32_t lo, hi, wab, wcd;
+            legal_masks(parent, mover, lo, hi);
+            const int n_moves = popc(lo) + popc(hi);
+            if (n_moves == 0) { if (mover == 0) s_b0 += m; else s_b1 += m; }           // game_stats.py:426-443
+            else {
+                winning_squares(parent, wab, wcd);
+                s_moves += (u64)n_moves * m;                                            // :401
+                const u64 wins = (u64)(popc(lo & wab) + popc(hi & wcd)) * m;            // :411-415
+                if (mover == 0) s_w0 += wins; else s_w1 += wins;
+                nl = lo & ~wab; nh = hi & ~wcd;
+            }
+            ws.state[lane] = v; ws.mult[lane] = m; ws.mover[lane] = (unsigned char)mover;
+        }
+        const uint32_t cnt = (uint32_t)(popc(nl) + popc(nh));
+        uint32_t incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= (unsigned)o) incl += t; }
+        const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+        uint32_t at = incl - cnt;
+        for (uint32_t w = nl; w; w &= w - 1) ws.queue[at++] = (unsigned short)((lane << 6) | (uint32_t)(__ffs((int)w) - 1));
+        for (uint32_t w = nh; w; w &= w - 1) ws.queue[at++] = (unsigned short)((lane << 6) | (uint32_t)(32 + __ffs((int)w) - 1));
+        __syncwarp();
+        // ---- full warps: one child per lane per round, canonical form -> its (part, block) range
+        for (uint32_t base = 0; base < total; base += 32) {
+            const uint32_t idx = base + lane;
+            if (idx < total) {
+                const uint32_t e = ws.queue[idx], pl = e >> 6;
+                const uint4 pv = ws.state[pl];
+                const State4 parent = { pv.x, pv.y, pv.z, pv.w };
+                const State4 c = canonical<COLOR_SWAP>(apply_action(parent, ws.mover[pl], (int)(e & 63u)));   // :453,:468
+                bucket_put(b, s_cur, ((u64)prmt(c.x, 0, 0x0123) << 32) | prmt(c.y, 0, 0x0123),
+                           ((u64)prmt(c.z, 0, 0x0123) << 32) | prmt(c.w, 0, 0x0123), ws.mult[pl], all_ones_count, overflow);
+            }
+        }
+        __syncwarp();
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s_moves += __shfl_xor_sync(0xFFFFFFFFu, s_moves, o); s_w0 += __shfl_xor_sync(0xFFFFFFFFu, s_w0, o);
+        s_w1 += __shfl_xor_sync(0xFFFFFFFFu, s_w1, o); s_b0 += __shfl_xor_sync(0xFFFFFFFFu, s_b0, o);
+        s_b1 += __shfl_xor_sync(0xFFFFFFFFu, s_b1, o);
+    }
+    if (lane == 0) {
+        if (s_moves) atomicAdd(stats + 0, s_moves);
+        if (s_w0) atomicAdd(stats + 1, s_w0);
+        if (s_w1) atomicAdd(stats + 2, s_w1);
+        if (s_b0) atomicAdd(stats + 3, s_b0);
+        if (s_b1) atomicAdd(stats + 4, s_b1);
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < b.parts; k += kBlock)
+        b.counts[(size_t)k * b.blocks + blockIdx.x] = s_cur[k] < b.sub_cap ? s_cur[k] : b.sub_cap;
+}
+
 // pass B, first half: every sub-bucket of one part into the L2-resident table.  Four keys per thread at a time: the
 // four key loads, then the four probe loads are in flight together (a probe read early may be stale, which is safe:
 // a slot only ever changes from empty to a key, an "empty" that is no longer true fails its CAS and a key stays).
@@ -723,7 +821,8 @@ static int dedup_streams()
 // twice the launches.  The parts are independent -- different keys, different tables; they share only the append
 // cursor and the counters, which are atomics.
 static int merge_buckets(Call &call, const Buckets &b, int streams, u64 *meta, size_t expected_unique, uint16_t *uniq,
-                         uint64_t *uniq_mult, size_t cap, size_t *n_uniq, bool sort_output, const char *who, bool *fallback)
+                         uint64_t *uniq_mult, size_t cap, size_t *n_uniq, bool sort_output, const char *who, bool *fallback,
+                         uint64_t *h_stats = nullptr)
 {
     cudaStream_t s = call.stream();
     Ctx *c = call.ctx();
@@ -760,10 +859,11 @@ static int merge_buckets(Call &call, const Buckets &b, int streams, u64 *meta, s
     }
     QK_CUDA(launch_err);
     QK_CUDA(cudaGetLastError());
-    u64 h_meta[4];
+    u64 h_meta[10];
     QK_CUDA(cudaMemcpyAsync(h_meta, meta, sizeof h_meta, cudaMemcpyDeviceToHost, s));
     QK_CUDA(cudaStreamSynchronize(s));
     if ((int)h_meta[3] != 0) { *fallback = true; return QK_OK; }         // a range or the part table was too small
+    if (h_stats) for (int i = 0; i < 5; ++i) h_stats[i] = h_meta[4 + i];
     const size_t nu = (size_t)h_meta[0];
     const bool special = h_meta[1] != 0;
     if (nu + (special ? 1 : 0) > cap && (uniq || uniq_mult)) {
@@ -825,11 +925,70 @@ int run_dedup(Call &call, const uint4 *states, const uint64_t *mult, size_t n, i
     return dedup_finish(call, t, uniq, uniq_mult, cap, n_uniq, nullptr, "qk_canon_dedup", !unsorted);
 }
 
+// the two-level form of one BFS level; *fallback = a range or a part table was too small (the caller runs the one-level form)
+static int bfs_level_two_level(Call &call, const uint4 *parents, const uint64_t *mult, size_t n, int color_swap, int sort_output,
+                               uint16_t *uniq, uint64_t *uniq_mult, size_t cap, size_t *n_uniq, uint64_t *h_stats, bool *fallback)
+{
+    cudaStream_t s = call.stream();
+    Ctx *c = call.ctx();
+    *fallback = true;
+    Buckets b;
+    b.blocks = (unsigned)c->sms * 4;
+    size_t per_block = (n + b.blocks - 1) / b.blocks;
+    per_block = (per_block + 31) / 32 * 32;
+    unsigned *d_children = (unsigned *)call.temp(b.blocks * sizeof(unsigned), true);
+    if (!d_children) return call.status();
+    k_bfs_count_children<<<b.blocks, kBlock, 0, s>>>(parents, n, per_block, d_children);
+    QK_CUDA(cudaGetLastError());
+    std::vector<unsigned> h_children(b.blocks);
+    QK_CUDA(cudaMemcpyAsync(h_children.data(), d_children, b.blocks * sizeof(unsigned), cudaMemcpyDeviceToHost, s));
+    QK_CUDA(cudaStreamSynchronize(s));
+    call.release(d_children);
+    unsigned most = 0;
+    for (unsigned v : h_children) most = v > most ? v : most;
+    // parts: the table of `cap` classes cut into L2-sized pieces; a part's classes and a block's share of a part are
+    // hash-uniform, sized at mean + 6 sigma as in plan_two_level
+    const size_t slots = cap + cap / 2 + 2;
+    size_t parts = (slots * sizeof(TSlot) + l2_table_bytes() - 1) / l2_table_bytes();
+    if (parts < 2) parts = 2;
+    if (parts > (size_t)kMaxParts) return QK_OK;
+    const double mean = (double)cap / (double)parts, share = (double)most / (double)parts;
+    size_t part_slots = (size_t)(1.5 * (mean + 6.0 * sqrt(mean) + 64.0));
+    part_slots = (part_slots + 255) / 256 * 256;
+    if (part_slots >= (1ull << 32)) return QK_OK;
+    b.parts = (int)parts;
+    b.part_slots = (uint32_t)part_slots;
+    b.sub_cap = (uint32_t)(share + 6.0 * sqrt(share) + 32.0);
+    int rc = alloc_buckets(call, b, true);
+    if (rc != QK_OK) return rc;
+    u64 *meta = (u64 *)call.temp(10 * sizeof(u64), true);      // n_unique, all-ones mult, cursor, overflow, stats[5]
+    if (!meta) return call.status();
+    const size_t smem = (size_t)b.parts * sizeof(unsigned);
+    if (color_swap)
+        k_bfs_expand_bucket<true><<<b.blocks, kBlock, smem, s>>>(parents, (const u64 *)mult, n, per_block, b, meta + 1, (int *)(meta + 3), meta + 4);
+    else
+        k_bfs_expand_bucket<false><<<b.blocks, kBlock, smem, s>>>(parents, (const u64 *)mult, n, per_block, b, meta + 1, (int *)(meta + 3), meta + 4);
+    QK_CUDA(cudaGetLastError());
+    rc = merge_buckets(call, b, dedup_streams(), meta, cap, uniq, uniq_mult, cap, n_uniq, sort_output != 0, "qk_bfs_level", fallback, h_stats);
+    call.release(b.keys); call.release(b.mults); call.release(b.counts);
+    return rc;
+}
+
 int run_bfs_level(Call &call, const uint4 *parents, const uint64_t *mult, size_t n, int color_swap, int sort_output,
                   uint16_t *uniq, uint64_t *uniq_mult, size_t cap, size_t *n_uniq, uint64_t *h_stats)
 {
     cudaStream_t s = call.stream();
     Ctx *c = call.ctx();
+    // The routed (two-level) form is built and parity-tested but NOT the default here: on the largest level (4.1 x 10^8
+    // children, 55 M classes) it takes 10.3 ms to expand + route and 10.3 + 1.3 ms to merge 42 parts, against 16.0 +
+    // 0.85 + 1.2 ms for this one table (complete game tree 0.096 s against 0.063 s; profiles/r02n_bfs_two_level.txt).
+    // qk_set_option("dedup_mode", 2) selects it.
+    const long long mode = option(OPT_DEDUP_MODE);
+    if (mode == 2 && n > 0) {
+        bool fallback = false;
+        const int rc = bfs_level_two_level(call, parents, mult, n, color_swap, sort_output, uniq, uniq_mult, cap, n_uniq, h_stats, &fallback);
+        if (rc != QK_OK || !fallback) return rc;
+    }
     DedupTable t;
     int rc = dedup_begin(call, cap, t);
     if (rc != QK_OK) return rc;

@@ -468,7 +468,7 @@ def test_perft_is_symmetry_invariant():
 
 
 # ----------------------------------------------------------------------------- canonical BFS
-def test_symmetry_table_bfs_reproduces_published_table_with_unique_counts():
+def test_symmetry_table_bfs_reproduces_published_table_with_unique_counts(options):
     # GAME_TREE_ANALYSIS.md:4-11: total legal moves, unique canonical, P0 wins, P1 wins, ongoing
     table = [[64, 3, 0, 0, 64], [3392, 51, 0, 0, 3392], [167552, 726, 0, 0, 167552], [6776960, 10946, 0, 6912, 6770048],
              [231883776, 105632, 1050624, 0, 230833152], [6241600512, 901916, 0, 81653760, 6159946752],
@@ -476,6 +476,11 @@ def test_symmetry_table_bfs_reproduces_published_table_with_unique_counts():
              [2097048766464, 17900160, 0, 118862401536, 1978186364928]]
     assert B.symmetry_table(8) == table
     assert B.symmetry_table(5, on_device=False) == table[:5]          # host-buffer path of the same call
+    for mode in (1, 2):       # every level through the one table / through the routed (two-level) form, whatever its size
+        options("dedup_mode", mode)
+        assert B.symmetry_table(8) == table, mode
+        assert B.symmetry_table(4, on_device=False, sort_output=True) == table[:4], mode
+    options("dedup_mode", 0)
     assert [r[1] for r in table] == [3, 51, 726, 10946, 105632, 901916, 4658465, 17900160]   # beam_search.py:210-219
     # the depth-4 frontier equals the reference's own (states and multiplicities)
     f, m = np.zeros((1, 8), np.uint16), np.ones(1, np.uint64)
@@ -485,7 +490,9 @@ def test_symmetry_table_bfs_reproduces_published_table_with_unique_counts():
     assert np.array_equal(f, d["states"]) and np.array_equal(m, d["mult"])
 
 
-def test_bfs_level_vs_oracle_composition():
+@pytest.mark.parametrize("dedup_mode", [0, 2])
+def test_bfs_level_vs_oracle_composition(options, dedup_mode):
+    options("dedup_mode", dedup_mode)
     parents = np.unique(O.canonical(O.make_roots(3000, seed=5, min_plies=6, span=6)), axis=0)
     mult = np.random.default_rng(8).integers(1, 50, len(parents)).astype(np.uint64)
     f, m, st = B.bfs_level(parents, mult)

@@ -85,6 +85,8 @@ QK_API const char *qk_last_error(void);
  *   "dedup_streams"       1..4: part tables in use at a time, each on its own stream (0 = 2)
  *   "table_slots_x10"     >= 11: slots of the one-level merge table per expected class, times ten (0 = 15)
  *   "guided_scoring"      0 children dealt out over the warp | 1 every lane scores its own children
+ *   "call_stage"          1: host buffers and scratch of small calls go through the memory pool like large ones, not
+ *                         through the per-device staging block
  *   "grid_waves"          > 0: waves of CTAs a grid-stride kernel is launched with (0 = 16)
  *   "playout_grab"        > 0: playouts a lane of the single-root playout kernel takes from the work queue at a time  */
 QK_API int qk_set_option(const char *name, long long value);

@@ -13,6 +13,7 @@ static thread_local std::string g_error;
 static Ctx g_ctx[64];
 static std::mutex g_mu;
 static std::atomic<long long> g_option[OPT_COUNT];
+static std::atomic<int> g_stage_busy[64];
 
 long long option(Option o) { return g_option[o].load(std::memory_order_relaxed); }
 
@@ -49,14 +50,38 @@ Call::Call(int dev, void *stream) : stream_((cudaStream_t)stream)
     if (!ctx_) { status_ = QK_E_NO_DEVICE; return; }
     cudaGetDevice(&prev_dev_);
     cudaError_t e = cudaSetDevice(dev);
-    if (e != cudaSuccess) { status_ = cuda_fail(e, "cudaSetDevice"); ctx_ = nullptr; }
+    if (e != cudaSuccess) { status_ = cuda_fail(e, "cudaSetDevice"); ctx_ = nullptr; return; }
+    // the small-call stage, if nobody else holds it; work an earlier holder left running on another stream goes first
+    int expected = 0;
+    if (ctx_->stage_dev && option(OPT_CALL_STAGE) != 1 && g_stage_busy[dev].compare_exchange_strong(expected, 1)) {
+        staged_ = true;
+        if (ctx_->stage_pending && ctx_->stage_stream != stream_) cudaStreamWaitEvent(stream_, ctx_->stage_ev, 0);
+    }
 }
 
 Call::~Call()
 {
     for (void *t : temps_) cudaFreeAsync(t, stream_);
     temps_.clear();
+    if (staged_) {
+        if (stage_used_ && !synced_) {
+            if (stage_host_in_flight_) cudaStreamSynchronize(stream_);      // an error path left before finish(): the pinned block is still being read
+            else { cudaEventRecord(ctx_->stage_ev, stream_); ctx_->stage_stream = stream_; ctx_->stage_pending = true; }
+        } else if (stage_used_) ctx_->stage_pending = false;
+        g_stage_busy[ctx_->dev].store(0);
+    }
     if (prev_dev_ >= 0 && ctx_ && prev_dev_ != ctx_->dev) cudaSetDevice(prev_dev_);
+}
+
+char *Call::stage_alloc(size_t bytes)
+{
+    if (!staged_) return nullptr;
+    const size_t need = (bytes + 255) & ~(size_t)255;
+    if (need == 0 || need > Ctx::kStageBytes - stage_off_) return nullptr;
+    char *d = ctx_->stage_dev + stage_off_;
+    stage_off_ += need;
+    stage_used_ = true;
+    return d;
 }
 
 void *Call::alloc(size_t bytes)
@@ -73,6 +98,14 @@ const void *Call::in(const void *p, size_t bytes)
     if (!p || status_ != QK_OK) return nullptr;
     if (is_device_pointer(p)) return p;
     any_host_ = true;
+    if (char *sd = stage_alloc(bytes)) {          // through the pinned block: one asynchronous copy, no allocation
+        char *sh = ctx_->stage_host + (sd - ctx_->stage_dev);
+        memcpy(sh, p, bytes);
+        stage_host_in_flight_ = true;
+        cudaError_t e = cudaMemcpyAsync(sd, sh, bytes, cudaMemcpyHostToDevice, stream_);
+        if (e != cudaSuccess) { status_ = cuda_fail(e, "cudaMemcpyAsync(H2D)"); return nullptr; }
+        return sd;
+    }
     void *d = alloc(bytes);
     if (!d) return nullptr;
     cudaError_t e = cudaMemcpyAsync(d, p, bytes, cudaMemcpyHostToDevice, stream_);
@@ -86,9 +119,10 @@ void *Call::out(void *p, size_t bytes, bool zero)
     void *d = p;
     if (!is_device_pointer(p)) {
         any_host_ = true;
-        d = alloc(bytes);
+        const bool staged = (d = stage_alloc(bytes)) != nullptr;
+        if (!staged) d = alloc(bytes);
         if (!d) return nullptr;
-        backs_.push_back({ p, d, bytes });
+        backs_.push_back({ p, d, bytes, staged });
     }
     if (zero) {
         cudaError_t e = cudaMemsetAsync(d, 0, bytes, stream_);
@@ -100,7 +134,8 @@ void *Call::out(void *p, size_t bytes, bool zero)
 void *Call::temp(size_t bytes, bool zero)
 {
     if (status_ != QK_OK) return nullptr;
-    void *d = alloc(bytes);
+    void *d = stage_alloc(bytes);
+    if (!d) d = alloc(bytes);
     if (d && zero) {
         cudaError_t e = cudaMemsetAsync(d, 0, bytes, stream_);
         if (e != cudaSuccess) { status_ = cuda_fail(e, "cudaMemsetAsync"); return nullptr; }
@@ -110,6 +145,7 @@ void *Call::temp(size_t bytes, bool zero)
 
 void Call::release(void *p)
 {
+    if (in_stage(p)) return;                  // a block of the stage: nothing to free
     for (size_t i = 0; i < temps_.size(); ++i)
         if (temps_[i] == p) {
             temps_[i] = temps_.back();
@@ -131,7 +167,19 @@ int Call::finish()
     QK_CUDA(cudaGetLastError());
     std::vector<Back> backs;
     backs.swap(backs_);
-    for (const Back &b : backs) QK_CUDA(cudaMemcpyAsync(b.host, b.dev, b.bytes, cudaMemcpyDeviceToHost, stream_));
+    // staged outputs come back in ONE copy into the pinned block (everything between the first and the last of
+    // them), and go to the caller's buffers after the synchronisation below
+    size_t lo = Ctx::kStageBytes, hi = 0;
+    for (const Back &b : backs) {
+        if (!b.staged) { QK_CUDA(cudaMemcpyAsync(b.host, b.dev, b.bytes, cudaMemcpyDeviceToHost, stream_)); continue; }
+        const size_t at = (size_t)((char *)b.dev - ctx_->stage_dev);
+        lo = at < lo ? at : lo;
+        hi = at + b.bytes > hi ? at + b.bytes : hi;
+    }
+    if (hi > lo) {
+        stage_host_in_flight_ = true;
+        QK_CUDA(cudaMemcpyAsync(ctx_->stage_host + lo, ctx_->stage_dev + lo, hi - lo, cudaMemcpyDeviceToHost, stream_));
+    }
     std::vector<void *> temps;
     temps.swap(temps_);                       // whatever happens below, ~Call must not free these a second time
     cudaError_t first = cudaSuccess;
@@ -140,7 +188,12 @@ int Call::finish()
         if (first == cudaSuccess) first = e;
     }
     QK_CUDA(first);
-    if (any_host_) QK_CUDA(cudaStreamSynchronize(stream_));
+    if (any_host_) {
+        QK_CUDA(cudaStreamSynchronize(stream_));
+        synced_ = true;
+        for (const Back &b : backs)
+            if (b.staged) memcpy(b.host, ctx_->stage_host + ((char *)b.dev - ctx_->stage_dev), b.bytes);
+    }
     return QK_OK;
 }
 
@@ -167,7 +220,7 @@ const char *qk_last_error(void) { return g_error.c_str(); }
 int qk_set_option(const char *name, long long value)
 {
     static const char *const names[OPT_COUNT] = { "perft_kernel", "perft_min_items", "perft_tile_generic", "playout_variant",
-                                                  "dedup_mode", "dedup_part_mb", "playout_grab", "grid_waves", "dedup_streams", "table_slots_x10", "guided_scoring" };
+                                                  "dedup_mode", "dedup_part_mb", "playout_grab", "grid_waves", "dedup_streams", "table_slots_x10", "guided_scoring", "call_stage" };
     QK_REQUIRE(name, "qk_set_option: name is NULL");
     for (int i = 0; i < OPT_COUNT; ++i)
         if (strcmp(name, names[i]) == 0) { g_option[i].store(value, std::memory_order_relaxed); return QK_OK; }
@@ -205,6 +258,10 @@ int qk_init(int dev)
     QK_CUDA(cudaDeviceGetDefaultMemPool(&c.pool, dev));
     uint64_t keep = UINT64_MAX;   // the pool is the scratch arena: never hand memory back between calls
     QK_CUDA(cudaMemPoolSetAttribute(c.pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    QK_CUDA(cudaMalloc((void **)&c.stage_dev, Ctx::kStageBytes));
+    QK_CUDA(cudaHostAlloc((void **)&c.stage_host, Ctx::kStageBytes, cudaHostAllocDefault));
+    QK_CUDA(cudaEventCreateWithFlags(&c.stage_ev, cudaEventDisableTiming));
+    g_stage_busy[dev].store(0);
     c.ok = true;
     cudaSetDevice(prev);
     return QK_OK;
@@ -224,6 +281,9 @@ int qk_shutdown(int dev)
         if (g_ctx[dev].join_ev[i]) cudaEventDestroy(g_ctx[dev].join_ev[i]);
     }
     if (g_ctx[dev].fork_ev) cudaEventDestroy(g_ctx[dev].fork_ev);
+    if (g_ctx[dev].stage_ev) cudaEventDestroy(g_ctx[dev].stage_ev);
+    if (g_ctx[dev].stage_dev) cudaFree(g_ctx[dev].stage_dev);
+    if (g_ctx[dev].stage_host) cudaFreeHost(g_ctx[dev].stage_host);
     cudaMemPoolTrimTo(g_ctx[dev].pool, 0);
     g_ctx[dev] = Ctx();
     cudaSetDevice(prev);

@@ -21,11 +21,18 @@ struct Ctx {
     static constexpr int kAux = 3;
     cudaStream_t aux[kAux] = { nullptr, nullptr, nullptr };
     cudaEvent_t fork_ev = nullptr, join_ev[kAux] = { nullptr, nullptr, nullptr };
+    // small-call stage (qk_abi.cu: Call): one device buffer and one pinned host buffer of kStageBytes, handed to one
+    // call at a time; a call whose host buffers and scratch fit makes no allocation and one copy each way
+    static constexpr size_t kStageBytes = 256u << 10;
+    char *stage_dev = nullptr, *stage_host = nullptr;
+    cudaEvent_t stage_ev = nullptr;         // recorded by a call that left without synchronising
+    cudaStream_t stage_stream = nullptr;    // ... on this stream
+    bool stage_pending = false;
 };
 
 // Tuning / testing switches (qk_set_option in include/quantik_b200.h).  Process-wide, 0 = the default
 // behaviour; the library never reads the environment.
-enum Option { OPT_PERFT_KERNEL = 0, OPT_PERFT_MIN_ITEMS, OPT_PERFT_TILE_GENERIC, OPT_PLAYOUT_VARIANT, OPT_DEDUP_MODE, OPT_DEDUP_PART_MB, OPT_PLAYOUT_GRAB, OPT_GRID_WAVES, OPT_DEDUP_STREAMS, OPT_TABLE_SLOTS_X10, OPT_GUIDED_SCORING, OPT_COUNT };
+enum Option { OPT_PERFT_KERNEL = 0, OPT_PERFT_MIN_ITEMS, OPT_PERFT_TILE_GENERIC, OPT_PLAYOUT_VARIANT, OPT_DEDUP_MODE, OPT_DEDUP_PART_MB, OPT_PLAYOUT_GRAB, OPT_GRID_WAVES, OPT_DEDUP_STREAMS, OPT_TABLE_SLOTS_X10, OPT_GUIDED_SCORING, OPT_CALL_STAGE, OPT_COUNT };
 long long option(Option o);
 
 void set_error(const std::string &msg);
@@ -57,7 +64,7 @@ public:
     int sync();
 
 private:
-    struct Back { void *host; void *dev; size_t bytes; };
+    struct Back { void *host; void *dev; size_t bytes; bool staged; };
     Ctx *ctx_ = nullptr;
     cudaStream_t stream_ = nullptr;
     int status_ = QK_OK;
@@ -65,7 +72,12 @@ private:
     int prev_dev_ = -1;
     std::vector<void *> temps_;
     std::vector<Back> backs_;
+    bool staged_ = false;            // this call holds the device's small-call stage
+    bool stage_used_ = false, stage_host_in_flight_ = false, synced_ = false;
+    size_t stage_off_ = 0;
     void *alloc(size_t bytes);
+    char *stage_alloc(size_t bytes); // nullptr when the stage is not ours or the block does not fit
+    bool in_stage(const void *p) const { return ctx_ && ctx_->stage_dev && (const char *)p >= ctx_->stage_dev && (const char *)p < ctx_->stage_dev + Ctx::kStageBytes; }
 };
 
 inline unsigned grid_for(size_t n, unsigned block, int sms, unsigned per_sm)

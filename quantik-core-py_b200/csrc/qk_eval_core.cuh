@@ -164,6 +164,53 @@ QK_HD void child_reply_masks(uint32_t opp_lo, uint32_t opp_hi, int action, uint3
     chi = opp_hi & ~bit2 & ~(s < 2 ? 0u : closed);
 }
 
+// ---- a child's features from its PARENT's data (k_playout_guided scores the children of a position without
+// building them).  A threat line -- three pieces, three shapes -- has one empty square and one missing shape, and a
+// player "can complete" it (evaluation.py:99-112, :170-175) exactly when that placement is among his legal moves;
+// the legal moves of both players in the child follow from the parent's:
+//   the mover's:    what he could play in the parent, minus the square just taken, minus the whole shape if this was
+//                   its second piece (`once` = his shapes with exactly one piece placed);
+//   the opponent's: child_reply_masks.
+QK_HD uint32_t placed_once(const State4 &s, int player)
+{
+    const uint32_t m01 = player ? s.z : s.x, m23 = player ? s.w : s.y;
+    return (popc(m01 & 0xFFFFu) == 1 ? 1u : 0u) | (popc(m01 >> 16) == 1 ? 2u : 0u) |
+           (popc(m23 & 0xFFFFu) == 1 ? 4u : 0u) | (popc(m23 >> 16) == 1 ? 8u : 0u);
+}
+QK_HD uint64_t mover_options_in_child(uint64_t parent_mask, uint32_t once, int action)
+{
+    const int shape = action >> 4;
+    uint64_t own = parent_mask & ~(0x0001000100010001ull << (action & 15));
+    if ((once >> shape) & 1u) own &= ~(0xFFFFull << (shape << 4));
+    return own;
+}
+// features from the MOVER's point of view (the side to move in the child is the opponent: sign = -1 in
+// evaluation.py:130-194); ce = the child's line fields, own64 / opp64 = 64-bit action masks of what the mover /
+// the opponent may play in the child, line_sq[l] = the squares of line l (line_squares)
+QK_HD void eval_features_child(const EvalPos &ce, uint64_t own64, uint64_t opp64, const uint32_t *line_sq, int f[6])
+{
+    const uint64_t diff = ce.occ - ce.np;
+    const uint64_t live = ~(diff | (diff >> 1)) & kLineLsb;
+    const uint64_t b0 = ce.occ, b1 = ce.occ >> 1;
+    f[5] = -popc64(b0 & ~b1 & live); f[4] = -popc64(b1 & ~b0 & live);
+    int t_own = 0, t_opp = 0, t_both = 0;
+    for (uint64_t threats = b0 & b1 & live; threats; threats &= threats - 1) {
+        const uint32_t tlo = (uint32_t)threats;
+        int bit;
+#ifdef __CUDA_ARCH__
+        bit = tlo ? __ffs((int)tlo) - 1 : 32 + __ffs((int)(uint32_t)(threats >> 32)) - 1;
+#else
+        bit = tlo ? __builtin_ctz(tlo) : 32 + __builtin_ctz((uint32_t)(threats >> 32));
+#endif
+        const uint32_t absent = ~(uint32_t)(ce.pres >> bit) & 0xFu;          // exactly one bit: the missing shape
+        const int lane16 = (int)(((absent >> 1) - (absent >> 3)) << 4);       // 1,2,4,8 -> 0,16,32,48
+        const uint32_t line = line_sq[bit >> 2];
+        const uint32_t o = ((uint32_t)(own64 >> lane16) & line) ? 1u : 0u, q = ((uint32_t)(opp64 >> lane16) & line) ? 1u : 0u;
+        t_own += (int)o; t_opp += (int)q; t_both += (int)(o & q);
+    }
+    f[0] = t_own; f[1] = t_opp; f[2] = -t_both; f[3] = -popc64(opp64);
+}
+
 QK_HD int guided_greedy_action(const State4 &cur, const EvalPos &ev, int player, uint64_t mask, const double w[6],
                                const double *tab = nullptr)
 {

@@ -59,33 +59,6 @@ struct GuidedWarp {
     unsigned char best_a[32];
 };
 
-// sortable evaluation (from the mover's point of view, evaluation.py:130-212) of the child reached by `a`, from the
-// PARENT's data: the child's line fields `ce`, what its mover (own64) and the player to move in it (opp64) may still
-// play there as 64-bit action masks, and the squares of each line (s_line).  The child itself is never built.
-// A threat line -- three pieces, three shapes -- has one empty square and one missing shape, and a player "can
-// complete" it (evaluation.py:99-112, :170-175) exactly when that placement is among his legal moves.
-__device__ __forceinline__ uint64_t dealt_child_key(const EvalPos &ce, uint64_t own64, uint64_t opp64, int n_reply,
-                                                    const uint32_t *s_line, const double *tab)
-{
-    const uint64_t diff = ce.occ - ce.np;
-    const uint64_t live = ~(diff | (diff >> 1)) & kLineLsb;
-    const uint64_t b0 = ce.occ, b1 = ce.occ >> 1;
-    int f[6];
-    f[5] = -popc64(b0 & ~b1 & live); f[4] = -popc64(b1 & ~b0 & live);        // build_one, build_two; the side to move is the opponent
-    int t_own = 0, t_opp = 0, t_both = 0;
-    for (uint64_t threats = b0 & b1 & live; threats; threats &= threats - 1) {
-        const uint32_t tlo = (uint32_t)threats;
-        const int bit = tlo ? __ffs((int)tlo) - 1 : 32 + __ffs((int)(uint32_t)(threats >> 32)) - 1;
-        const uint32_t absent = ~(uint32_t)(ce.pres >> bit) & 0xFu;          // exactly one bit: the missing shape
-        const int lane16 = (int)(((absent >> 1) - (absent >> 3)) << 4);       // 1,2,4,8 -> 0,16,32,48
-        const uint32_t line = s_line[bit >> 2];
-        const uint32_t o = ((uint32_t)(own64 >> lane16) & line) ? 1u : 0u, q = ((uint32_t)(opp64 >> lane16) & line) ? 1u : 0u;
-        t_own += (int)o; t_opp += (int)q; t_both += (int)(o & q);
-    }
-    f[0] = t_own; f[1] = t_opp; f[2] = -t_both; f[3] = -n_reply;
-    return sortable(eval_dot_tab(f, tab));
-}
-
 // The greedy moves of ALL lanes in need, worked out by the whole warp: every such lane lists its children in the
 // warp's queue, and the queue is scored 32 children per round, one per lane, whoever they belong to -- full warps
 // however few lanes need a move and however different their child counts are.  Children of one lane are consecutive
@@ -104,9 +77,7 @@ __device__ __forceinline__ int dealt_greedy_actions(bool need, const State4 &cur
     if (need) {
         uint32_t opp_lo, opp_hi;
         legal_masks(cur, 1 - player, opp_lo, opp_hi);
-        const uint32_t all = cur.x | cur.y | cur.z | cur.w, m01 = player ? cur.z : cur.x, m23 = player ? cur.w : cur.y;
-        const uint32_t once = (__popc(m01 & 0xFFFFu) == 1 ? 1u : 0u) | (__popc(m01 >> 16) == 1 ? 2u : 0u) |
-                              (__popc(m23 & 0xFFFFu) == 1 ? 4u : 0u) | (__popc(m23 >> 16) == 1 ? 8u : 0u);
+        const uint32_t all = cur.x | cur.y | cur.z | cur.w, once = placed_once(cur, player);
         GuidedSlot &g = w.slot[lane];
         g.occ_lo = (uint32_t)ev.occ; g.occ_hi = (uint32_t)(ev.occ >> 32); g.np_lo = (uint32_t)ev.np; g.np_hi = (uint32_t)(ev.np >> 32);
         g.pres_lo = (uint32_t)ev.pres; g.pres_hi = (uint32_t)(ev.pres >> 32); g.mask_lo = (uint32_t)mask; g.mask_hi = (uint32_t)(mask >> 32);
@@ -131,11 +102,10 @@ __device__ __forceinline__ int dealt_greedy_actions(bool need, const State4 &cur
         child_reply_masks(g2.x, g2.y, a, clo, chi);
         uint64_t key = have ? ~0ull : 0ull;                              // decisive: a fourth shape on a line, or no reply
         if (have && !((ce.np & (kLineLsb << 2)) != 0 || (clo | chi) == 0)) {
-            // the mover's own options in the child: the parent's, without the square just taken and without the
-            // shape just played if that was its second piece
-            uint64_t own64 = (((uint64_t)g1.w << 32) | g1.z) & ~(0x0001000100010001ull << sq);
-            if ((g2.z >> (16 + shape)) & 1u) own64 &= ~(0xFFFFull << (shape << 4));
-            key = dealt_child_key(ce, own64, ((uint64_t)chi << 32) | clo, __popc(clo) + __popc(chi), s_line, tab);
+            // scored from the parent's data (qk_eval_core.cuh: eval_features_child); the child is never built
+            int f[6];
+            eval_features_child(ce, mover_options_in_child(((uint64_t)g1.w << 32) | g1.z, g2.z >> 16, a), ((uint64_t)chi << 32) | clo, s_line, f);
+            key = sortable(eval_dot_tab(f, tab));
         }
         const unsigned seg = __match_any_sync(kFull, have ? src : 64);
         const uint32_t kh = (uint32_t)(key >> 32), mh = __reduce_max_sync(seg, kh);

@@ -13,6 +13,10 @@ import quantik_b200 as Q  # noqa: E402
 
 e = np.zeros((1, 8), np.uint16)
 ed = torch.zeros((1, 8), dtype=torch.int16, device="cuda")
+if len(sys.argv) > 1:
+    Q._native.init(0)
+    Q._native.set_option("call_stage", int(sys.argv[1]))
+    print("call_stage option =", sys.argv[1])
 for n in (1, 1000, 100_000, 1_000_000, 10_000_000):
     Q.playouts(e, n)
     t0 = time.perf_counter()

@@ -60,6 +60,36 @@ void hs_leaf_from_parent(const uint16_t *s, size_t n, uint64_t *checked, uint64_
         }
     }
 }
+// every child of every position (valid, not won): the features the guided playout kernel derives from the PARENT's
+// data against the evaluation of the child itself from its mover's point of view; -> children checked, mismatches
+void hs_child_features(const uint16_t *s, size_t n, uint64_t *checked, uint64_t *mismatch)
+{
+    uint32_t line_sq[12];
+    for (int l = 0; l < 12; ++l) line_sq[l] = line_squares(l);
+    *checked = 0; *mismatch = 0;
+    for (size_t i = 0; i < n; ++i) {
+        const State4 node = ld(s + 8 * i);
+        int player, status;
+        const uint64_t mask = movegen(node, &player, &status);
+        if (status != 0 || win_status(node) != 0) continue;
+        const EvalPos ev = eval_pos(node);
+        uint32_t opp_lo, opp_hi;
+        legal_masks(node, 1 - player, opp_lo, opp_hi);
+        const uint32_t once = placed_once(node, player);
+        for (int a = 0; a < 64; ++a) {
+            if (!((mask >> a) & 1)) continue;
+            EvalPos ce = ev;
+            eval_pos_place(ce, a >> 4, a & 15);
+            uint32_t clo, chi;
+            child_reply_masks(opp_lo, opp_hi, a, clo, chi);
+            int f0[6], f1[6];
+            eval_features_child(ce, mover_options_in_child(mask, once, a), ((uint64_t)chi << 32) | clo, line_sq, f0);
+            eval_features(apply_action(node, player, a), player, f1);
+            ++*checked;
+            for (int k = 0; k < 6; ++k) if (f0[k] != f1[k]) { ++*mismatch; break; }
+        }
+    }
+}
 void hs_features(const uint16_t *s, const uint8_t *pl, size_t n, double *out)
 { for (size_t i = 0; i < n; ++i) { int f[6]; eval_features(ld(s + 8 * i), pl[i], f); for (int k = 0; k < 6; ++k) out[6 * i + k] = f[k]; } }
 void hs_guided(const uint16_t *roots, size_t n_roots, uint32_t rollouts, uint64_t seed, uint64_t first, uint32_t root_base,

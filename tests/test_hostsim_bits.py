@@ -181,6 +181,17 @@ def test_eval_features_and_guided_policy(hs):
         assert np.array_equal(oc, o["outcome"]) and np.array_equal(pl, o["plies"]), (eps, mp, nr)
 
 
+def test_child_features_from_parent_data(hs):
+    """k_playout_guided scores a child without building it: its line fields come from the parent's plus one table word,
+    and a threat line counts for a player exactly when the completing placement is among his legal moves, which follow
+    from the parent's (qk_eval_core.cuh: eval_features_child).  Same six features as evaluating the child itself
+    (evaluation.py:130-194), for every child of 24 000 reachable positions."""
+    s = np.ascontiguousarray(O.make_roots(24000, seed=321, min_plies=0, span=15))
+    checked, bad = ctypes.c_uint64(0), ctypes.c_uint64(0)
+    hs.hs_child_features(P(s), ctypes.c_size_t(len(s)), ctypes.byref(checked), ctypes.byref(bad))
+    assert checked.value > 200_000 and bad.value == 0, (checked.value, bad.value)
+
+
 def test_fuzz_random_boards_vs_oracle(hs):
     """Hypothesis-style sweep (tests/test_core.py:126-181 of the reference): arbitrary 8 x 16-bit boards -- reachable,
     sparse garbage and dense garbage -- through the kernels' rule code vs the oracle's literal loops."""

@@ -467,6 +467,55 @@ def test_perft_is_symmetry_invariant():
         assert np.array_equal(base[k], img[k])
 
 
+def test_part_streams_and_table_sizes_do_not_change_the_merge(options):
+    """The two-level merge with 1-4 part tables in flight (side streams) and part tables from 1 MiB (many parts) to larger
+    than the input needs (two parts, fewer than the streams) returns the same classes and multiplicities as the one table."""
+    states = B.random_roots(1 << 20, seed=5, min_plies=2, span=7)
+    wts = np.random.default_rng(2).integers(1, 1 << 33, len(states)).astype(np.uint64)
+    options("dedup_mode", 1)
+    want = B.canon_dedup(states, wts)
+    options("dedup_mode", 2)
+    for streams, mb in ((1, 1), (2, 1), (3, 4), (4, 16), (4, 512), (2, 0)):
+        options("dedup_streams", streams)
+        options("dedup_part_mb", mb)
+        u, m = B.canon_dedup(states, wts)
+        assert np.array_equal(u, want[0]) and np.array_equal(m, want[1]), (streams, mb)
+
+
+def test_small_call_staging_block_is_transparent(options):
+    """Host buffers of small calls travel through the per-device staging block (pinned + device, 256 KiB); larger ones
+    and calls made with the block switched off go through the memory pool.  Same results either way, also for a call
+    whose buffers only partly fit, and for device-buffer calls on two streams that share the block for their scratch."""
+    import torch
+    small, big = _random_positions(500, seed=21), _random_positions(40_000, seed=22)      # 8 KB / 640 KB of states
+    e = np.zeros((1, 8), np.uint16)
+    res = {}
+    for stage in (1, 0):
+        options("call_stage", stage)
+        res[stage] = (B.movegen_masks(small), B.canonical_payloads(small), B.win_status(big), B.canonical_payloads(big),
+                      B.playouts(e, 4096, seed=SEED), B.perft(e, 4), B.canon_dedup(small))
+    for a, b in zip(res[0], res[1]):
+        if isinstance(a, dict):
+            assert all(np.array_equal(a[k], b[k]) for k in a)
+        elif isinstance(a, tuple):
+            assert all(np.array_equal(x, y) for x, y in zip(a, b))
+        else:
+            assert np.array_equal(a, b)
+    # two streams, device buffers: the stage's scratch is handed from one stream to the other through an event
+    options("call_stage", 0)
+    roots = torch.from_numpy(B.random_roots(64, seed=3, min_plies=3, span=6).view(np.int16)).cuda()
+    want = B.playouts(roots, 512, seed=SEED)
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    torch.cuda.synchronize()
+    outs = []
+    for rep in range(6):
+        with torch.cuda.stream(s1 if rep % 2 == 0 else s2):
+            outs.append(B.playouts(roots, 512, seed=SEED))
+    torch.cuda.synchronize()
+    for o in outs:
+        assert all(np.array_equal(np.asarray(o[k].cpu() if hasattr(o[k], "cpu") else o[k]), np.asarray(want[k].cpu() if hasattr(want[k], "cpu") else want[k])) for k in ("wins_p0", "wins_p1", "draws"))
+
+
 # ----------------------------------------------------------------------------- canonical BFS (SURVEY 8f-1)
 def test_symmetry_table_bfs_reproduces_published_table_with_unique_counts(options):
     # GAME_TREE_ANALYSIS.md:4-11: total legal moves, unique canonical, P0 wins, P1 wins, ongoing

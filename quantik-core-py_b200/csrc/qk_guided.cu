@@ -67,7 +67,7 @@ struct GuidedWarp {
 // of all (first decisive child, else first best child -- mcts.py:362-383), and across rounds an owner keeps the
 // earlier winner unless a later one is strictly better.
 __device__ __forceinline__ int dealt_greedy_actions(bool need, const State4 &cur, const EvalPos &ev, int player, uint64_t mask,
-                                                    uint32_t n_mine, GuidedWarp &w, const uint32_t *s_line, const double *tab)
+                                                    uint32_t n_mine, GuidedWarp &w, const uint32_t *s_line, const uint4 *s_sq, const double *tab)
 {
     const unsigned lane = threadIdx.x & 31u;
     uint32_t incl = n_mine;
@@ -96,15 +96,23 @@ __device__ __forceinline__ int dealt_greedy_actions(bool need, const State4 &cur
         const int src = (int)(e >> 6), a = (int)(e & 63u), shape = a >> 4, sq = a & 15;
         const uint4 g0 = *reinterpret_cast<const uint4 *>(&w.slot[src].occ_lo), g1 = *reinterpret_cast<const uint4 *>(&w.slot[src].pres_lo),
                     g2 = *reinterpret_cast<const uint4 *>(&w.slot[src].opp_lo);
+        // per-square table: the fields of the three lines through the square (line_fields), its scope, its bit in both lanes
+        const uint4 q = s_sq[sq];
+        const uint64_t lf = ((uint64_t)q.y << 32) | q.x;
         EvalPos ce = { ((uint64_t)g0.y << 32) | g0.x, ((uint64_t)g0.w << 32) | g0.z, ((uint64_t)g1.y << 32) | g1.x };
-        eval_pos_place(ce, shape, sq);
-        uint32_t clo, chi;
-        child_reply_masks(g2.x, g2.y, a, clo, chi);
+        ce.occ += lf; ce.np += lf & ~(ce.pres >> shape); ce.pres |= lf << shape;             // eval_pos_place
+        // what the opponent may answer (child_reply_masks): not the square, not the shape inside the square's scope
+        const uint32_t closed = q.z << ((shape & 1) << 4);
+        const uint32_t clo = g2.x & ~(q.w | (shape < 2 ? closed : 0u)), chi = g2.y & ~(q.w | (shape < 2 ? 0u : closed));
         uint64_t key = have ? ~0ull : 0ull;                              // decisive: a fourth shape on a line, or no reply
         if (have && !((ce.np & (kLineLsb << 2)) != 0 || (clo | chi) == 0)) {
-            // scored from the parent's data (qk_eval_core.cuh: eval_features_child); the child is never built
+            // scored from the parent's data (qk_eval_core.cuh: eval_features_child); the child is never built.
+            // The mover's own options (mover_options_in_child): the parent's without the square, and without the
+            // shape if this was its second piece
+            const uint32_t gone = ((g2.z >> (16 + shape)) & 1u) ? 0xFFFFu << ((shape & 1) << 4) : 0u;
+            const uint32_t olo = g1.z & ~(q.w | (shape < 2 ? gone : 0u)), ohi = g1.w & ~(q.w | (shape < 2 ? 0u : gone));
             int f[6];
-            eval_features_child(ce, mover_options_in_child(((uint64_t)g1.w << 32) | g1.z, g2.z >> 16, a), ((uint64_t)chi << 32) | clo, s_line, f);
+            eval_features_child(ce, ((uint64_t)ohi << 32) | olo, ((uint64_t)chi << 32) | clo, s_line, f);
             key = sortable(eval_dot_tab(f, tab));
         }
         const unsigned seg = __match_any_sync(kFull, have ? src : 64);
@@ -128,7 +136,12 @@ __global__ void __launch_bounds__(kBlock) k_playout_guided(const uint4 *__restri
     __shared__ double s_tab[6 * kEvalTabStride];
     __shared__ GuidedWarp s_warp[kBlock / 32];
     __shared__ uint32_t s_line[12];
+    __shared__ uint4 s_sq[16];
     if (threadIdx.x < 12) s_line[threadIdx.x] = line_squares((int)threadIdx.x);
+    if (threadIdx.x < 16) {
+        const uint64_t lf = line_fields((int)threadIdx.x);
+        s_sq[threadIdx.x] = make_uint4((uint32_t)lf, (uint32_t)(lf >> 32), scope_of_square((int)threadIdx.x), 0x00010001u << threadIdx.x);
+    }
 #pragma unroll
     for (int i = 0; i < 6; ++i)
         for (int v = threadIdx.x; v < kEvalTabStride; v += kBlock) s_tab[i * kEvalTabStride + v] = __dmul_rn(weights.w[i], (double)(v - 64));
@@ -191,7 +204,7 @@ __global__ void __launch_bounds__(kBlock) k_playout_guided(const uint4 *__restri
                 // with a per-ply choice and 3.3e8 with every lane scanning its own children: the dealt child is also
                 // the cheaper one to score); the lane-serial scan is kept for the parity tests
                 if (scoring != 1) {
-                    const int a = dealt_greedy_actions(need, cur, ev, player, mask, n_mine, s_warp[threadIdx.x >> 5], s_line, s_tab);
+                    const int a = dealt_greedy_actions(need, cur, ev, player, mask, n_mine, s_warp[threadIdx.x >> 5], s_line, s_sq, s_tab);
                     if (need) action = a;
                 } else if (need) action = guided_greedy_action(cur, ev, player, mask, weights.w, s_tab);
             }

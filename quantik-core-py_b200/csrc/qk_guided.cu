@@ -158,6 +158,7 @@ __global__ void __launch_bounds__(kBlock) k_playout_guided(const uint4 *__restri
         EvalPos ev = eval_pos(cur);
         const GuidedLine *line = lines ? lines + root : nullptr;
         bool on_line = line != nullptr;
+        int p0 = on_line ? (int)line->player : -1;      // the mover at the root, once known (the line of a finished or invalid root has no moves)
         const uint64_t rollout = first_rollout + j;
         int result = 0, plies = 0;
         Philox4 rnd = { { 0, 0, 0, 0 } };
@@ -170,12 +171,25 @@ __global__ void __launch_bounds__(kBlock) k_playout_guided(const uint4 *__restri
                 else if (on_line) {
                     if (ply == (int)line->len) { result = line->result; done = true; }
                     else player = (line->player + ply) & 1;
-                } else {
+                } else if (p0 < 0) {
+                    // first look at a position this playout did not reach by its own moves: the full rules
                     const int ws = win_status(cur);
                     if (ws) { result = ws == 1 ? 1 : -1; done = true; }
                     else {
                         int status;
                         mask = movegen(cur, &player, &status);
+                        p0 = (player - ply) & 1;
+                        if (mask == 0) { result = player == 0 ? -1 : 1; done = true; }
+                    }
+                } else {
+                    // reached by legal moves from a valid position: it is valid, the players alternate, and a completed
+                    // line shows as a fourth shape in the line fields the playout carries (the last mover made it)
+                    player = (p0 + ply) & 1;
+                    if (ev.np & (kLineLsb << 2)) { result = player ? 1 : -1; done = true; }
+                    else {
+                        uint32_t lo, hi;
+                        legal_masks(cur, player, lo, hi);
+                        mask = ((uint64_t)hi << 32) | lo;
                         if (mask == 0) { result = player == 0 ? -1 : 1; done = true; }
                     }
                 }
@@ -191,7 +205,7 @@ __global__ void __launch_bounds__(kBlock) k_playout_guided(const uint4 *__restri
             if (!done) {
                 const uint32_t r_eps = (ply & 1) ? rnd.v[2] : rnd.v[0], r_pick = (ply & 1) ? rnd.v[3] : rnd.v[1];
                 if (epsilon > 0.0 && (double)r_eps * (1.0 / 4294967296.0) < epsilon) {
-                    if (on_line) { int status; mask = movegen(cur, &player, &status); }
+                    if (on_line) { uint32_t lo, hi; legal_masks(cur, player, lo, hi); mask = ((uint64_t)hi << 32) | lo; }
                     const uint32_t lo = (uint32_t)mask, hi = (uint32_t)(mask >> 32);
                     action = select_bit64(lo, hi, __popc(lo), (int)__umulhi(r_pick, (uint32_t)(__popc(lo) + __popc(hi))));
                     on_line = on_line && action == (int)line->action[ply];

@@ -369,12 +369,19 @@ def main():
         one_rows = [list(map(int, r)) for r in B.symmetry_table(16, device=dev)]
         boxes = D.PeerInboxes(1 << 14, dev, copies=2)
         D.fused_symmetry_table(16, device=dev, inboxes=boxes)          # sizes the inboxes for the deepest level
-        rows_f, t_fused = timed_job(lambda: D.fused_symmetry_table(16, device=dev, inboxes=boxes))
-        assert rows_f == one_rows, "fused partitioned BFS differs from the single-GPU table"
+        # both forms: one warm-up call, then the better of two timed calls (the first timed call of the two-step form
+        # still grows torch's allocator on some boxes: 1.18 s against 0.22 s on two GPUs)
+        t_fused = t_nccl = float("inf")
+        for _ in range(2):
+            rows_f, t = timed_job(lambda: D.fused_symmetry_table(16, device=dev, inboxes=boxes))
+            assert rows_f == one_rows, "fused partitioned BFS differs from the single-GPU table"
+            t_fused = min(t_fused, t)
         del boxes
         D.sharded_symmetry_table(16, device=dev)
-        rows_n, t_nccl = timed_job(lambda: D.sharded_symmetry_table(16, device=dev))
-        assert rows_n == one_rows, "NCCL partitioned BFS differs from the single-GPU table"
+        for _ in range(2):
+            rows_n, t = timed_job(lambda: D.sharded_symmetry_table(16, device=dev))
+            assert rows_n == one_rows, "NCCL partitioned BFS differs from the single-GPU table"
+            t_nccl = min(t_nccl, t)
         # (2) global canonical dedup: every rank holds 2^24 symmetric images of mid-game positions
         import itertools
         n_img = 1 << 24                                   # the size of the single-GPU canon_dedup metric below

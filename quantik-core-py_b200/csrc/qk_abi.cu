@@ -220,7 +220,7 @@ const char *qk_last_error(void) { return g_error.c_str(); }
 int qk_set_option(const char *name, long long value)
 {
     static const char *const names[OPT_COUNT] = { "perft_kernel", "perft_min_items", "perft_tile_generic", "playout_variant",
-                                                  "dedup_mode", "dedup_part_mb", "playout_grab", "grid_waves", "dedup_streams", "table_slots_x10", "guided_scoring", "call_stage" };
+                                                  "dedup_mode", "dedup_part_mb", "playout_grab", "grid_waves", "dedup_streams", "table_slots_x10", "guided_scoring", "call_stage", "perft_own_lanes" };
     QK_REQUIRE(name, "qk_set_option: name is NULL");
     for (int i = 0; i < OPT_COUNT; ++i)
         if (strcmp(name, names[i]) == 0) { g_option[i].store(value, std::memory_order_relaxed); return QK_OK; }

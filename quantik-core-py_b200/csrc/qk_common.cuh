@@ -32,7 +32,7 @@ struct Ctx {
 
 // Tuning / testing switches (qk_set_option in include/quantik_b200.h).  Process-wide, 0 = the default
 // behaviour; the library never reads the environment.
-enum Option { OPT_PERFT_KERNEL = 0, OPT_PERFT_MIN_ITEMS, OPT_PERFT_TILE_GENERIC, OPT_PLAYOUT_VARIANT, OPT_DEDUP_MODE, OPT_DEDUP_PART_MB, OPT_PLAYOUT_GRAB, OPT_GRID_WAVES, OPT_DEDUP_STREAMS, OPT_TABLE_SLOTS_X10, OPT_GUIDED_SCORING, OPT_CALL_STAGE, OPT_COUNT };
+enum Option { OPT_PERFT_KERNEL = 0, OPT_PERFT_MIN_ITEMS, OPT_PERFT_TILE_GENERIC, OPT_PLAYOUT_VARIANT, OPT_DEDUP_MODE, OPT_DEDUP_PART_MB, OPT_PLAYOUT_GRAB, OPT_GRID_WAVES, OPT_DEDUP_STREAMS, OPT_TABLE_SLOTS_X10, OPT_GUIDED_SCORING, OPT_CALL_STAGE, OPT_PERFT_OWN_LANES, OPT_COUNT };
 long long option(Option o);
 
 void set_error(const std::string &msg);

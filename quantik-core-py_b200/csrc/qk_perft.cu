@@ -498,6 +498,12 @@ template <> struct LeafAcc<false> {
         const u64 w = (u64)nw * pm, b = nm ? 0ull : pm;
         if (leaf_mover_p1) { w1 += w; b1 += b; } else { w0 += w; b0 += b; }
     }
+    __device__ __forceinline__ void add_sums(uint32_t nm, uint32_t nw, uint32_t blocked, u64 pm, bool leaf_mover_p1)
+    {
+        nodes += (u64)nm * pm;
+        const u64 w = (u64)nw * pm, b = (u64)blocked * pm;
+        if (leaf_mover_p1) { w1 += w; b1 += b; } else { w0 += w; b0 += b; }
+    }
     __device__ __forceinline__ void finish(bool) {}
 };
 template <> struct LeafAcc<true> {
@@ -509,13 +515,44 @@ template <> struct LeafAcc<true> {
         w0 += (u64)((uint32_t)nw) * m32;
         b0 += nm ? 0u : m32;
     }
+    __device__ __forceinline__ void add_sums(uint32_t nm, uint32_t nw, uint32_t blocked, u64 pm, bool)
+    {
+        const uint32_t m32 = (uint32_t)pm;
+        nodes += (u64)nm * m32;
+        w0 += (u64)nw * m32;
+        b0 += (u64)blocked * m32;
+    }
     __device__ __forceinline__ void finish(bool leaf_mover_p1)
     {
         if (leaf_mover_p1) { w1 = w0; b1 = b0; w0 = 0; b0 = 0; }
     }
 };
 
-template <bool FAST>
+// k_perft_tile, own lists: the children of shape S that this lane's node gives (bits of `word`'s S lane), evaluated by
+// the lane itself; the loop's trip count is warp-uniform.  What is left in `word` afterwards goes to the dealt stage.
+template <int S>
+__device__ __forceinline__ void own_shape(uint32_t &word, uint32_t ylo, uint32_t yhi, const Presence &pres, const TileLut *lut,
+                                          bool giver, bool longest, uint32_t &s_nm, uint32_t &s_nw, uint32_t &s_blk)
+{
+    constexpr int kShift = (S & 1) ? 16 : 0;
+    uint32_t kids = giver ? (word >> kShift) & 0xFFFFu : 0u;
+    const uint32_t mine = (uint32_t)popc(kids);
+    const uint32_t K = longest ? __reduce_max_sync(kFull, mine) : __reduce_min_sync(kFull, giver ? mine : 0xFFFFFFFFu);
+    if (K == 0) return;
+    const ShapeLoop<S> loop(ylo, yhi, pres);
+    for (uint32_t k = 0; k < K; ++k) {
+        if (kids) {
+            const int p = __ffs((int)kids) - 1;
+            kids &= kids - 1;
+            int nm, nw;
+            loop.child(lut[p], nm, nw);
+            s_nm += (uint32_t)nm; s_nw += (uint32_t)nw; s_blk += nm == 0 ? 1u : 0u;
+        }
+    }
+    word = (word & ~(0xFFFFu << kShift)) | (kids << kShift);
+}
+
+template <bool FAST, bool OWN>
 __global__ void __launch_bounds__(kTileWarps * 32) k_perft_tile(const uint4 *__restrict__ items, const u64 *__restrict__ mult,
                                                                  u64 n_items, int d0, int depth, int uniform_parity,
                                                                  u64 *__restrict__ next_item, u64 *__restrict__ counters, unsigned own_lanes)
@@ -632,27 +669,23 @@ __global__ void __launch_bounds__(kTileWarps * 32) k_perft_tile(const uint4 *__r
             }
             flush = sp < 0 || since_flush >= kTileFlushEvery;
         }
-        // ---- leaf parents, first part: when (nearly) every lane has children to give, each giver evaluates the first
-        //      K of its own -- K = the smallest list in the warp, so the loop runs with full lanes -- straight from its
-        //      registers; only what exceeds K goes to the dealt stage.  Measured: it costs about as much per leaf parent
-        //      as the dealt stage (perft(7), K = 17 of 27 children per lane: 24.65 vs 24.68 ms), but when the 32 lists of
-        //      an iteration together exceed the ring (perft(6): 1 091 children per iteration, K = 31 of 34) it replaces
-        //      the four-pass form of the dealt stage: tile kernel 1.07 -> 0.83 ms, perft(6) 1.28 -> 1.04 ms.
-        {
+        // ---- leaf parents, first part (wide trees only, see run_perft): when (nearly) every lane has children to give,
+        //      each giver evaluates children of its own straight from its registers, shape by shape (own_shape: the
+        //      lanes of a shape are compile-time masks, the other word pair's masks are hoisted out of the loop, the
+        //      counts are summed unweighted and multiplied once per node -- about 50 instructions per leaf parent
+        //      against 72 in the dealt stage, 83 for the generic evaluation in a loop).  The loop of a shape runs as
+        //      often as the longest list of that shape in the warp (own_lanes >= 64; shorter lists idle) or the
+        //      shortest; what is left goes to the dealt stage.
+        if (OWN) {
             const bool giver = (give_lo | give_hi) != 0;
-            if ((unsigned)__popc(__ballot_sync(kFull, giver)) >= own_lanes) {
-                const uint32_t K = __reduce_min_sync(kFull, giver ? (uint32_t)(popc(give_lo) + popc(give_hi)) : 0xFFFFFFFFu);
-                for (uint32_t k = 0; k < K; ++k) {
-                    if (giver) {
-                        const bool in_lo = give_lo != 0;
-                        const uint32_t w = in_lo ? give_lo : give_hi;
-                        const int action = (in_lo ? 0 : 32) + __ffs((int)w) - 1;
-                        if (in_lo) give_lo = w & (w - 1); else give_hi = w & (w - 1);
-                        int nm, nw;
-                        leaf_counts_from_parent(give_ylo, give_yhi, give_pres, action, s_lut, nm, nw);
-                        acc.add(nm, nw, m, give_mover == 0);          // the leaf parent's mover is the OTHER player
-                    }
-                }
+            if ((unsigned)__popc(__ballot_sync(kFull, giver)) >= (own_lanes & 63u)) {
+                uint32_t s_nm = 0, s_nw = 0, s_blk = 0;
+                const bool longest = own_lanes >= 64u;
+                own_shape<0>(give_lo, give_ylo, give_yhi, give_pres, s_lut, giver, longest, s_nm, s_nw, s_blk);
+                own_shape<1>(give_lo, give_ylo, give_yhi, give_pres, s_lut, giver, longest, s_nm, s_nw, s_blk);
+                own_shape<2>(give_hi, give_ylo, give_yhi, give_pres, s_lut, giver, longest, s_nm, s_nw, s_blk);
+                own_shape<3>(give_hi, give_ylo, give_yhi, give_pres, s_lut, giver, longest, s_nm, s_nw, s_blk);
+                acc.add_sums(s_nm, s_nw, s_blk, m, give_mover == 0);      // the leaf parents' mover is the OTHER player
             }
         }
         seen_kids += (uint32_t)__reduce_add_sync(kFull, kids);
@@ -896,12 +929,22 @@ int run_perft(Call &call, const uint4 *roots, const uint64_t *mult, size_t n_roo
                 int per_sm = 0;
                 const size_t smem = kTileWarps * tile_warp_bytes(rem);
                 const bool fast = one_side && small_mult && !option(OPT_PERFT_TILE_GENERIC);
-                void (*tile)(const uint4 *, const u64 *, u64, int, int, int, u64 *, u64 *, unsigned) = fast ? k_perft_tile<true> : k_perft_tile<false>;
-                const long long own_opt = option(OPT_PERFT_OWN_LANES);       // 0 = default; 33 = never
+                // Own lists (k_perft_tile<., true>) pay in the widest part of the game, where the nodes that give the leaf
+                // parents hold at most 5 pieces: every lane gives in nearly every iteration and the lists of a shape are
+                // about equally long, so the loops run to the LONGEST list of the warp (shorter ones idle) and nothing is
+                // left for the dealt stage.  From the empty board (scripts/perft_own_lanes.py): perft(6) 1.28 -> 0.82 ms,
+                // perft(7) 24.8 -> 23.3 ms, perft(8) 532 -> 558 ms (not used there: the givers hold 6 pieces).  Running to
+                // the shortest list instead leaves most children to the dealt stage (0.93 / 24.8 / 546 ms).
+                // "perft_own_lanes": 33 never | n: always, from n giving lanes on | 64 + n: ... and to the longest list.
+                const long long own_opt = option(OPT_PERFT_OWN_LANES);
+                const bool own = own_opt == 0 ? (int)head.max_pieces + depth <= 7 : own_opt != 33;
+                typedef void (*TileFn)(const uint4 *, const u64 *, u64, int, int, int, u64 *, u64 *, unsigned);
+                const TileFn tile = fast ? (own ? (TileFn)k_perft_tile<true, true> : (TileFn)k_perft_tile<true, false>)
+                                         : (own ? (TileFn)k_perft_tile<false, true> : (TileFn)k_perft_tile<false, false>);
                 QK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tile, kTileWarps * 32, smem));
                 tile<<<c->sms * (per_sm > 0 ? per_sm : 1), kTileWarps * 32, smem, s>>>(cur_s, cur_m, n_cur, d, depth,
                                                                                      (root_parity + d) & 1, d_next, d_ctr,
-                                                                                     own_opt > 0 ? (unsigned)own_opt : kTileOwnLanes);
+                                                                                     own_opt > 0 ? (unsigned)own_opt : 64u + kTileOwnLanes);
             } else if (use_lane) {
                 int per_sm = 0;
                 QK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_perft_lane, kLaneWarps * 32, 0));

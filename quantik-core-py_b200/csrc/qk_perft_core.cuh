@@ -85,6 +85,37 @@ QK_HD void leaf_counts_from_parent(uint32_t legal_lo, uint32_t legal_hi, Presenc
     n_wins = popc(lo & wab) + popc(hi & wcd);
 }
 
+// The same counts for the children of ONE shape of a node, with everything that does not depend on the square hoisted:
+// a child of shape S changes the line presence of S's word pair only (A,B live in r01/z01/c01, C,D in r23/z23/c23), so
+// the other pair's expanded masks and its "both shapes" masks are loop invariants, and the lane of S inside its word is
+// a compile-time mask.  About 40 instructions per child against 83 for leaf_counts_from_parent in a loop
+// (k_perft_tile: a lane evaluating its own children).
+template <int S> struct ShapeLoop {
+    static constexpr uint32_t kLane = (S & 1) ? 0xFFFF0000u : 0x0000FFFFu;
+    uint32_t legal_own, legal_oth;            // what the child's mover could play one ply earlier: the pair holding S / the other pair
+    uint32_t r_own, z_own, c_own;             // presence words of S's pair
+    uint32_t R_oth, Z_oth, C_oth;             // the other pair's presence, expanded to squares
+    uint32_t rb_oth, zb_oth, cb_oth;          // ... and where BOTH its shapes are present, replicated in both lanes
+    QK_HD ShapeLoop(uint32_t legal_lo, uint32_t legal_hi, const Presence &p)
+    {
+        legal_own = S < 2 ? legal_lo : legal_hi; legal_oth = S < 2 ? legal_hi : legal_lo;
+        r_own = S < 2 ? p.r01 : p.r23; z_own = S < 2 ? p.z01 : p.z23; c_own = S < 2 ? p.c01 : p.c23;
+        R_oth = (S < 2 ? p.r23 : p.r01) * 0xFu; Z_oth = (S < 2 ? p.z23 : p.z01) * 0x33u; C_oth = (S < 2 ? p.c23 : p.c01) * 0x1111u;
+        rb_oth = R_oth & swap_lanes(R_oth); zb_oth = Z_oth & swap_lanes(Z_oth); cb_oth = C_oth & swap_lanes(C_oth);
+    }
+    // the child that puts shape S on the square of table entry e
+    QK_HD void child(const TileLut &e, int &n_moves, int &n_wins) const
+    {
+        const uint32_t own = legal_own & ~(e.bit2 | (e.scope2 & kLane)), oth = legal_oth & ~e.bit2;
+        const uint32_t R = (r_own | (e.row2 & kLane)) * 0xFu, Z = (z_own | (e.zone2 & kLane)) * 0x33u, C = (c_own | (e.col2 & kLane)) * 0x1111u;
+        // winning squares as in winning_from_presence: own pair needs both shapes of the other pair plus its partner lane
+        const uint32_t win_own = swap_lanes((R & rb_oth) | (Z & zb_oth) | (C & cb_oth));
+        const uint32_t win_oth = swap_lanes((R_oth & R & swap_lanes(R)) | (Z_oth & Z & swap_lanes(Z)) | (C_oth & C & swap_lanes(C)));
+        n_moves = popc(own) + popc(oth);
+        n_wins = popc(own & win_own) + popc(oth & win_oth);
+    }
+};
+
 // same, when the caller already knows who is to move (depth parity): saves the four popcounts of piece_balance
 QK_HD void leaf_parent_counts_for(const State4 &s, int mover, int &n_moves, int &n_wins)
 {

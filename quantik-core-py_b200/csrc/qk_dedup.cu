@@ -895,11 +895,13 @@ int run_dedup(Call &call, const uint4 *states, const uint64_t *mult, size_t n, i
     Ctx *c = call.ctx();
     const bool unsorted = (color_swap & QK_DEDUP_UNSORTED) != 0;
     const size_t expected = n < cap ? n : cap;
-    // two-level merge when the one-level table would not stay in L2 (qk_set_option "dedup_mode": 1 = never, 2 = always)
+    // two-level merge for all but small inputs (qk_set_option "dedup_mode": 1 = never, 2 = always)
     const long long mode = option(OPT_DEDUP_MODE);
     Buckets b;
     size_t per_block = 0;
-    if (mode != 1 && (mode == 2 || (expected + expected / 2) * sizeof(TSlot) > 2 * l2_table_bytes()) &&
+    // measured (scripts/dedup_threshold.py, whole call, one table / two-level): 2^18 keys 0.098 / 0.113 ms, 2^19 0.134 / 0.123,
+    // 2^20 0.207 / 0.148, 2^22 0.575 / 0.347, 2^24 1.48 / 1.06, 2^25 2.48 / 2.26 -- the routed form wins from half a million keys on
+    if (mode != 1 && (mode == 2 || (expected + expected / 2) * sizeof(TSlot) > (24u << 20)) &&
         plan_two_level(n, expected, c->sms, dedup_streams(), b, per_block)) {
         int rc = alloc_buckets(call, b, mult != nullptr);
         if (rc != QK_OK) return rc;

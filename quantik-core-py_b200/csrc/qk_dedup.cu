@@ -825,9 +825,10 @@ static int dedup_streams()
 // splitting the L2 between the tables instead (2 x 48 MiB: 1.31 ms, 4 x 24 MiB: 1.55 ms) loses -- twice the parts,
 // twice the launches.  The parts are independent -- different keys, different tables; they share only the append
 // cursor and the counters, which are atomics.
-static int merge_buckets(Call &call, const Buckets &b, int streams, u64 *meta, size_t expected_unique, uint16_t *uniq,
-                         uint64_t *uniq_mult, size_t cap, size_t *n_uniq, bool sort_output, const char *who, bool *fallback,
-                         uint64_t *h_stats = nullptr)
+struct DenseClasses { Slot *keys; u64 *mults; size_t padded, n; u64 all_ones_mult; };   // n classes + the all-ones payload's multiplicity (0 = absent)
+
+static int merge_buckets_dense(Call &call, const Buckets &b, int streams, u64 *meta, size_t expected_unique, bool sort_output,
+                               DenseClasses &out, bool *fallback, uint64_t *h_stats = nullptr)
 {
     cudaStream_t s = call.stream();
     Ctx *c = call.ctx();
@@ -869,14 +870,26 @@ static int merge_buckets(Call &call, const Buckets &b, int streams, u64 *meta, s
     QK_CUDA(cudaStreamSynchronize(s));
     if ((int)h_meta[3] != 0) { *fallback = true; return QK_OK; }         // a range or the part table was too small
     if (h_stats) for (int i = 0; i < 5; ++i) h_stats[i] = h_meta[4 + i];
-    const size_t nu = (size_t)h_meta[0];
-    const bool special = h_meta[1] != 0;
-    if (nu + (special ? 1 : 0) > cap && (uniq || uniq_mult)) {
-        *n_uniq = nu + (special ? 1 : 0);
+    call.release(table);
+    out.keys = keys; out.mults = mults; out.padded = padded; out.n = (size_t)h_meta[0]; out.all_ones_mult = h_meta[1];
+    return QK_OK;
+}
+
+// ... and into the caller's buffers
+static int merge_buckets(Call &call, const Buckets &b, int streams, u64 *meta, size_t expected_unique, uint16_t *uniq,
+                         uint64_t *uniq_mult, size_t cap, size_t *n_uniq, bool sort_output, const char *who, bool *fallback,
+                         uint64_t *h_stats = nullptr)
+{
+    DenseClasses d;
+    const int rc = merge_buckets_dense(call, b, streams, meta, expected_unique, sort_output, d, fallback, h_stats);
+    if (rc != QK_OK || *fallback) return rc;
+    const bool special = d.all_ones_mult != 0;
+    if (d.n + (special ? 1 : 0) > cap && (uniq || uniq_mult)) {
+        *n_uniq = d.n + (special ? 1 : 0);
         set_error(std::string(who) + ": more distinct canonical states than `cap`");
         return QK_E_NOMEM;
     }
-    return dedup_emit_dense(call, keys, mults, padded, nu, special, h_meta[1], uniq, uniq_mult, n_uniq, sort_output);
+    return dedup_emit_dense(call, d.keys, d.mults, d.padded, d.n, special, d.all_ones_mult, uniq, uniq_mult, n_uniq, sort_output);
 }
 
 static int alloc_buckets(Call &call, Buckets &b, bool with_mults)
@@ -1093,6 +1106,46 @@ __global__ void __launch_bounds__(kBlock) k_dedup_scatter(const TSlot *table, si
     }
 }
 
+// the same from a dense list of classes (the two-level merge's output): every entry is a class
+__global__ void __launch_bounds__(kBlock) k_dense_scatter(const Slot *__restrict__ keys, const u64 *__restrict__ mults, size_t n, Peers p,
+                                                           u64 *cursor, int *overflow)
+{
+    __shared__ unsigned s_cnt[QK_MAX_WORLD];
+    __shared__ u64 s_base[QK_MAX_WORLD];
+    const size_t stride = (size_t)gridDim.x * kBlock;
+    const size_t rounds = (n + stride - 1) / stride;
+    for (size_t round = 0; round < rounds; ++round) {
+        const size_t i = round * stride + blockIdx.x * (size_t)kBlock + threadIdx.x;
+        if (threadIdx.x < QK_MAX_WORLD) s_cnt[threadIdx.x] = 0;
+        __syncthreads();
+        const bool have = i < n;
+        Slot k = { 0, 0 };
+        u64 m = 0;
+        int dst = 0;
+        unsigned r = 0;
+        if (have) {
+            k = keys[i]; m = mults[i];
+            dst = owner_of(k.hi, k.lo, p.world);
+            r = atomicAdd(&s_cnt[dst], 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x < (unsigned)p.world && s_cnt[threadIdx.x])
+            s_base[threadIdx.x] = atomicAdd(cursor + threadIdx.x, (u64)s_cnt[threadIdx.x]);
+        __syncthreads();
+        if (have) {
+            const u64 pos = s_base[dst] + r;
+            if (pos < p.slots_per_src) {
+                const InboxView v = inbox_view(p.inbox[dst], p.world, p.slots_per_src);
+                const size_t at = (size_t)p.rank * p.slots_per_src + pos;
+                v.keys[at] = k;
+                v.mults[at] = m;
+            } else {
+                *overflow = 1;
+            }
+        }
+    }
+}
+
 // after the scatter: the all-ones payload (kept outside the table) joins its owner's region, and every
 // destination learns how many entries this source wrote
 __global__ void k_scatter_publish(Peers p, u64 *cursor, u64 all_ones_mult)
@@ -1127,24 +1180,18 @@ __global__ void __launch_bounds__(kBlock) k_inbox_insert(const Slot *keys, const
     flush_claims(claims, n_unique, overflow, max_unique);
 }
 
-// local table -> peers; h_stats (5 x u64, may be null), h_sent (world x u64, may be null)
-static int scatter_finish(Call &call, DedupTable &t, const Peers &peers, uint64_t *h_stats, uint64_t *h_sent, const char *who)
+// classes (a local table, or a dense list) -> peers; h_sent (world x u64, may be null)
+static int deliver(Call &call, const DedupTable *t, const DenseClasses *d, u64 all_ones_mult, const Peers &peers, uint64_t *h_sent,
+                   const char *who)
 {
     cudaStream_t s = call.stream();
     Ctx *c = call.ctx();
-    u64 h_meta[10];
-    QK_CUDA(cudaMemcpyAsync(h_meta, t.meta, sizeof h_meta, cudaMemcpyDeviceToHost, s));
-    QK_CUDA(cudaStreamSynchronize(s));
-    if (h_stats) for (int i = 0; i < 5; ++i) h_stats[i] = h_meta[4 + i];
-    if ((int)h_meta[3] != 0) {
-        set_error(std::string(who) + ": more distinct canonical states than the local table holds");
-        return QK_E_NOMEM;
-    }
     u64 *cursor = (u64 *)call.temp((QK_MAX_WORLD + 1) * sizeof(u64), true);     // [QK_MAX_WORLD] = overflow flag
     if (!cursor) return call.status();
     int *overflow = (int *)(cursor + QK_MAX_WORLD);
-    k_dedup_scatter<<<grid_for(t.slots, kBlock, c->sms, 8), kBlock, 0, s>>>(t.table, t.slots, peers, cursor, overflow);
-    k_scatter_publish<<<1, 32, 0, s>>>(peers, cursor, h_meta[1]);
+    if (t) k_dedup_scatter<<<grid_for(t->slots, kBlock, c->sms, 8), kBlock, 0, s>>>(t->table, t->slots, peers, cursor, overflow);
+    else if (d->n) k_dense_scatter<<<grid_for(d->n, kBlock, c->sms, 8), kBlock, 0, s>>>(d->keys, d->mults, d->n, peers, cursor, overflow);
+    k_scatter_publish<<<1, 32, 0, s>>>(peers, cursor, all_ones_mult);
     QK_CUDA(cudaGetLastError());
     u64 h_cursor[QK_MAX_WORLD + 1];
     QK_CUDA(cudaMemcpyAsync(h_cursor, cursor, sizeof h_cursor, cudaMemcpyDeviceToHost, s));
@@ -1161,10 +1208,48 @@ static int scatter_finish(Call &call, DedupTable &t, const Peers &peers, uint64_
     return QK_OK;
 }
 
+// local table -> peers; h_stats (5 x u64, may be null), h_sent (world x u64, may be null)
+static int scatter_finish(Call &call, DedupTable &t, const Peers &peers, uint64_t *h_stats, uint64_t *h_sent, const char *who)
+{
+    cudaStream_t s = call.stream();
+    u64 h_meta[10];
+    QK_CUDA(cudaMemcpyAsync(h_meta, t.meta, sizeof h_meta, cudaMemcpyDeviceToHost, s));
+    QK_CUDA(cudaStreamSynchronize(s));
+    if (h_stats) for (int i = 0; i < 5; ++i) h_stats[i] = h_meta[4 + i];
+    if ((int)h_meta[3] != 0) {
+        set_error(std::string(who) + ": more distinct canonical states than the local table holds");
+        return QK_E_NOMEM;
+    }
+    return deliver(call, &t, nullptr, h_meta[1], peers, h_sent, who);
+}
+
 int run_dedup_scatter(Call &call, const uint4 *states, const uint64_t *mult, size_t n, int flags, const Peers &peers, uint64_t *h_sent)
 {
     cudaStream_t s = call.stream();
     Ctx *c = call.ctx();
+    // the local merge in two-level form (as run_dedup chooses it), its dense output delivered directly
+    const long long mode = option(OPT_DEDUP_MODE);
+    Buckets b;
+    size_t per_block = 0;
+    if (n && mode != 1 && (mode == 2 || (n + n / 2) * sizeof(TSlot) > (24u << 20)) && plan_two_level(n, n, c->sms, dedup_streams(), b, per_block)) {
+        int rc = alloc_buckets(call, b, mult != nullptr);
+        if (rc != QK_OK) return rc;
+        u64 *meta = (u64 *)call.temp(10 * sizeof(u64), true);
+        if (!meta) return call.status();
+        const size_t smem = (size_t)b.parts * sizeof(unsigned);
+        if (flags & 1)
+            k_bucket_states<true><<<b.blocks, kBlock, smem, s>>>(states, (const u64 *)mult, n, per_block, b, meta + 1, (int *)(meta + 3));
+        else
+            k_bucket_states<false><<<b.blocks, kBlock, smem, s>>>(states, (const u64 *)mult, n, per_block, b, meta + 1, (int *)(meta + 3));
+        QK_CUDA(cudaGetLastError());
+        DenseClasses d;
+        bool fallback = false;
+        rc = merge_buckets_dense(call, b, dedup_streams(), meta, n, false, d, &fallback);
+        if (rc != QK_OK) return rc;
+        call.release(b.keys); call.release(b.counts);
+        if (b.mults) call.release(b.mults);
+        if (!fallback) return deliver(call, nullptr, &d, d.all_ones_mult, peers, h_sent, "qk_canon_dedup_scatter");
+    }
     DedupTable t;
     int rc = dedup_begin(call, n, t);
     if (rc != QK_OK) return rc;

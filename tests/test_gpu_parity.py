@@ -823,11 +823,15 @@ def test_exchange_step_functions_at_world_size_one_and_two_gpus():
         assert rec["fused_bfs_matches_single_gpu"] and rec["fused_dedup_matches_single_gpu"]      # peer-memory path
 
 
-def test_fused_exchange_with_emulated_ranks_on_one_gpu():
+@pytest.mark.parametrize("dedup_mode", [1, 2])
+def test_fused_exchange_with_emulated_ranks_on_one_gpu(options, dedup_mode):
     """qk_canon_dedup_scatter / qk_bfs_level_scatter / qk_inbox_merge with W ranks played by ONE GPU (every inbox
     is a local buffer): the owners' shares must be disjoint and add up to the single-table result; a BFS run
-    through the inboxes must give the published table.  The real peer-memory run is scripts/multi_gpu_bfs.py."""
+    through the inboxes must give the published table.  The real peer-memory run is scripts/multi_gpu_bfs.py.
+    dedup_mode 1 / 2: the local merge in one table (delivered from the table) / in two-level form (delivered from
+    its dense list of classes)."""
     import torch
+    options("dedup_mode", dedup_mode)
     W, sps = 3, 40_000
     nbytes = B.inbox_bytes(W, sps)
     bufs = [torch.empty(nbytes, dtype=torch.uint8, device="cuda:0") for _ in range(W)]

@@ -55,8 +55,16 @@ void hs_leaf_from_parent(const uint16_t *s, size_t n, uint64_t *checked, uint64_
             int m0, w0, m1, w1;
             leaf_parent_counts_for(apply_action(node, mover, a), mover ^ 1, m0, w0);
             leaf_counts_from_parent(ylo, yhi, pres, a, lut, m1, w1);
+            // the shape-specialised form with the other word pair's masks hoisted (k_perft_tile's own lists)
+            int m2 = -1, w2 = -1;
+            switch (a >> 4) {
+            case 0: ShapeLoop<0>(ylo, yhi, pres).child(lut[a & 15], m2, w2); break;
+            case 1: ShapeLoop<1>(ylo, yhi, pres).child(lut[a & 15], m2, w2); break;
+            case 2: ShapeLoop<2>(ylo, yhi, pres).child(lut[a & 15], m2, w2); break;
+            default: ShapeLoop<3>(ylo, yhi, pres).child(lut[a & 15], m2, w2); break;
+            }
             ++*checked;
-            if (m0 != m1 || w0 != w1) ++*mismatch;
+            if (m0 != m1 || w0 != w1 || m0 != m2 || w0 != w2) ++*mismatch;
         }
     }
 }

@@ -137,7 +137,8 @@ def test_leaf_parent_bulk_counts(hs):
 
 def test_leaf_parent_from_parent_data(hs):
     """The perft tile kernel never materialises a leaf parent: its legal squares and line presence are derived from
-    its parent's.  Same counts as the direct evaluation, for every non-winning child of reachable positions."""
+    its parent's -- in the generic form (dealt stage) and in the shape-specialised form with hoisted masks (own lists).
+    Same counts as the direct evaluation, for every non-winning child of reachable positions."""
     d = np.load(os.path.join(G, "states_reference.npz"))
     nv = int(d["n_valid"])
     s = np.concatenate([d["states"][:nv][d["win"][:nv] == 0], O.make_roots(4000, seed=99, min_plies=0, span=14)])

@@ -80,7 +80,7 @@ QK_API const char *qk_last_error(void);
  *   "perft_tile_generic"  1: k_perft_tile without the one-side / 32-bit-multiplicity fast form
  *   "perft_own_lanes"     k_perft_tile, lanes evaluating children of their own instead of dealing them: 0 auto (wide
  *                         trees only) | 33 never | n = 1..32 always, from n giving lanes of a warp on, loops as long
- *                         as the shortest list | 64 + n: ... as long as the longest list
+ *                         as the shortest list | 64 + n: ... as the longest list | 128 + n: ... as the mean length
  *   "playout_variant"     0 auto | 2 the general kernel for every case | 3 / 4 the predicated tallies-only kernels at
  *                         5 / 6 resident CTAs per SM instead of 4 | 1 / 6 the older single-root kernels
  *   "dedup_mode"          0 auto | 1 one-level table insert | 2 partitioned (two-level) insert

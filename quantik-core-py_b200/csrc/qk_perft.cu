@@ -532,12 +532,17 @@ template <> struct LeafAcc<true> {
 // the lane itself; the loop's trip count is warp-uniform.  What is left in `word` afterwards goes to the dealt stage.
 template <int S>
 __device__ __forceinline__ void own_shape(uint32_t &word, uint32_t ylo, uint32_t yhi, const Presence &pres, const TileLut *lut,
-                                          bool giver, bool longest, uint32_t &s_nm, uint32_t &s_nw, uint32_t &s_blk)
+                                          bool giver, unsigned mode, uint32_t n_givers, uint32_t &s_nm, uint32_t &s_nw, uint32_t &s_blk)
 {
     constexpr int kShift = (S & 1) ? 16 : 0;
     uint32_t kids = giver ? (word >> kShift) & 0xFFFFu : 0u;
     const uint32_t mine = (uint32_t)popc(kids);
-    const uint32_t K = longest ? __reduce_max_sync(kFull, mine) : __reduce_min_sync(kFull, giver ? mine : 0xFFFFFFFFu);
+    // trip count: the shortest list of the warp (full lanes, the rest is dealt), the longest (nothing left to deal, shorter
+    // lists idle), or the mean (most children covered, most lanes busy)
+    uint32_t K;
+    if (mode == 1) K = __reduce_max_sync(kFull, mine);
+    else if (mode == 2) K = ((uint32_t)__reduce_add_sync(kFull, mine) + n_givers / 2) / n_givers;
+    else K = __reduce_min_sync(kFull, giver ? mine : 0xFFFFFFFFu);
     if (K == 0) return;
     const ShapeLoop<S> loop(ylo, yhi, pres);
     for (uint32_t k = 0; k < K; ++k) {
@@ -675,17 +680,18 @@ __global__ void __launch_bounds__(kTileWarps * 32, 8) k_perft_tile(const uint4 *
         //      lanes of a shape are compile-time masks, the other word pair's masks are hoisted out of the loop, the
         //      counts are summed unweighted and multiplied once per node -- about 50 instructions per leaf parent
         //      against 72 in the dealt stage, 83 for the generic evaluation in a loop).  The loop of a shape runs as
-        //      often as the longest list of that shape in the warp (own_lanes >= 64; shorter lists idle) or the
-        //      shortest; what is left goes to the dealt stage.
+        //      often as the shortest / the longest / the mean list of that shape in the warp (own_lanes >> 6 = 0 / 1 / 2);
+        //      what is left goes to the dealt stage.
         if (OWN) {
             const bool giver = (give_lo | give_hi) != 0;
-            if ((unsigned)__popc(__ballot_sync(kFull, giver)) >= (own_lanes & 63u)) {
+            const uint32_t n_givers = (uint32_t)__popc(__ballot_sync(kFull, giver));
+            if (n_givers >= (own_lanes & 63u) && n_givers) {
                 uint32_t s_nm = 0, s_nw = 0, s_blk = 0;
-                const bool longest = own_lanes >= 64u;
-                own_shape<0>(give_lo, give_ylo, give_yhi, give_pres, s_lut, giver, longest, s_nm, s_nw, s_blk);
-                own_shape<1>(give_lo, give_ylo, give_yhi, give_pres, s_lut, giver, longest, s_nm, s_nw, s_blk);
-                own_shape<2>(give_hi, give_ylo, give_yhi, give_pres, s_lut, giver, longest, s_nm, s_nw, s_blk);
-                own_shape<3>(give_hi, give_ylo, give_yhi, give_pres, s_lut, giver, longest, s_nm, s_nw, s_blk);
+                const unsigned mode = own_lanes >> 6;
+                own_shape<0>(give_lo, give_ylo, give_yhi, give_pres, s_lut, giver, mode, n_givers, s_nm, s_nw, s_blk);
+                own_shape<1>(give_lo, give_ylo, give_yhi, give_pres, s_lut, giver, mode, n_givers, s_nm, s_nw, s_blk);
+                own_shape<2>(give_hi, give_ylo, give_yhi, give_pres, s_lut, giver, mode, n_givers, s_nm, s_nw, s_blk);
+                own_shape<3>(give_hi, give_ylo, give_yhi, give_pres, s_lut, giver, mode, n_givers, s_nm, s_nw, s_blk);
                 acc.add_sums(s_nm, s_nw, s_blk, m, give_mover == 0);      // the leaf parents' mover is the OTHER player
             }
         }
@@ -930,22 +936,25 @@ int run_perft(Call &call, const uint4 *roots, const uint64_t *mult, size_t n_roo
                 int per_sm = 0;
                 const size_t smem = kTileWarps * tile_warp_bytes(rem);
                 const bool fast = one_side && small_mult && !option(OPT_PERFT_TILE_GENERIC);
-                // Own lists (k_perft_tile<., true>) pay in the widest part of the game, where the nodes that give the leaf
-                // parents hold at most 5 pieces: every lane gives in nearly every iteration and the lists of a shape are
-                // about equally long, so the loops run to the LONGEST list of the warp (shorter ones idle) and nothing is
-                // left for the dealt stage.  From the empty board (scripts/perft_own_lanes.py): perft(6) 1.28 -> 0.82 ms,
-                // perft(7) 24.8 -> 23.3 ms, perft(8) 532 -> 558 ms (not used there: the givers hold 6 pieces).  Running to
-                // the shortest list instead leaves most children to the dealt stage (0.93 / 24.8 / 546 ms).
-                // "perft_own_lanes": 33 never | n: always, from n giving lanes on | 64 + n: ... and to the longest list.
+                // Own lists (k_perft_tile<., true>) pay in the widest part of the game, where every lane gives in nearly every
+                // iteration and the lists of a shape are about equally long.  Givers with at most 4 pieces: the loops run to
+                // the LONGEST list of the warp (shorter ones idle) and nothing is left for the dealt stage; with 5 pieces: to
+                // the MEAN length, the excess is dealt; beyond: not used.  From the empty board, never / longest / mean
+                // (scripts/perft_own_lanes.py): perft(6) 1.28 / 0.83 / 0.87 ms, perft(7) 24.9 / 24.1 / 23.0 ms, perft(8)
+                // 533 / 583 / 532 ms, the depth-4 classes + 6 plies 181 / 254 / 202 ms.
+                // "perft_own_lanes": 33 never | n: always, from n giving lanes on, to the shortest list | 64 + n: ... to the
+                // longest | 128 + n: ... to the mean length.
                 const long long own_opt = option(OPT_PERFT_OWN_LANES);
-                const bool own = own_opt == 0 ? (int)head.max_pieces + depth <= 7 : own_opt != 33;
+                const int target_pieces_own = (int)head.max_pieces + depth;
+                const bool own = own_opt == 0 ? target_pieces_own <= 7 : own_opt != 33;
+                const unsigned own_arg = own_opt > 0 ? (unsigned)own_opt : (target_pieces_own <= 6 ? 64u : 128u) + kTileOwnLanes;
                 typedef void (*TileFn)(const uint4 *, const u64 *, u64, int, int, int, u64 *, u64 *, unsigned);
                 const TileFn tile = fast ? (own ? (TileFn)k_perft_tile<true, true> : (TileFn)k_perft_tile<true, false>)
                                          : (own ? (TileFn)k_perft_tile<false, true> : (TileFn)k_perft_tile<false, false>);
                 QK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tile, kTileWarps * 32, smem));
                 tile<<<c->sms * (per_sm > 0 ? per_sm : 1), kTileWarps * 32, smem, s>>>(cur_s, cur_m, n_cur, d, depth,
                                                                                      (root_parity + d) & 1, d_next, d_ctr,
-                                                                                     own_opt > 0 ? (unsigned)own_opt : 64u + kTileOwnLanes);
+                                                                                     own_arg);
             } else if (use_lane) {
                 int per_sm = 0;
                 QK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_perft_lane, kLaneWarps * 32, 0));

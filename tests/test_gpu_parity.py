@@ -423,11 +423,11 @@ def test_perft_lane_kernel_matches_warp_kernel_and_oracle(options):
     mult = np.arange(1, 65, dtype=np.uint64)
     mid = O.make_roots(3000, seed=17, min_plies=4, span=5)
     ref6 = None
-    for mode in ("tile", "tile-generic", "tile-dealt-only", "tile-own-lists", "tile-own-longest", "warp", "lane", "tile-small"):
+    for mode in ("tile", "tile-generic", "tile-dealt-only", "tile-own-lists", "tile-own-longest", "tile-own-mean", "warp", "lane", "tile-small"):
         options("perft_kernel", {"tile": 1, "lane": 2, "warp": 3}[mode[:4]])
         # leaf parents: everything through the dealt stage / lanes evaluate children of their own as soon as one lane
-        # of the warp gives, as many as the shortest or as the longest list of the warp (default: wide trees only)
-        options("perft_own_lanes", {"tile-dealt-only": 33, "tile-own-lists": 1, "tile-own-longest": 65}.get(mode, 0))
+        # of the warp gives, as many as the shortest / longest / mean list of the warp (default: wide trees only)
+        options("perft_own_lanes", {"tile-dealt-only": 33, "tile-own-lists": 1, "tile-own-longest": 65, "tile-own-mean": 129}.get(mode, 0))
         # tile-generic: 64-bit multiplicities / mixed sides-to-move form, on inputs that allow the fast one
         options("perft_tile_generic", 1 if mode == "tile-generic" else 0)
         if mode == "tile-small":        # the depth-first kernel straight on the 64 mixed-parity roots: every frame depth

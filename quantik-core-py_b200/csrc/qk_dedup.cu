@@ -129,7 +129,7 @@ __device__ __forceinline__ TSlot load_entry(const TSlot *table, size_t i)
 
 // table -> dense output.  A block takes runs of kBlock x kCompactItems slots, counts the run's entries and reserves
 // their place with ONE atomic.  (One reservation per warp made the single cursor the bottleneck -- 2.6 M atomics on
-// one address for the largest BFS level: 5.1 ms for a 2.6 GB table that is read in 0.5 ms.)  `slots` is a
+// one address for the largest BFS level: 5.1 ms for a 4.8 GB table that is read in 0.85 ms.)  `slots` is a
 // multiple of 256.  EMIT: straight into the caller's payload / multiplicity arrays (unsorted output), else into
 // the (key, multiplicity) arrays the sort works on.
 static constexpr int kCompactItems = 4;
@@ -470,7 +470,7 @@ __global__ void __launch_bounds__(kBlock) k_bucket_states(const uint4 *__restric
         b.counts[(size_t)k * b.blocks + blockIdx.x] = s_cur[k] < b.sub_cap ? s_cur[k] : b.sub_cap;
 }
 
-// ---- the BFS level in two-level form (k_bfs_expand_insert's table is DRAM-sized at the large levels -- 2.6 GB for 55 M
+// ---- the BFS level in two-level form (k_bfs_expand_insert's table is DRAM-sized at the large levels -- 4.8 GB for 55 M
 // classes -- and every child is a random DRAM sector there: 3.7 x 10^10 random reads per second on this machine,
 // profiles/r02n_atomics_sweep.txt, against 2 x 10^11 on an L2-resident table).  Same plan as the dedup above: a
 // count pass (how many children each block of parents will emit: the sub-bucket ranges are sized from it), the

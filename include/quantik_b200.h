@@ -85,7 +85,7 @@ QK_API const char *qk_last_error(void);
  *                         5 / 6 resident CTAs per SM instead of 4 | 1 / 6 the older single-root kernels
  *   "dedup_mode"          0 auto | 1 one-level table insert | 2 partitioned (two-level) insert
  *   "dedup_part_mb"       > 0: size in MiB of the table one part of the two-level insert is merged in (0 = 112)
- *   "dedup_streams"       1..4: part tables in use at a time, each on its own stream (0 = 2)
+ *   "dedup_streams"       1..4: part tables in use at a time, each on its own stream (0 = 3)
  *   "table_slots_x10"     >= 11: slots of the one-level merge table per expected class, times ten (0 = 15)
  *   "guided_scoring"      0 children dealt out over the warp | 1 every lane scores its own children
  *   "call_stage"          1: host buffers and scratch of small calls go through the memory pool like large ones, not

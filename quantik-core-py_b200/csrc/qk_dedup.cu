@@ -814,14 +814,15 @@ static int merge_streams(Ctx *c, int n_aux)
 static int dedup_streams()
 {
     const long long v = option(OPT_DEDUP_STREAMS);
-    return v <= 0 ? 2 : (v > Ctx::kAux + 1 ? Ctx::kAux + 1 : (int)v);
+    return v <= 0 ? 3 : (v > Ctx::kAux + 1 ? Ctx::kAux + 1 : (int)v);
 }
 
 // pass B for every part + the tail.  meta = n_unique, all-ones mult, cursor, overflow (as DedupTable::meta).
 // One part's kernels are short (about 75 + 19 us at 2^24 keys, a fifth of it ramp-up and tail), so `streams` parts
 // are in flight at a time, each in its own full-size table on its own stream: part k + 1 starts on the SMs that part
 // k's tail and drain leave idle.  An insert kernel fills the machine, so the parts mostly run one after the other and
-// the L2 holds the table that is being filled.  Measured (2^24 keys, whole call): one stream 1.15 ms, two 1.07 ms;
+// the L2 holds the table that is being filled.  Measured (2^24 keys, whole call): one stream 1.15 ms, two 1.07 ms, three 1.04 ms
+// (the default);
 // splitting the L2 between the tables instead (2 x 48 MiB: 1.31 ms, 4 x 24 MiB: 1.55 ms) loses -- twice the parts,
 // twice the launches.  The parts are independent -- different keys, different tables; they share only the append
 // cursor and the counters, which are atomics.
